@@ -1,0 +1,125 @@
+/*
+ * rgp_psi.h - C ABI of librgp_psi.so: RBF-ARD psi-statistics under Gaussian q(X) and
+ * their gradients, fp64, hand-written CUDA for sm_100a (B200).
+ *
+ * This is the drop-in boundary for the ONE hot path of zhenwendai/RGP.  The reference
+ * reaches the path through GPy's RBF kernel (a `psicomp` plugin object); each entry
+ * point below cites the reference interface it stands behind.  GPy itself is a
+ * third-party dependency that is not part of /root/reference.
+ *
+ *   forward  : GPy  PSICOMP_RBF.psicomputations(kern, Z, variational_posterior)
+ *              <- kern.psi0/psi1/psi2(Z, X)   autoreg/inference/vardtc.py:59-61
+ *                                             autoreg/inference/svi_vardtc.py:48-50
+ *   backward : GPy  PSICOMP_RBF.psiDerivativecomputations(kern, dL_dpsi0, dL_dpsi1,
+ *                                                         dL_dpsi2, Z, variational_posterior)
+ *              <- kern.update_gradients_expectations   autoreg/layers.py:98-102
+ *                 kern.gradients_Z_expectations         autoreg/layers.py:127-132
+ *                 kern.gradients_qX_expectations        autoreg/layers.py:574-580
+ *
+ * Conventions
+ *   - all matrices row-major (C order) fp64:  mu,S [N,Q]  Z [M,Q]  ell [Q]
+ *     psi1, dL_dpsi1 [N,M]   psi2, dL_dpsi2 [M,M]   dmu,dS [N,Q]  dZ [M,Q]  dell [Q]
+ *   - `ell` always has Q entries (a non-ARD kernel passes its single lengthscale
+ *     replicated; the host wrapper sums dell back to a scalar as GPy does).
+ *   - `*_dev` entry points take DEVICE pointers and enqueue on `stream`
+ *     (a cudaStream_t passed as void*; NULL = legacy default stream) without
+ *     synchronising; `*_host` entry points take HOST pointers, copy in, run, copy
+ *     out and synchronise before returning.
+ *   - every function returns 0 on success or a negative rgp_psi_status; the message
+ *     is available from rgp_psi_last_error() (thread local).  Nothing aborts.
+ *   - a handle is bound to one device and may be used from one thread at a time;
+ *     handles are independent (no hidden globals), one per (process, GPU).
+ *   - there is NO CPU fallback: without a CUDA device rgp_psi_create fails.
+ */
+#ifndef RGP_PSI_H_
+#define RGP_PSI_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RGP_PSI_ABI_VERSION 1
+
+typedef struct rgp_psi_ctx* rgp_psi_handle_t;
+
+typedef enum {
+  RGP_PSI_OK = 0,
+  RGP_PSI_ERR_INVALID = -1,   /* bad argument (null pointer, non-positive size, ...) */
+  RGP_PSI_ERR_CUDA = -2,      /* a CUDA runtime call or kernel launch failed */
+  RGP_PSI_ERR_NOMEM = -3,     /* device or pinned-host allocation failed */
+  RGP_PSI_ERR_NODEVICE = -4   /* no usable sm_100 device */
+} rgp_psi_status;
+
+/* Which kernels serve a call.  AUTO picks FAST when the shape is supported
+ * (Q <= 64) and REFERENCE otherwise.  REFERENCE = the simple one-thread-per-output
+ * kernels kept as an on-device cross-check. */
+typedef enum { RGP_PSI_IMPL_AUTO = 0, RGP_PSI_IMPL_FAST = 1, RGP_PSI_IMPL_REFERENCE = 2 } rgp_psi_impl;
+
+int rgp_psi_abi_version(void);
+const char* rgp_psi_last_error(void);
+
+/* Handle lifetime.  `device` is a CUDA ordinal. */
+int rgp_psi_create(int device, rgp_psi_handle_t* out);
+int rgp_psi_destroy(rgp_psi_handle_t h);
+
+/* Options: "impl" (rgp_psi_impl), "row_chunk" (rows per internal pass, 0 = auto),
+ * "profile" (1 = record a CUDA-event pair around every kernel launch). */
+int rgp_psi_set_option(rgp_psi_handle_t h, const char* key, int64_t value);
+
+/* ---- forward: Psi0 (optional N-vector), Psi1 (optional), Psi2 -------------------
+ * Replaces psicomputations().  psi0_out / psi1_out may be NULL to skip them;
+ * psi2_out must hold M*M doubles.  Psi0[n] = variance (the caller sums it,
+ * vardtc.py:68). */
+int rgp_psi_forward_dev(rgp_psi_handle_t h, void* stream, int64_t N, int M, int Q,
+                        const double* mu, const double* S, const double* Z,
+                        const double* ell, double variance,
+                        double* psi0_out, double* psi1_out, double* psi2_out);
+
+/* ---- backward: all five gradient blocks --------------------------------------
+ * Replaces psiDerivativecomputations().  dL_dpsi0 may be NULL, in which case every
+ * row uses dL_dpsi0_const (vardtc.py:175 passes a constant vector).  dL_dpsi1 may be
+ * NULL (treated as zero).  dL_dpsi2 is symmetrised internally as GPy does.
+ * Outputs: dmu,dS [N,Q], dZ [M,Q], dell [Q], dvar [1]; all overwritten. */
+int rgp_psi_backward_dev(rgp_psi_handle_t h, void* stream, int64_t N, int M, int Q,
+                         const double* mu, const double* S, const double* Z,
+                         const double* ell, double variance,
+                         const double* dL_dpsi0, double dL_dpsi0_const,
+                         const double* dL_dpsi1, const double* dL_dpsi2,
+                         double* dmu_out, double* dS_out, double* dZ_out,
+                         double* dell_out, double* dvar_out);
+
+/* ---- host-buffer convenience wrappers (the numpy-in / numpy-out plugin path) ---- */
+int rgp_psi_forward_host(rgp_psi_handle_t h, int64_t N, int M, int Q,
+                         const double* mu, const double* S, const double* Z,
+                         const double* ell, double variance,
+                         double* psi0_out, double* psi1_out, double* psi2_out);
+int rgp_psi_backward_host(rgp_psi_handle_t h, int64_t N, int M, int Q,
+                          const double* mu, const double* S, const double* Z,
+                          const double* ell, double variance,
+                          const double* dL_dpsi0, double dL_dpsi0_const,
+                          const double* dL_dpsi1, const double* dL_dpsi2,
+                          double* dmu_out, double* dS_out, double* dZ_out,
+                          double* dell_out, double* dvar_out);
+
+/* ---- measurement support ------------------------------------------------------- */
+/* Kernel launches issued through this handle since creation (or the last reset). */
+int64_t rgp_psi_launch_count(rgp_psi_handle_t h);
+int rgp_psi_reset_counters(rgp_psi_handle_t h);
+/* With option "profile"=1: per-kernel accumulated device time since the last reset.
+ * Fills up to `cap` entries; names are static strings.  Synchronises the device.
+ * Returns the number of distinct kernels (may exceed cap) or a negative status. */
+int rgp_psi_kernel_times(rgp_psi_handle_t h, int cap, const char** names,
+                         double* total_ms, int64_t* launches);
+/* DFMA-chain microbenchmark: achieved fp64 FMA throughput of this GPU in TFLOP/s
+ * (2 flop per FMA), best of `reps` launches.  The roofline denominator. */
+int rgp_psi_fp64_peak(rgp_psi_handle_t h, void* stream, int reps, double* tflops_out);
+/* Device workspace currently held by the handle, in bytes. */
+int64_t rgp_psi_workspace_bytes(rgp_psi_handle_t h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RGP_PSI_H_ */

@@ -1,0 +1,226 @@
+// microbench.cu - standalone hardware probes that shape the kernel design (run on the
+// GPU box; results are summarised in profiles/).  Not part of librgp_psi.so.
+//   1. DFMA-chain peak (the fp64 roofline denominator) at several occupancies
+//   2. DMMA (mma.sync m8n8k4 f64) peak, alone and interleaved with DFMA
+//   3. LDS.128 cost versus number of distinct addresses per warp (broadcast merging)
+//   4. exp throughput: library exp() versus rgp::exp_neg()
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+
+#define CK(x)                                                                     \
+  do {                                                                            \
+    cudaError_t e = (x);                                                          \
+    if (e != cudaSuccess) {                                                       \
+      printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); \
+      exit(1);                                                                    \
+    }                                                                             \
+  } while (0)
+
+template <int CH>
+__global__ void __launch_bounds__(256) k_dfma(int outer, double* out) {
+  double a[CH];
+#pragma unroll
+  for (int i = 0; i < CH; ++i) a[i] = 0.5 + 1e-3 * (threadIdx.x + i);
+  const double m = 0.999999, c = 1e-7;
+  for (int o = 0; o < outer; ++o)
+#pragma unroll 4
+    for (int k = 0; k < 256; ++k)
+#pragma unroll
+      for (int i = 0; i < CH; ++i) a[i] = fma(a[i], m, c);
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < CH; ++i) s += a[i];
+  if (s == 123.456) out[0] = s;
+}
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+// MODE 0: DMMA only; 1: DMMA + DFMA interleaved (per 1 DMMA, NF DFMAs)
+template <int MODE, int NF>
+__global__ void __launch_bounds__(256) k_dmma(int outer, double* out) {
+  double c[8][2];
+  double f[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    c[i][0] = 0.0;
+    c[i][1] = 0.0;
+    f[i] = 0.5 + i;
+  }
+  double a = 1e-3 * threadIdx.x, b = 1.0 + 1e-4 * threadIdx.x;
+  const double m = 0.999999, cc = 1e-7;
+  for (int o = 0; o < outer; ++o) {
+#pragma unroll 2
+    for (int k = 0; k < 64; ++k) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        dmma884(c[i][0], c[i][1], a, b);
+        if (MODE == 1) {
+#pragma unroll
+          for (int j = 0; j < NF; ++j) f[(i + j) & 7] = fma(f[(i + j) & 7], m, cc);
+        }
+      }
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1] + f[i];
+  if (s == 123.456) out[0] = s;
+}
+
+// LDS.128 probe: every lane loads double2 at smem[(pattern(lane)) * stride]; NLD loads per
+// iteration into independent registers, summed afterwards.
+__global__ void __launch_bounds__(1024) k_lds(int iters, int distinct, int stride_d2, double* out,
+                                              long long* cycles) {
+  extern __shared__ double2 sm2[];
+  for (int i = threadIdx.x; i < 4096; i += blockDim.x) sm2[i] = make_double2(i, -i);
+  __syncthreads();
+  int lane = threadIdx.x & 31;
+  int idx;
+  if (distinct >= 32) idx = lane;                 // all distinct, contiguous
+  else if (distinct == 8) idx = lane & 7;         // 8 distinct, each quarter-warp sees all 8
+  else if (distinct == 4) idx = lane >> 3;        // one address per quarter-warp
+  else if (distinct == 2) idx = lane >> 4;
+  else idx = 0;                                   // full broadcast
+  const double2* p = sm2 + idx * stride_d2;
+  double2 acc = make_double2(0, 0);
+  long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      double2 v;
+      unsigned addr = (unsigned)__cvta_generic_to_shared(p + j * 64);
+      asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+      acc.x += v.x;
+      acc.y += v.y;
+    }
+  }
+  long long t1 = clock64();
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+  if (acc.x == 123.456) out[0] = acc.y;
+}
+
+template <int WHICH>
+__global__ void __launch_bounds__(256) k_exp(int outer, double* out) {
+  double x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = -1e-3 * (threadIdx.x + 1) - i;
+  double s = 0;
+  for (int o = 0; o < outer; ++o) {
+#pragma unroll 4
+    for (int k = 0; k < 64; ++k) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        double e = WHICH == 0 ? exp(x[i]) : rgp::exp_neg(x[i]);
+        s += e;
+        x[i] = x[i] * 0.999 - 1e-4;
+      }
+    }
+  }
+  if (s == 123.456) out[0] = s;
+}
+
+template <typename F>
+static float time_ms(F f, int reps = 5) {
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  f();
+  CK(cudaDeviceSynchronize());
+  float best = 1e30f;
+  for (int r = 0; r < reps; ++r) {
+    CK(cudaEventRecord(e0));
+    f();
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms < best) best = ms;
+  }
+  CK(cudaGetLastError());
+  return best;
+}
+
+int main() {
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, 0));
+  int sms = prop.multiProcessorCount;
+  printf("{\"device\": \"%s\", \"sms\": %d, \"clock_khz\": %d}\n", prop.name, sms, prop.clockRate);
+  double* out;
+  CK(cudaMalloc(&out, 1024));
+  long long* cyc;
+  CK(cudaMalloc(&cyc, sizeof(long long) * 1024));
+
+  // 1. DFMA peak vs chains / occupancy
+  {
+    const int outer = 64;
+    for (int bps : {1, 2, 4, 8}) {
+      int blocks = sms * bps;
+      float ms8 = time_ms([&] { k_dfma<8><<<blocks, 256>>>(outer, out); });
+      float ms16 = time_ms([&] { k_dfma<16><<<blocks, 256>>>(outer, out); });
+      double f8 = 2.0 * blocks * 256.0 * outer * 256 * 8, f16 = 2.0 * blocks * 256.0 * outer * 256 * 16;
+      printf("{\"probe\": \"dfma\", \"blocks_per_sm\": %d, \"tflops_ch8\": %.3f, \"tflops_ch16\": %.3f}\n",
+             bps, f8 / ms8 / 1e9, f16 / ms16 / 1e9);
+    }
+    // sustained: ~2 s of back-to-back launches
+    int blocks = sms * 8;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0));
+    int n = 200;
+    for (int i = 0; i < n; ++i) k_dfma<16><<<blocks, 256>>>(64, out);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    printf("{\"probe\": \"dfma_sustained\", \"seconds\": %.3f, \"tflops\": %.3f}\n", ms / 1e3,
+           2.0 * blocks * 256.0 * 64 * 256 * 16 * n / ms / 1e9);
+  }
+  // 2. DMMA
+  {
+    const int outer = 32;
+    int blocks = sms * 8;
+    double mma_flops = 2.0 * 256.0 * (double)blocks * (256 / 32) * outer * 64 * 8;  // 256 FMA / warp-instr
+    float ms = time_ms([&] { k_dmma<0, 0><<<blocks, 256>>>(outer, out); });
+    printf("{\"probe\": \"dmma884\", \"tflops\": %.3f}\n", mma_flops / ms / 1e9);
+    float ms4 = time_ms([&] { k_dmma<1, 4><<<blocks, 256>>>(outer, out); });
+    double fma4 = 2.0 * blocks * 256.0 * outer * 64 * 8 * 4;
+    printf("{\"probe\": \"dmma884+4dfma\", \"tflops_total\": %.3f, \"tflops_mma\": %.3f, \"tflops_fma\": %.3f}\n",
+           (mma_flops + fma4) / ms4 / 1e9, mma_flops / ms4 / 1e9, fma4 / ms4 / 1e9);
+    float ms8 = time_ms([&] { k_dmma<1, 8><<<blocks, 256>>>(outer, out); });
+    double fma8 = 2.0 * blocks * 256.0 * outer * 64 * 8 * 8;
+    printf("{\"probe\": \"dmma884+8dfma\", \"tflops_total\": %.3f, \"tflops_mma\": %.3f, \"tflops_fma\": %.3f}\n",
+           (mma_flops + fma8) / ms8 / 1e9, mma_flops / ms8 / 1e9, fma8 / ms8 / 1e9);
+  }
+  // 3. LDS.128 vs distinct addresses
+  {
+    CK(cudaFuncSetAttribute(k_lds, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    for (int warps : {1, 4, 16, 32}) {
+      for (int distinct : {1, 2, 4, 8, 32}) {
+        int iters = 2000;
+        k_lds<<<1, warps * 32, 65536>>>(iters, distinct, 1, out, cyc);
+        CK(cudaDeviceSynchronize());
+        long long c;
+        CK(cudaMemcpy(&c, cyc, sizeof(c), cudaMemcpyDeviceToHost));
+        printf("{\"probe\": \"lds128\", \"warps\": %d, \"distinct\": %d, \"cycles_per_lds_per_sm\": %.3f}\n",
+               warps, distinct, (double)c / (iters * 16.0 * warps));
+      }
+    }
+  }
+  // 4. exp
+  {
+    int blocks = sms * 8, outer = 16;
+    double n = (double)blocks * 256 * outer * 64 * 8;
+    float m0 = time_ms([&] { k_exp<0><<<blocks, 256>>>(outer, out); });
+    float m1 = time_ms([&] { k_exp<1><<<blocks, 256>>>(outer, out); });
+    printf("{\"probe\": \"exp\", \"lib_Gexp_s\": %.2f, \"exp_neg_Gexp_s\": %.2f}\n", n / m0 / 1e6, n / m1 / 1e6);
+  }
+  return 0;
+}

@@ -1,0 +1,398 @@
+// rgp_psi.cu - C ABI of librgp_psi.so (see include/rgp_psi.h for the contract and the
+// reference interfaces each entry point replaces).
+#include <stdarg.h>
+
+#include <algorithm>
+#include <new>
+
+#include "context.cuh"
+#include "common.cuh"
+#include "ref_kernels.cuh"
+#include "fast_path.cuh"
+#include "fp64_peak.cuh"
+
+namespace rgp {
+
+thread_local char g_last_error[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+static int check_common(rgp_psi_ctx* h, int64_t N, int M, int Q, const void* mu, const void* S,
+                        const void* Z, const void* ell, double variance) {
+  if (!h) return set_error(RGP_PSI_ERR_INVALID, "null handle");
+  if (N <= 0 || M <= 0 || Q <= 0)
+    return set_error(RGP_PSI_ERR_INVALID, "N, M, Q must be positive (got %lld, %d, %d)",
+                     (long long)N, M, Q);
+  if (!mu || !S || !Z || !ell) return set_error(RGP_PSI_ERR_INVALID, "null input pointer");
+  if (!(variance > 0.0)) return set_error(RGP_PSI_ERR_INVALID, "variance must be positive");
+  if ((int64_t)M * M > (int64_t)1 << 30)
+    return set_error(RGP_PSI_ERR_INVALID, "M = %d too large", M);
+  return 0;
+}
+
+static bool use_fast(const rgp_psi_ctx* h, int M, int Q) {
+  if (h->impl == RGP_PSI_IMPL_REFERENCE) return false;
+  return fast::supported(M, Q);
+}
+
+// ------------------------------------------------------------------ reference path
+namespace refdrv {
+
+static int64_t pick_chunk(const rgp_psi_ctx* h, int64_t N, int M, int Q) {
+  if (h->row_chunk > 0) return std::min<int64_t>(N, h->row_chunk);
+  // keep the per-chunk workspace (L1: chunk*M, dinv: chunk*Q) under ~1 GiB
+  int64_t per_row = 8ll * (M + Q + 2);
+  int64_t c = ((int64_t)1 << 30) / per_row;
+  return std::max<int64_t>(1, std::min<int64_t>(N, c));
+}
+
+static int psi2_splits(const rgp_psi_ctx* h, int64_t rows, int M) {
+  int tiles = ceil_div(M, 16) * ceil_div(M, 16);
+  int64_t want = std::max<int64_t>(1, (int64_t)h->sm_count * 16 / tiles);
+  return (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(rows, want), 65535));
+}
+
+static int forward(rgp_psi_ctx* h, cudaStream_t st, int64_t N, int M, int Q, const double* mu,
+                   const double* S, const double* Z, const double* ell, double variance,
+                   double* psi0, double* psi1, double* psi2) {
+  const int64_t rc = pick_chunk(h, N, M, Q);
+  size_t need = bump_size(rc, 8) * 2 + bump_size(rc * Q, 8) + bump_size((size_t)M * M, 8);
+  RGP_TRY(arena_reserve(&h->ws, &h->ws_bytes, need));
+  Bump b(h->ws, h->ws_bytes);
+  double* c1 = b.take<double>(rc);
+  double* c2 = b.take<double>(rc);
+  double* dinv = b.take<double>(rc * Q);
+  double* zz = b.take<double>((size_t)M * M);
+  RGP_LAUNCH(h, st, "ref_pair_terms", ref::pair_terms, ceil_div((int64_t)M * M, 256), 256, 0, M, Q,
+             Z, ell, (const double*)nullptr, zz, (double*)nullptr);
+  RGP_CUDA(cudaMemsetAsync(psi2, 0, sizeof(double) * M * M, st));
+  if (psi0) RGP_LAUNCH(h, st, "ref_fill", ref::fill, ceil_div(N, 256), 256, 0, N, variance, psi0);
+  for (int64_t s = 0; s < N; s += rc) {
+    int64_t r = std::min(rc, N - s);
+    const double* mu_c = mu + s * Q;
+    const double* S_c = S + s * Q;
+    RGP_LAUNCH(h, st, "ref_row_terms", ref::row_terms, ceil_div(r, 128), 128, 0, r, Q, S_c, ell, c1,
+               c2, dinv);
+    if (psi1)
+      RGP_LAUNCH(h, st, "ref_psi1", ref::psi1, ceil_div(r * M, 256), 256, 0, r, M, Q, mu_c, S_c, Z,
+                 ell, c1, variance, (const double*)nullptr, psi1 + s * M);
+    dim3 grid(ceil_div(M, 16), ceil_div(M, 16), psi2_splits(h, r, M));
+    RGP_LAUNCH(h, st, "ref_psi2", ref::psi2, grid, dim3(16, 16), 0, r, M, Q, mu_c, Z, c2, dinv, zz,
+               variance, psi2);
+  }
+  return 0;
+}
+
+static int backward(rgp_psi_ctx* h, cudaStream_t st, int64_t N, int M, int Q, const double* mu,
+                    const double* S, const double* Z, const double* ell, double variance,
+                    const double* dL0, double dL0c, const double* dL1, const double* dL2,
+                    double* dmu, double* dS, double* dZ, double* dell, double* dvar) {
+  if (Q > 128)
+    return set_error(RGP_PSI_ERR_INVALID, "reference backward supports Q <= 128 (got %d)", Q);
+  const int64_t rc = pick_chunk(h, N, M, Q);
+  size_t need = bump_size(rc, 8) * 2 + bump_size(rc * Q, 8) + bump_size((size_t)M * M, 8) * 3 +
+                bump_size(rc * M, 8);
+  RGP_TRY(arena_reserve(&h->ws, &h->ws_bytes, need));
+  Bump b(h->ws, h->ws_bytes);
+  double* c1 = b.take<double>(rc);
+  double* c2 = b.take<double>(rc);
+  double* dinv = b.take<double>(rc * Q);
+  double* zz = b.take<double>((size_t)M * M);
+  double* dLs = b.take<double>((size_t)M * M);
+  double* p2 = b.take<double>((size_t)M * M);
+  double* L1 = b.take<double>(rc * M);
+
+  RGP_CUDA(cudaMemsetAsync(dmu, 0, sizeof(double) * N * Q, st));
+  RGP_CUDA(cudaMemsetAsync(dS, 0, sizeof(double) * N * Q, st));
+  RGP_CUDA(cudaMemsetAsync(dZ, 0, sizeof(double) * M * Q, st));
+  RGP_CUDA(cudaMemsetAsync(dell, 0, sizeof(double) * Q, st));
+  RGP_CUDA(cudaMemsetAsync(p2, 0, sizeof(double) * M * M, st));
+  if (dL0) {
+    RGP_CUDA(cudaMemsetAsync(dvar, 0, sizeof(double), st));
+    RGP_LAUNCH(h, st, "ref_sum_dL0", ref::sum_to, std::min(1024, ceil_div(N, 256)), 256, 0, N, dL0,
+               dvar);
+  } else {
+    RGP_LAUNCH(h, st, "ref_fill", ref::fill, 1, 32, 0, (int64_t)1, dL0c * (double)N, dvar);
+  }
+  RGP_LAUNCH(h, st, "ref_pair_terms", ref::pair_terms, ceil_div((int64_t)M * M, 256), 256, 0, M, Q,
+             Z, ell, dL2, zz, dLs);
+  for (int64_t s = 0; s < N; s += rc) {
+    int64_t r = std::min(rc, N - s);
+    const double* mu_c = mu + s * Q;
+    const double* S_c = S + s * Q;
+    RGP_LAUNCH(h, st, "ref_row_terms", ref::row_terms, ceil_div(r, 128), 128, 0, r, Q, S_c, ell, c1,
+               c2, dinv);
+    if (dL1) {
+      RGP_LAUNCH(h, st, "ref_psi1", ref::psi1, ceil_div(r * M, 256), 256, 0, r, M, Q, mu_c, S_c, Z,
+                 ell, c1, variance, dL1 + s * M, L1);
+      RGP_LAUNCH(h, st, "ref_psi1_bwd_rows", ref::psi1_bwd_rows, ceil_div(r * Q, 128), 128, 0, r, M,
+                 Q, mu_c, S_c, Z, ell, L1, variance, dmu + s * Q, dS + s * Q, dell, dvar);
+      dim3 gz(ceil_div((int64_t)M * Q, 128), (unsigned)std::max<int64_t>(1, std::min<int64_t>(r / 64, 64)));
+      RGP_LAUNCH(h, st, "ref_psi1_bwd_Z", ref::psi1_bwd_Z, gz, 128, 0, r, M, Q, mu_c, S_c, Z, ell, L1,
+                 dZ);
+    }
+    dim3 grid(ceil_div(M, 16), ceil_div(M, 16), psi2_splits(h, r, M));
+    RGP_LAUNCH(h, st, "ref_psi2", ref::psi2, grid, dim3(16, 16), 0, r, M, Q, mu_c, Z, c2, dinv, zz,
+               variance, p2);
+    int rows_grid = (int)std::min<int64_t>(r, (int64_t)h->sm_count * 8);
+    size_t smem = sizeof(double) * (1 + 3 * (size_t)Q);
+    RGP_LAUNCH(h, st, "ref_psi2_bwd_rows", (ref::psi2_bwd_rows<128>), rows_grid, 128, smem, r, M, Q,
+               mu_c, S_c, Z, ell, c2, dinv, zz, dLs, variance, dmu + s * Q, dS + s * Q, dZ, dell,
+               dvar);
+  }
+  RGP_LAUNCH(h, st, "ref_psi2_bwd_tails", ref::psi2_bwd_tails, ceil_div((int64_t)M * Q, 128), 128, 0,
+             M, Q, Z, ell, dLs, p2, dZ, dell);
+  return 0;
+}
+
+}  // namespace refdrv
+}  // namespace rgp
+
+using namespace rgp;
+
+extern "C" {
+
+int rgp_psi_abi_version(void) { return RGP_PSI_ABI_VERSION; }
+const char* rgp_psi_last_error(void) { return g_last_error; }
+
+int rgp_psi_create(int device, rgp_psi_handle_t* out) {
+  if (!out) return set_error(RGP_PSI_ERR_INVALID, "null out pointer");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0) {
+    cudaGetLastError();
+    return set_error(RGP_PSI_ERR_NODEVICE,
+                     "no CUDA device available (%s); librgp_psi has no CPU fallback",
+                     e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  }
+  if (device < 0 || device >= count)
+    return set_error(RGP_PSI_ERR_INVALID, "device %d out of range [0,%d)", device, count);
+  cudaDeviceProp prop;
+  RGP_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return set_error(RGP_PSI_ERR_NODEVICE,
+                     "device %d is sm_%d%d; this library carries sm_100a code only", device,
+                     prop.major, prop.minor);
+  RGP_CUDA(cudaSetDevice(device));
+  rgp_psi_ctx* h = new (std::nothrow) rgp_psi_ctx();
+  if (!h) return set_error(RGP_PSI_ERR_NOMEM, "host allocation failed");
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  int s = fast::init(h);
+  if (s != 0) {
+    delete h;
+    return s;
+  }
+  *out = h;
+  return 0;
+}
+
+int rgp_psi_destroy(rgp_psi_handle_t h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (auto& p : h->pending) {
+    cudaEventDestroy(p.start);
+    cudaEventDestroy(p.stop);
+  }
+  for (auto e : h->event_pool) cudaEventDestroy(e);
+  if (h->ws) cudaFree(h->ws);
+  if (h->io) cudaFree(h->io);
+  delete h;
+  return 0;
+}
+
+int rgp_psi_set_option(rgp_psi_handle_t h, const char* key, int64_t value) {
+  if (!h || !key) return set_error(RGP_PSI_ERR_INVALID, "null handle or key");
+  if (!strcmp(key, "impl")) {
+    if (value < 0 || value > 2) return set_error(RGP_PSI_ERR_INVALID, "impl must be 0, 1 or 2");
+    h->impl = (int)value;
+  } else if (!strcmp(key, "row_chunk")) {
+    if (value < 0) return set_error(RGP_PSI_ERR_INVALID, "row_chunk must be >= 0");
+    h->row_chunk = value;
+  } else if (!strcmp(key, "profile")) {
+    h->profile = value != 0;
+  } else {
+    return set_error(RGP_PSI_ERR_INVALID, "unknown option '%s'", key);
+  }
+  return 0;
+}
+
+int rgp_psi_forward_dev(rgp_psi_handle_t h, void* stream, int64_t N, int M, int Q, const double* mu,
+                        const double* S, const double* Z, const double* ell, double variance,
+                        double* psi0_out, double* psi1_out, double* psi2_out) {
+  RGP_TRY(check_common(h, N, M, Q, mu, S, Z, ell, variance));
+  if (!psi2_out) return set_error(RGP_PSI_ERR_INVALID, "psi2_out must not be null");
+  RGP_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (h->impl == RGP_PSI_IMPL_FAST && !fast::supported(M, Q))
+    return set_error(RGP_PSI_ERR_INVALID, "fast path does not support M=%d Q=%d", M, Q);
+  if (use_fast(h, M, Q))
+    return fast::forward(h, st, N, M, Q, mu, S, Z, ell, variance, psi0_out, psi1_out, psi2_out);
+  return refdrv::forward(h, st, N, M, Q, mu, S, Z, ell, variance, psi0_out, psi1_out, psi2_out);
+}
+
+int rgp_psi_backward_dev(rgp_psi_handle_t h, void* stream, int64_t N, int M, int Q,
+                         const double* mu, const double* S, const double* Z, const double* ell,
+                         double variance, const double* dL_dpsi0, double dL_dpsi0_const,
+                         const double* dL_dpsi1, const double* dL_dpsi2, double* dmu_out,
+                         double* dS_out, double* dZ_out, double* dell_out, double* dvar_out) {
+  RGP_TRY(check_common(h, N, M, Q, mu, S, Z, ell, variance));
+  if (!dL_dpsi2 || !dmu_out || !dS_out || !dZ_out || !dell_out || !dvar_out)
+    return set_error(RGP_PSI_ERR_INVALID, "null dL_dpsi2 or output pointer");
+  RGP_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (h->impl == RGP_PSI_IMPL_FAST && !fast::supported(M, Q))
+    return set_error(RGP_PSI_ERR_INVALID, "fast path does not support M=%d Q=%d", M, Q);
+  if (use_fast(h, M, Q))
+    return fast::backward(h, st, N, M, Q, mu, S, Z, ell, variance, dL_dpsi0, dL_dpsi0_const,
+                          dL_dpsi1, dL_dpsi2, dmu_out, dS_out, dZ_out, dell_out, dvar_out);
+  return refdrv::backward(h, st, N, M, Q, mu, S, Z, ell, variance, dL_dpsi0, dL_dpsi0_const,
+                          dL_dpsi1, dL_dpsi2, dmu_out, dS_out, dZ_out, dell_out, dvar_out);
+}
+
+// ------------------------------------------------------------- host-buffer wrappers
+int rgp_psi_forward_host(rgp_psi_handle_t h, int64_t N, int M, int Q, const double* mu,
+                         const double* S, const double* Z, const double* ell, double variance,
+                         double* psi0_out, double* psi1_out, double* psi2_out) {
+  RGP_TRY(check_common(h, N, M, Q, mu, S, Z, ell, variance));
+  if (!psi2_out) return set_error(RGP_PSI_ERR_INVALID, "psi2_out must not be null");
+  RGP_CUDA(cudaSetDevice(h->device));
+  size_t nq = (size_t)N * Q, nm = (size_t)N * M, mq = (size_t)M * Q, mm = (size_t)M * M;
+  size_t need = bump_size(nq, 8) * 2 + bump_size(mq, 8) + bump_size(Q, 8) + bump_size(mm, 8) +
+                (psi0_out ? bump_size(N, 8) : 0) + (psi1_out ? bump_size(nm, 8) : 0);
+  RGP_TRY(arena_reserve(&h->io, &h->io_bytes, need));
+  Bump b(h->io, h->io_bytes);
+  double* d_mu = b.take<double>(nq);
+  double* d_S = b.take<double>(nq);
+  double* d_Z = b.take<double>(mq);
+  double* d_ell = b.take<double>(Q);
+  double* d_p2 = b.take<double>(mm);
+  double* d_p0 = psi0_out ? b.take<double>(N) : nullptr;
+  double* d_p1 = psi1_out ? b.take<double>(nm) : nullptr;
+  cudaStream_t st = 0;
+  RGP_CUDA(cudaMemcpyAsync(d_mu, mu, nq * 8, cudaMemcpyHostToDevice, st));
+  RGP_CUDA(cudaMemcpyAsync(d_S, S, nq * 8, cudaMemcpyHostToDevice, st));
+  RGP_CUDA(cudaMemcpyAsync(d_Z, Z, mq * 8, cudaMemcpyHostToDevice, st));
+  RGP_CUDA(cudaMemcpyAsync(d_ell, ell, (size_t)Q * 8, cudaMemcpyHostToDevice, st));
+  RGP_TRY(rgp_psi_forward_dev(h, st, N, M, Q, d_mu, d_S, d_Z, d_ell, variance, d_p0, d_p1, d_p2));
+  if (psi0_out) RGP_CUDA(cudaMemcpyAsync(psi0_out, d_p0, (size_t)N * 8, cudaMemcpyDeviceToHost, st));
+  if (psi1_out) RGP_CUDA(cudaMemcpyAsync(psi1_out, d_p1, nm * 8, cudaMemcpyDeviceToHost, st));
+  RGP_CUDA(cudaMemcpyAsync(psi2_out, d_p2, mm * 8, cudaMemcpyDeviceToHost, st));
+  RGP_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int rgp_psi_backward_host(rgp_psi_handle_t h, int64_t N, int M, int Q, const double* mu,
+                          const double* S, const double* Z, const double* ell, double variance,
+                          const double* dL_dpsi0, double dL_dpsi0_const, const double* dL_dpsi1,
+                          const double* dL_dpsi2, double* dmu_out, double* dS_out, double* dZ_out,
+                          double* dell_out, double* dvar_out) {
+  RGP_TRY(check_common(h, N, M, Q, mu, S, Z, ell, variance));
+  if (!dL_dpsi2 || !dmu_out || !dS_out || !dZ_out || !dell_out || !dvar_out)
+    return set_error(RGP_PSI_ERR_INVALID, "null dL_dpsi2 or output pointer");
+  RGP_CUDA(cudaSetDevice(h->device));
+  size_t nq = (size_t)N * Q, nm = (size_t)N * M, mq = (size_t)M * Q, mm = (size_t)M * M;
+  size_t need = bump_size(nq, 8) * 4 + bump_size(mq, 8) * 2 + bump_size(Q, 8) * 2 + bump_size(mm, 8) +
+                bump_size(1, 8) + (dL_dpsi0 ? bump_size(N, 8) : 0) + (dL_dpsi1 ? bump_size(nm, 8) : 0);
+  RGP_TRY(arena_reserve(&h->io, &h->io_bytes, need));
+  Bump b(h->io, h->io_bytes);
+  double* d_mu = b.take<double>(nq);
+  double* d_S = b.take<double>(nq);
+  double* d_dmu = b.take<double>(nq);
+  double* d_dS = b.take<double>(nq);
+  double* d_Z = b.take<double>(mq);
+  double* d_dZ = b.take<double>(mq);
+  double* d_ell = b.take<double>(Q);
+  double* d_dell = b.take<double>(Q);
+  double* d_dL2 = b.take<double>(mm);
+  double* d_dvar = b.take<double>(1);
+  double* d_dL0 = dL_dpsi0 ? b.take<double>(N) : nullptr;
+  double* d_dL1 = dL_dpsi1 ? b.take<double>(nm) : nullptr;
+  cudaStream_t st = 0;
+  RGP_CUDA(cudaMemcpyAsync(d_mu, mu, nq * 8, cudaMemcpyHostToDevice, st));
+  RGP_CUDA(cudaMemcpyAsync(d_S, S, nq * 8, cudaMemcpyHostToDevice, st));
+  RGP_CUDA(cudaMemcpyAsync(d_Z, Z, mq * 8, cudaMemcpyHostToDevice, st));
+  RGP_CUDA(cudaMemcpyAsync(d_ell, ell, (size_t)Q * 8, cudaMemcpyHostToDevice, st));
+  RGP_CUDA(cudaMemcpyAsync(d_dL2, dL_dpsi2, mm * 8, cudaMemcpyHostToDevice, st));
+  if (dL_dpsi0) RGP_CUDA(cudaMemcpyAsync(d_dL0, dL_dpsi0, (size_t)N * 8, cudaMemcpyHostToDevice, st));
+  if (dL_dpsi1) RGP_CUDA(cudaMemcpyAsync(d_dL1, dL_dpsi1, nm * 8, cudaMemcpyHostToDevice, st));
+  RGP_TRY(rgp_psi_backward_dev(h, st, N, M, Q, d_mu, d_S, d_Z, d_ell, variance, d_dL0,
+                               dL_dpsi0_const, d_dL1, d_dL2, d_dmu, d_dS, d_dZ, d_dell, d_dvar));
+  RGP_CUDA(cudaMemcpyAsync(dmu_out, d_dmu, nq * 8, cudaMemcpyDeviceToHost, st));
+  RGP_CUDA(cudaMemcpyAsync(dS_out, d_dS, nq * 8, cudaMemcpyDeviceToHost, st));
+  RGP_CUDA(cudaMemcpyAsync(dZ_out, d_dZ, mq * 8, cudaMemcpyDeviceToHost, st));
+  RGP_CUDA(cudaMemcpyAsync(dell_out, d_dell, (size_t)Q * 8, cudaMemcpyDeviceToHost, st));
+  RGP_CUDA(cudaMemcpyAsync(dvar_out, d_dvar, 8, cudaMemcpyDeviceToHost, st));
+  RGP_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// ------------------------------------------------------------------ measurement
+int64_t rgp_psi_launch_count(rgp_psi_handle_t h) { return h ? h->launches : -1; }
+
+static void drain_pending(rgp_psi_ctx* h) {
+  for (auto& p : h->pending) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, p.start, p.stop) == cudaSuccess) {
+      bool found = false;
+      for (auto& s : h->stats)
+        if (s.name == p.name || !strcmp(s.name, p.name)) {
+          s.total_ms += ms;
+          s.launches++;
+          found = true;
+          break;
+        }
+      if (!found) h->stats.push_back({p.name, (double)ms, 1});
+    } else {
+      cudaGetLastError();
+    }
+    h->event_pool.push_back(p.start);
+    h->event_pool.push_back(p.stop);
+  }
+  h->pending.clear();
+}
+
+int rgp_psi_reset_counters(rgp_psi_handle_t h) {
+  if (!h) return set_error(RGP_PSI_ERR_INVALID, "null handle");
+  RGP_CUDA(cudaSetDevice(h->device));
+  RGP_CUDA(cudaDeviceSynchronize());
+  drain_pending(h);
+  h->stats.clear();
+  h->launches = 0;
+  return 0;
+}
+
+int rgp_psi_kernel_times(rgp_psi_handle_t h, int cap, const char** names, double* total_ms,
+                         int64_t* launches) {
+  if (!h) return set_error(RGP_PSI_ERR_INVALID, "null handle");
+  RGP_CUDA(cudaSetDevice(h->device));
+  RGP_CUDA(cudaDeviceSynchronize());
+  drain_pending(h);
+  int n = (int)h->stats.size();
+  for (int i = 0; i < n && i < cap; ++i) {
+    if (names) names[i] = h->stats[i].name;
+    if (total_ms) total_ms[i] = h->stats[i].total_ms;
+    if (launches) launches[i] = h->stats[i].launches;
+  }
+  return n;
+}
+
+int rgp_psi_fp64_peak(rgp_psi_handle_t h, void* stream, int reps, double* tflops_out) {
+  if (!h || !tflops_out) return set_error(RGP_PSI_ERR_INVALID, "null handle or output");
+  RGP_CUDA(cudaSetDevice(h->device));
+  return peak::measure(h, (cudaStream_t)stream, reps, tflops_out);
+}
+
+int64_t rgp_psi_workspace_bytes(rgp_psi_handle_t h) {
+  return h ? (int64_t)(h->ws_bytes + h->io_bytes) : -1;
+}
+
+}  // extern "C"

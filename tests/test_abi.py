@@ -1,0 +1,104 @@
+"""CPU tests of the boundary: the C-ABI library loads and exports every symbol that
+include/rgp_psi.h declares; the host-side plugin logic (argument handling, errors,
+pickling) behaves like GPy's psicomp.  No compute calls without a GPU."""
+import copy
+import os
+import pickle
+import re
+
+import numpy as np
+import pytest
+
+import rgp_b200
+from rgp_b200 import _lib
+from rgp_b200.gpy_compat import RBF, NormalPosterior
+from rgp_b200.psicomp import PSICOMP_RBF_B200, _fingerprint
+from conftest import HAS_GPU
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "rgp_psi.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(rgp_psi_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_builds_loads_and_exports_every_declared_symbol():
+    lib = rgp_b200.load_library()
+    names = _declared_symbols()
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(lib, n), "missing export " + n
+    assert sorted(_lib.SIGNATURES) == names           # the ctypes table covers the header exactly
+    assert lib.rgp_psi_abi_version() == 1
+
+
+def test_shared_object_contains_sm100a_code_only():
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", rgp_b200.library_path()], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    assert "sm_100a" in out.stdout
+    assert not re.search(r"sm_(?!100a)\d+", out.stdout)
+
+
+@pytest.mark.skipif(HAS_GPU, reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback_create_fails_loudly_without_a_device():
+    with pytest.raises(rgp_b200.PsiError) as ei:
+        rgp_b200.Handle(0)._ensure()
+    assert "no CPU fallback" in str(ei.value)
+    kern = RBF(3, ARD=True)
+    X = NormalPosterior(np.zeros((4, 3)), np.ones((4, 3)))
+    with pytest.raises(rgp_b200.PsiError):
+        kern.psi2(np.zeros((2, 3)), X)
+
+
+def test_invalid_arguments_are_reported_not_aborted():
+    lib = rgp_b200.load_library()
+    assert lib.rgp_psi_create(0, None) == -1
+    assert b"null" in lib.rgp_psi_last_error()
+    assert lib.rgp_psi_forward_dev(None, None, 1, 1, 1, None, None, None, None, 1.0, None, None, None) == -1
+    assert lib.rgp_psi_set_option(None, b"impl", 0) == -1
+    assert lib.rgp_psi_launch_count(None) == -1
+
+
+def test_psicomp_rejects_non_normal_posteriors_like_gpy():
+    pc = PSICOMP_RBF_B200()
+    kern = RBF(2, ARD=True, psicomp=pc)
+    with pytest.raises(ValueError, match="unknown distriubtion"):
+        pc.psicomputations(kern, np.zeros((3, 2)), np.zeros((5, 2)))
+
+    class SpikeAndSlab(NormalPosterior):
+        binary_prob = 0.5
+
+    with pytest.raises(ValueError):
+        pc.psicomputations(kern, np.zeros((3, 2)), SpikeAndSlab(np.zeros((5, 2)), np.ones((5, 2))))
+    with pytest.raises(ValueError, match="shape mismatch"):
+        pc.psicomputations(kern, np.zeros((3, 4)), NormalPosterior(np.zeros((5, 2)), np.ones((5, 2))))
+    with pytest.raises(NotImplementedError):
+        pc.psicomputations(kern, np.zeros((3, 2)), NormalPosterior(np.zeros((5, 2)), np.ones((5, 2))),
+                           return_psi2_n=True)
+
+
+def test_psicomp_survives_deepcopy_and_pickle_without_device_state():
+    pc = PSICOMP_RBF_B200(device=0, impl="reference")
+    kern = RBF(3, ARD=True, inv_l=True, psicomp=pc)
+    k2 = copy.deepcopy(kern)                           # minibatch_tests.py:91 deep-copies models
+    assert k2.psicomp is not pc and k2.psicomp.impl == "reference"
+    k3 = pickle.loads(pickle.dumps(kern))
+    assert k3.psicomp.impl == "reference" and k3.psicomp._handle._h is None
+
+
+def test_fingerprint_sees_in_place_mutation():
+    a = np.arange(12.0).reshape(3, 4)
+    f1 = _fingerprint(a)
+    a[1, 2] += 1e-9                                    # layers.py:537-543 mutates X in place
+    assert _fingerprint(a) != f1
+    assert _fingerprint(a.copy()) == _fingerprint(a)
+
+
+def test_inv_lengthscale_chain_rule_matches_reference_kernels():
+    kern = RBF(2, ARD=True, inv_l=True, lengthscale=[2.0, 0.5])
+    np.testing.assert_allclose(kern.lengthscale, [2.0, 0.5])
+    np.testing.assert_allclose(kern.inv_l, [0.25, 4.0])

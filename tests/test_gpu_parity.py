@@ -1,0 +1,293 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI and
+the GPy-shaped plugin, against the CPU oracle on identical seeded inputs.
+
+Tolerance: BASELINE.json's north star asks for 1e-9 relative in fp64; every comparison
+uses  max|a-b| / max|b|  per array with RTOL = 1e-9, and most
+cases are asserted much tighter (1e-11) so a regression shows before it matters.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import bound_oracle as bo
+from oracle.psi_oracle import psi_backward, psi_forward
+from synth import make_inputs, make_upstream, relerr
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9          # the north-star tolerance
+TIGHT = 2e-11        # what we actually expect
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+IMPLS = ["reference", "fast"]
+
+
+@pytest.fixture(scope="module")
+def plugins():
+    from rgp_b200.psicomp import PSICOMP_RBF_B200
+    return {"reference": PSICOMP_RBF_B200(impl="reference", cache=False),
+            "fast": PSICOMP_RBF_B200(impl="auto", cache=False)}
+
+
+def _kern(pc, var, ell, ard=True):
+    from rgp_b200.gpy_compat import RBF
+    k = RBF(len(ell) if ard else 1, variance=var, lengthscale=ell, ARD=ard, psicomp=pc)
+    return k
+
+
+def _run(pc, var, ell, Z, mu, S, dL0, dL1, dL2):
+    from rgp_b200.gpy_compat import NormalPosterior
+    kern = _kern(pc, var, ell, ard=np.size(ell) != 1)
+    kern.input_dim = mu.shape[1]
+    X = NormalPosterior(mu, S)
+    fwd = pc.psicomputations(kern, Z, X)
+    bwd = pc.psiDerivativecomputations(kern, dL0, dL1, dL2, Z, X)
+    return fwd, bwd
+
+
+def _compare(fwd, bwd, ofwd, obwd, tol):
+    for name, a, b in zip(["psi0", "psi1", "psi2"], fwd, ofwd):
+        assert relerr(a, b) < tol, (name, relerr(a, b))
+    for name, a, b in zip(["dvar", "dl", "dZ", "dmu", "dS"], bwd, obwd):
+        assert np.shape(a) == np.shape(b), name
+        assert relerr(a, b) < tol, (name, relerr(a, b))
+
+
+SHAPES = [
+    # N, M, Q, n_control
+    (1, 1, 1, 0),            # degenerate
+    (13, 7, 3, 1),           # ragged, smaller than every tile
+    (257, 65, 17, 4),        # one past the tile sizes
+    (502, 100, 20, 10),      # config 1 hidden layer (Actuator)
+    (502, 100, 10, 0),       # config 1 output layer
+    (490, 50, 20, 10),       # config 2 (Ballbeam)
+    (408, 200, 40, 20),      # config 3 (MoCap walk/run)
+    (2048, 128, 16, 0),      # sweep corner
+    (1024, 256, 32, 0),
+    (640, 192, 64, 16),      # headline Q, M not a power of two
+]
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("N,M,Q,nc", SHAPES)
+def test_forward_and_backward_match_oracle(plugins, impl, N, M, Q, nc):
+    var, ell, Z, mu, S = make_inputs(N, M, Q, seed=100 + N + M + Q, n_control=nc)
+    dL0, dL1, dL2 = make_upstream(N, M, seed=N + Q)
+    fwd, bwd = _run(plugins[impl], var, ell, Z, mu, S, dL0, dL1, dL2)
+    _compare(fwd, bwd, psi_forward(var, ell, Z, mu, S), psi_backward(dL0, dL1, dL2, var, ell, Z, mu, S), TIGHT)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_headline_tile_shape_small_n(plugins, impl):
+    # M=512, Q=64 (the headline kernel configuration) at an N the oracle finishes in seconds
+    N, M, Q = 192, 512, 64
+    var, ell, Z, mu, S = make_inputs(N, M, Q, seed=5)
+    dL0, dL1, dL2 = make_upstream(N, M, seed=6)
+    fwd, bwd = _run(plugins[impl], var, ell, Z, mu, S, dL0, dL1, dL2)
+    _compare(fwd, bwd, psi_forward(var, ell, Z, mu, S), psi_backward(dL0, dL1, dL2, var, ell, Z, mu, S), TIGHT)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("name", ["tiny_ragged", "actuator_hidden", "actuator_output"])
+def test_against_committed_golden_fixtures(plugins, impl, name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    fwd, bwd = _run(plugins[impl], float(g["variance"]), g["ell"], g["Z"], g["mu"], g["S"],
+                    g["dL0"], g["dL1"], g["dL2"])
+    _compare(fwd, bwd, (g["psi0"], g["psi1"], g["psi2"]),
+             (float(g["dvar"]), g["dl"], g["dZ"], g["dmu"], g["dS"]), TIGHT)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_non_ard_kernel_sums_lengthscale_gradient(plugins, impl):
+    var, ell, Z, mu, S = make_inputs(90, 12, 5, seed=21, ard=False)
+    dL0, dL1, dL2 = make_upstream(90, 12)
+    fwd, bwd = _run(plugins[impl], var, ell, Z, mu, S, dL0, dL1, dL2)
+    assert np.shape(bwd[1]) == (1,)
+    _compare(fwd, bwd, psi_forward(var, ell, Z, mu, S), psi_backward(dL0, dL1, dL2, var, ell, Z, mu, S), TIGHT)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_unsymmetric_dL_dpsi2_is_symmetrised(plugins, impl):
+    var, ell, Z, mu, S = make_inputs(70, 33, 6, seed=22)
+    dL0, dL1, _ = make_upstream(70, 33)
+    dL2 = np.random.default_rng(0).normal(size=(33, 33)) / 33 ** 2
+    _, bwd = _run(plugins[impl], var, ell, Z, mu, S, dL0, dL1, dL2)
+    ob = psi_backward(dL0, dL1, dL2, var, ell, Z, mu, S)
+    for a, b in zip(bwd, ob):
+        assert relerr(a, b) < TIGHT
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_far_inducing_points_underflow_cleanly(plugins, impl):
+    # exponents far below log(DBL_MIN): entries must come out 0, never NaN/Inf
+    var, ell, Z, mu, S = make_inputs(40, 16, 4, seed=23)
+    Z = Z.copy()
+    Z[:4] += 400.0
+    ell = np.full(4, 0.7)
+    dL0, dL1, dL2 = make_upstream(40, 16)
+    fwd, bwd = _run(plugins[impl], var, ell, Z, mu, S, dL0, dL1, dL2)
+    for a in list(fwd) + [np.asarray(x) for x in bwd]:
+        assert np.all(np.isfinite(a))
+    _compare(fwd, bwd, psi_forward(var, ell, Z, mu, S), psi_backward(dL0, dL1, dL2, var, ell, Z, mu, S), 1e-10)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_unnormalised_data_scale(plugins, impl):
+    # the reference's own test data is randn*100 (testing/minibatch_tests.py:16-33)
+    rng = np.random.default_rng(24)
+    N, M, Q = 120, 24, 6
+    mu = rng.normal(size=(N, Q)) * 100.0
+    S = rng.uniform(1.0, 50.0, size=(N, Q))
+    Z = mu[rng.choice(N, M, replace=False)] + rng.normal(size=(M, Q))
+    ell = np.full(Q, 150.0) * rng.uniform(0.7, 1.4, Q)
+    dL0, dL1, dL2 = make_upstream(N, M)
+    fwd, bwd = _run(plugins[impl], 30.0, ell, Z, mu, S, dL0, dL1, dL2)
+    _compare(fwd, bwd, psi_forward(30.0, ell, Z, mu, S), psi_backward(dL0, dL1, dL2, 30.0, ell, Z, mu, S), RTOL)
+
+
+def test_elbo_and_gradients_match_through_the_vardtc_and_svi_bounds(plugins):
+    """North star: 'along with the resulting ELBO and gradients'.  The restated
+    VarDTC / SVI bound (oracle/bound_oracle.py) is driven once by the oracle's psi
+    functions and once by the CUDA plugin."""
+    from rgp_b200.gpy_compat import RBF, NormalPosterior
+    N, M, Q, D = 502, 100, 20, 1
+    var, ell, Z, mu, S = make_inputs(N, M, Q, seed=31, n_control=10)
+    rng = np.random.default_rng(2)
+    Y = rng.normal(size=(N, D))
+    pc = plugins["fast"]
+
+    def cuda_fwd(v, l, Z_, mu_, S_):
+        return pc.psicomputations(RBF(Q, v, l, ARD=True, psicomp=pc), Z_, NormalPosterior(mu_, S_))
+
+    def cuda_bwd(d0, d1, d2, v, l, Z_, mu_, S_):
+        return pc.psiDerivativecomputations(RBF(Q, v, l, ARD=True, psicomp=pc), d0, d1, d2, Z_,
+                                            NormalPosterior(mu_, S_))
+
+    W = rng.normal(size=(M, M)) * 0.05
+    svi = dict(qU_mean=rng.normal(size=(M, D)), qU_var=W @ W.T + 0.5 * np.eye(M), qU_ratio=0.5)
+    for mode in (None, svi):
+        Lo, go = bo.layer_bound_and_grads(var, ell, Z, mu, S, Y, 0.05, psi_forward, psi_backward, svi=mode)
+        Lc, gc = bo.layer_bound_and_grads(var, ell, Z, mu, S, Y, 0.05, cuda_fwd, cuda_bwd, svi=mode)
+        assert abs(Lc - Lo) <= RTOL * abs(Lo)
+        for k in ("variance", "lengthscale", "Z", "mu", "S"):
+            assert relerr(gc[k], go[k]) < RTOL, (k, relerr(gc[k], go[k]))
+
+
+def test_plugin_cache_and_inplace_mutation(plugins):
+    from rgp_b200.gpy_compat import RBF, NormalPosterior
+    from rgp_b200.psicomp import PSICOMP_RBF_B200
+    pc = PSICOMP_RBF_B200(cache=True)
+    var, ell, Z, mu, S = make_inputs(64, 10, 4, seed=41)
+    kern = RBF(4, var, ell, ARD=True, inv_l=True, psicomp=pc)
+    X = NormalPosterior(mu, S)
+    n0 = pc.handle.launch_count()
+    p0, p1, p2 = kern.psi0(Z, X), kern.psi1(Z, X), kern.psi2(Z, X)      # vardtc.py:59-61
+    n1 = pc.handle.launch_count()
+    assert n1 > n0
+    assert pc.handle.launch_count() == n1                               # 2nd/3rd accessor: cache hits
+    p2[0, 0] = 123.0                                                    # callers own their arrays
+    assert kern.psi2(Z, X)[0, 0] != 123.0
+    X.mean[3, 1] += 0.25                                                # in-place update (layers.py:537)
+    q2 = kern.psi2(Z, X)
+    assert pc.handle.launch_count() > n1
+    assert relerr(q2, psi_forward(var, kern.lengthscale, Z, X.mean, X.variance)[2]) < TIGHT
+    dL0, dL1, dL2 = make_upstream(64, 10)
+    kern.update_gradients_expectations(dL0, dL1, dL2, Z, X)
+    n2 = pc.handle.launch_count()
+    dZ = kern.gradients_Z_expectations(dL0, dL1, dL2, Z, X)
+    dmu, dS = kern.gradients_qX_expectations(dL0, dL1, dL2, Z, X)
+    assert pc.handle.launch_count() == n2                               # one evaluation for all three
+    ob = psi_backward(dL0, dL1, dL2, var, kern.lengthscale, Z, X.mean, X.variance)
+    assert relerr(dZ, ob[2]) < TIGHT and relerr(dmu, ob[3]) < TIGHT and relerr(dS, ob[4]) < TIGHT
+    assert relerr(kern.inv_l_gradient, ob[1] * (kern.lengthscale ** 3 / -2.0)) < TIGHT
+
+
+def test_device_api_scalar_dL0_and_null_outputs():
+    import torch
+    from rgp_b200.device import DevicePsi
+    dp = DevicePsi(0)
+    N, M, Q = 300, 40, 8
+    var, ell, Z, mu, S = make_inputs(N, M, Q, seed=51)
+    _, dL1, dL2 = make_upstream(N, M)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    p0, p1, p2 = dp.forward(t(mu), t(S), t(Z), t(ell), var, want_psi0=False, want_psi1=False)
+    assert p0 is None and p1 is None
+    of = psi_forward(var, ell, Z, mu, S)
+    assert relerr(p2.cpu().numpy(), of[2]) < TIGHT
+    out = dp.backward(t(mu), t(S), t(Z), t(ell), var, -0.5, t(dL1), t(dL2))
+    ob = psi_backward(np.full(N, -0.5), dL1, dL2, var, ell, Z, mu, S)
+    for a, b in zip(out, ob):
+        assert relerr(a.cpu().numpy(), b) < TIGHT
+    out = dp.backward(t(mu), t(S), t(Z), t(ell), var, 0.0, None, t(dL2))       # dL_dpsi1 omitted
+    ob = psi_backward(np.zeros(N), np.zeros((N, M)), dL2, var, ell, Z, mu, S)
+    for a, b in zip(out, ob):
+        assert relerr(a.cpu().numpy(), b) < TIGHT
+
+
+# ---------------------------------------------------------------- size-independent properties
+def _device_inputs(N, M, Q, seed):
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    mu = torch.randn((N, Q), generator=g, device="cuda", dtype=torch.float64)
+    S = torch.rand((N, Q), generator=g, device="cuda", dtype=torch.float64) * 0.49 + 0.01
+    Z = torch.randn((M, Q), generator=g, device="cuda", dtype=torch.float64)
+    ell = (torch.rand(Q, generator=g, device="cuda", dtype=torch.float64) * 0.7 + 0.7) * Q ** 0.5
+    dL1 = torch.randn((N, M), generator=g, device="cuda", dtype=torch.float64) / M
+    dL2 = torch.randn((M, M), generator=g, device="cuda", dtype=torch.float64) / M ** 2
+    return mu, S, Z, ell, dL1, 0.5 * (dL2 + dL2.T)
+
+
+def test_large_shard_additivity_and_fast_vs_reference_kernels():
+    """At a size the CPU oracle cannot reach: (i) rows split 1/2/4/8 ways sum to the full
+    result (the reference's minibatch additivity property, rtol 1e-11 on gradients);
+    (ii) the tiled kernels agree with the independent one-thread-per-output kernels."""
+    import torch
+    from rgp_b200.device import DevicePsi
+    fast, ref = DevicePsi(0, impl=0), DevicePsi(0, impl=2)
+    N, M, Q = 16384, 256, 32
+    mu, S, Z, ell, dL1, dL2 = _device_inputs(N, M, Q, seed=3)
+    var = 1.3
+    _, p1, p2 = fast.forward(mu, S, Z, ell, var)
+    full = fast.backward(mu, S, Z, ell, var, -0.5, dL1, dL2)
+    for ways in (2, 4, 8):
+        acc2 = torch.zeros_like(p2)
+        accs = [torch.zeros(1, device="cuda", dtype=torch.float64), torch.zeros_like(ell), torch.zeros_like(Z)]
+        rows = []
+        for idx in torch.arange(N, device="cuda").chunk(ways):
+            s, e = int(idx[0]), int(idx[-1]) + 1
+            acc2 += fast.forward(mu[s:e].contiguous(), S[s:e].contiguous(), Z, ell, var, want_psi1=False)[2]
+            b = fast.backward(mu[s:e].contiguous(), S[s:e].contiguous(), Z, ell, var, -0.5,
+                              dL1[s:e].contiguous(), dL2)
+            for a, x in zip(accs, b[:3]):
+                a += x
+            rows.append(b[3])
+        assert relerr(acc2.cpu().numpy(), p2.cpu().numpy()) < 1e-12
+        for a, x in zip(accs, full[:3]):
+            assert relerr(a.cpu().numpy(), x.cpu().numpy()) < 1e-11
+        assert relerr(torch.cat(rows).cpu().numpy(), full[3].cpu().numpy()) < 1e-12
+    Nr = 2048                                                     # reference kernels are slow
+    sl = slice(0, Nr)
+    rp = ref.forward(mu[sl].contiguous(), S[sl].contiguous(), Z, ell, var)
+    fp = fast.forward(mu[sl].contiguous(), S[sl].contiguous(), Z, ell, var)
+    assert relerr(fp[1].cpu().numpy(), rp[1].cpu().numpy()) < TIGHT
+    assert relerr(fp[2].cpu().numpy(), rp[2].cpu().numpy()) < TIGHT
+    rb = ref.backward(mu[sl].contiguous(), S[sl].contiguous(), Z, ell, var, -0.5, dL1[sl].contiguous(), dL2)
+    fb = fast.backward(mu[sl].contiguous(), S[sl].contiguous(), Z, ell, var, -0.5, dL1[sl].contiguous(), dL2)
+    for a, b in zip(fb, rb):
+        assert relerr(a.cpu().numpy(), b.cpu().numpy()) < 1e-10
+
+
+def test_psi2_is_symmetric_psd_and_bounded():
+    import torch
+    from rgp_b200.device import DevicePsi
+    dp = DevicePsi(0)
+    N, M, Q = 8192, 192, 24
+    mu, S, Z, ell, _, _ = _device_inputs(N, M, Q, seed=9)
+    p0, p1, p2 = dp.forward(mu, S, Z, ell, 1.3, want_psi0=True)
+    assert torch.equal(p0, torch.full_like(p0, 1.3))
+    assert float((p2 - p2.T).abs().max()) <= 1e-12 * float(p2.abs().max())
+    assert float(torch.linalg.eigvalsh(0.5 * (p2 + p2.T)).min()) > -1e-8 * float(p2.abs().max())
+    assert float(p1.max()) <= 1.3 and float(p1.min()) >= 0.0
+    # Cauchy-Schwarz / Jensen: Psi2 - Psi1^T Psi1 is PSD summed over rows
+    gap = p2 - p1.T @ p1
+    assert float(torch.linalg.eigvalsh(0.5 * (gap + gap.T)).min()) > -1e-8 * float(p2.abs().max())
