@@ -1,9 +1,274 @@
-// fast_path.cuh - placeholder; replaced by the tiled kernels.
+// fast_path.cuh - host-side driver of the tiled kernels: workspace plan and launch order.
 #pragma once
+#include <algorithm>
+
 #include "context.cuh"
-namespace rgp { namespace fast {
-static inline bool supported(int, int) { return false; }
-static inline int init(rgp_psi_ctx*) { return 0; }
-static inline int forward(rgp_psi_ctx*, cudaStream_t, int64_t, int, int, const double*, const double*, const double*, const double*, double, double*, double*, double*) { return set_error(RGP_PSI_ERR_INVALID, "fast path not built"); }
-static inline int backward(rgp_psi_ctx*, cudaStream_t, int64_t, int, int, const double*, const double*, const double*, const double*, double, const double*, double, const double*, const double*, double*, double*, double*, double*, double*) { return set_error(RGP_PSI_ERR_INVALID, "fast path not built"); }
-}}
+#include "fast_prep.cuh"
+#include "psi2_kernels.cuh"
+
+namespace rgp {
+namespace fast {
+
+static inline bool supported(int M, int Q) { return Q >= 1 && Q <= 64 && M >= 1; }
+static inline int qc_for(int Q) { return Q <= 16 ? 16 : (Q <= 32 ? 32 : 64); }
+
+static int init(rgp_psi_ctx*) {
+  RGP_CUDA(cudaFuncSetAttribute(k_psi2_fwd<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<16>::FWD_SMEM));
+  RGP_CUDA(cudaFuncSetAttribute(k_psi2_fwd<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<32>::FWD_SMEM));
+  RGP_CUDA(cudaFuncSetAttribute(k_psi2_fwd<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<64>::FWD_SMEM));
+  RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwd<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<16>::BWD_SMEM));
+  RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwd<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<32>::BWD_SMEM));
+  RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwd<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<64>::BWD_SMEM));
+  return 0;
+}
+
+struct Shape {
+  int M, Mp, nt, nblocks, Q, QC, qk, RS;
+  int64_t rc;
+};
+
+static Shape make_shape(const rgp_psi_ctx* h, int64_t N, int M, int Q) {
+  Shape s;
+  s.M = M;
+  s.Mp = (int)round_up(M, BM);
+  s.nt = s.Mp / BM;
+  s.nblocks = s.nt * (s.nt + 1) / 2;
+  s.Q = Q;
+  s.QC = qc_for(Q);
+  s.qk = (int)round_up(Q, 4);
+  s.RS = s.QC + 4;
+  int64_t rc = h->row_chunk > 0 ? h->row_chunk : ((int64_t)1 << 20);
+  s.rc = std::min<int64_t>(N, rc);
+  return s;
+}
+
+// row ranges R x block groups G so that R*G ~ target CTAs
+static void pick_grid(int64_t rows, int nblocks, int target, int* R, int* G) {
+  int64_t rmax = std::max<int64_t>(1, (rows + 3) / 4);
+  if (rmax >= target) {
+    *R = target;
+    *G = 1;
+  } else {
+    *R = (int)rmax;
+    *G = (int)std::min<int64_t>(nblocks, (target + rmax - 1) / rmax);
+  }
+}
+
+static GemmOperand op(const double* p, int64_t sr, int64_t sk, int64_t rows) {
+  GemmOperand o;
+  o.p = p;
+  o.sr = sr;
+  o.sk = sk;
+  o.rows = (int)rows;
+  return o;
+}
+
+static GemmEpi epi_plain(double* out, int64_t ld, int64_t split_stride) {
+  GemmEpi e;
+  e.mode = EPI_PLAIN;
+  e.bias = nullptr;
+  e.variance = 0.0;
+  e.scale = nullptr;
+  e.scale_ld = 0;
+  e.M = 0;
+  e.out = out;
+  e.out_ld = ld;
+  e.split_stride = split_stride;
+  return e;
+}
+
+template <int QC>
+static int launch_fwd(rgp_psi_ctx* h, cudaStream_t st, const Shape& s, int64_t rows, int R, int G,
+                      const double* Zt, const double* w, const double* HP, double* P2p) {
+  RGP_LAUNCH(h, st, "psi2_fwd", (k_psi2_fwd<QC>), dim3(R, G), P2_THREADS, P2Cfg<QC>::FWD_SMEM, rows,
+             s.nt, s.nblocks, s.qk, Zt, w, HP, P2p);
+  return 0;
+}
+
+template <int QC>
+static int launch_bwd(rgp_psi_ctx* h, cudaStream_t st, const Shape& s, int64_t rows, int R, int G,
+                      const double* Zt, const double* Ct, const double* w, const double* HP,
+                      double* lam, double* Wq, double* ACCp) {
+  RGP_LAUNCH(h, st, "psi2_bwd", (k_psi2_bwd<QC>), dim3(R, G), P2_THREADS, P2Cfg<QC>::BWD_SMEM, rows,
+             s.Mp, s.nt, s.nblocks, s.qk, Zt, Ct, w, HP, lam, Wq, ACCp);
+  return 0;
+}
+
+// lam[0] += sum_{g>=1} lam[g]  (and the same for Wq); only launched when G > 1
+__global__ void k_collapse(int64_t count, int G, double* __restrict__ buf) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  double v = buf[i];
+  for (int g = 1; g < G; ++g) v += buf[(int64_t)g * count + i];
+  buf[i] = v;
+}
+
+static int static_prep(rgp_psi_ctx* h, cudaStream_t st, const Shape& s, const double* Z, double* o,
+                       double* Zt, double* ZB) {
+  RGP_LAUNCH(h, st, "center", k_center, s.Q, 128, 0, s.M, s.Q, Z, o);
+  RGP_LAUNCH(h, st, "build_Z", k_build_Z, ceil_div((int64_t)s.Mp * s.RS, 256), 256, 0, s.M, s.Mp, s.Q,
+             s.QC, Z, o, Zt, ZB);
+  return 0;
+}
+
+// HP[tile][rows][64] = b2 + A2 . ZB^T  (and Psi1 / L1 through the same GEMM)
+static int gemm_nt(rgp_psi_ctx* h, cudaStream_t st, const char* name, const Shape& s, int64_t rows,
+                   const double* A, const double* ZB, GemmEpi e) {
+  dim3 grid(ceil_div(rows, 64), s.nt, 1);
+  RGP_LAUNCH(h, st, name, (k_gemm<true, true>), grid, 256, 0, op(A, 2 * s.QC, 1, rows),
+             op(ZB, 2 * s.QC, 1, s.Mp), (int64_t)2 * s.QC, e);
+  return 0;
+}
+
+static int forward(rgp_psi_ctx* h, cudaStream_t st, int64_t N, int M, int Q, const double* mu,
+                   const double* S, const double* Z, const double* ell, double variance,
+                   double* psi0, double* psi1, double* psi2) {
+  const Shape s = make_shape(h, N, M, Q);
+  int R, G;
+  pick_grid(s.rc, s.nblocks, 2 * h->sm_count, &R, &G);
+  const int QC = s.QC;
+  size_t need = bump_size(Q, 8) + bump_size((size_t)s.Mp * s.RS, 8) + bump_size((size_t)s.Mp * 2 * QC, 8) +
+                bump_size((size_t)s.nblocks * R * 4096, 8) + bump_size(s.rc * QC, 8) +
+                bump_size(s.rc * 2 * QC, 8) * 2 + bump_size(s.rc, 8) * 2 + bump_size(s.rc * s.Mp, 8);
+  RGP_TRY(arena_reserve(&h->ws, &h->ws_bytes, need));
+  Bump b(h->ws, h->ws_bytes);
+  double* o = b.take<double>(Q);
+  double* Zt = b.take<double>((size_t)s.Mp * s.RS);
+  double* ZB = b.take<double>((size_t)s.Mp * 2 * QC);
+  double* P2p = b.take<double>((size_t)s.nblocks * R * 4096);
+  double* w = b.take<double>(s.rc * QC);
+  double* A2 = b.take<double>(s.rc * 2 * QC);
+  double* A1 = b.take<double>(s.rc * 2 * QC);
+  double* b2 = b.take<double>(s.rc);
+  double* b1 = b.take<double>(s.rc);
+  double* HP = b.take<double>(s.rc * s.Mp);
+
+  RGP_TRY(static_prep(h, st, s, Z, o, Zt, ZB));
+  if (psi0) RGP_LAUNCH(h, st, "fill_psi0", k_fill, ceil_div(N, 256), 256, 0, N, variance, psi0);
+  int chunk = 0;
+  for (int64_t r0 = 0; r0 < N; r0 += s.rc, ++chunk) {
+    const int64_t rows = std::min(s.rc, N - r0);
+    RGP_LAUNCH(h, st, "rowprep", k_rowprep, ceil_div(rows, 4), 128, 0, rows, Q, QC, mu + r0 * Q,
+               S + r0 * Q, ell, o, w, A2, b2, psi1 ? A1 : (double*)nullptr, psi1 ? b1 : (double*)nullptr);
+    GemmEpi e;
+    e.mode = EPI_HP; e.bias = b2; e.variance = variance; e.scale = nullptr; e.scale_ld = 0; e.M = M;
+    e.out = HP; e.out_ld = rows; e.split_stride = 0;
+    RGP_TRY(gemm_nt(h, st, "hprime_gemm", s, rows, A2, ZB, e));
+    if (psi1) {
+      e.mode = EPI_PSI1; e.bias = b1; e.out = psi1 + r0 * M; e.out_ld = M;
+      RGP_TRY(gemm_nt(h, st, "psi1_fwd", s, rows, A1, ZB, e));
+    }
+    int Rc, Gc;
+    pick_grid(rows, s.nblocks, 2 * h->sm_count, &Rc, &Gc);
+    Rc = std::min(Rc, R);
+    if (QC == 16) RGP_TRY(launch_fwd<16>(h, st, s, rows, Rc, Gc, Zt, w, HP, P2p));
+    else if (QC == 32) RGP_TRY(launch_fwd<32>(h, st, s, rows, Rc, Gc, Zt, w, HP, P2p));
+    else RGP_TRY(launch_fwd<64>(h, st, s, rows, Rc, Gc, Zt, w, HP, P2p));
+    RGP_LAUNCH(h, st, "psi2_reduce", k_psi2_reduce, s.nblocks, 256, 0, M, s.nt, Rc, variance * variance,
+               P2p, chunk > 0 ? 1 : 0, psi2);
+  }
+  return 0;
+}
+
+static int backward(rgp_psi_ctx* h, cudaStream_t st, int64_t N, int M, int Q, const double* mu,
+                    const double* S, const double* Z, const double* ell, double variance,
+                    const double* dL0, double dL0c, const double* dL1, const double* dL2,
+                    double* dmu, double* dS, double* dZ, double* dell, double* dvar) {
+  const Shape s = make_shape(h, N, M, Q);
+  int R, G;
+  pick_grid(s.rc, s.nblocks, h->sm_count, &R, &G);
+  const int QC = s.QC, Mp = s.Mp;
+  const int ncta = R * G;
+  const int tn_tiles = s.nt * (2 * QC / 64 > 0 ? (2 * QC + 63) / 64 : 1);
+  const int splits = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)64, (int64_t)(2 * h->sm_count / std::max(1, tn_tiles)),
+                                                                 (s.rc + 255) / 256}));
+  const int nfin = (int)std::min<int64_t>(ceil_div(s.rc, 4), (int64_t)8 * h->sm_count);
+  size_t need = bump_size(Q, 8) + bump_size((size_t)Mp * s.RS, 8) + bump_size((size_t)Mp * 2 * QC, 8) +
+                bump_size((size_t)s.nblocks * 4096, 8) + bump_size(s.rc * QC, 8) +
+                bump_size(s.rc * 2 * QC, 8) * 4 + bump_size(s.rc, 8) * 2 + bump_size(s.rc * Mp, 8) * 2 +
+                bump_size((size_t)G * s.rc * Mp, 8) + bump_size((size_t)G * s.rc * QC, 8) +
+                bump_size((size_t)ncta * Mp * QC, 8) + bump_size((size_t)splits * Mp * 2 * QC, 8) * 2 +
+                bump_size((size_t)nfin * (QC + 1), 8);
+  RGP_TRY(arena_reserve(&h->ws, &h->ws_bytes, need));
+  Bump b(h->ws, h->ws_bytes);
+  double* o = b.take<double>(Q);
+  double* Zt = b.take<double>((size_t)Mp * s.RS);
+  double* ZB = b.take<double>((size_t)Mp * 2 * QC);
+  double* Ct = b.take<double>((size_t)s.nblocks * 4096);
+  double* w = b.take<double>(s.rc * QC);
+  double* A2 = b.take<double>(s.rc * 2 * QC);
+  double* A1 = b.take<double>(s.rc * 2 * QC);
+  double* R2 = b.take<double>(s.rc * 2 * QC);
+  double* R1 = b.take<double>(s.rc * 2 * QC);
+  double* b2 = b.take<double>(s.rc);
+  double* b1 = b.take<double>(s.rc);
+  double* HP = b.take<double>(s.rc * Mp);
+  double* L1 = b.take<double>(s.rc * Mp);
+  double* lam = b.take<double>((size_t)G * s.rc * Mp);
+  double* Wq = b.take<double>((size_t)G * s.rc * QC);
+  double* ACCp = b.take<double>((size_t)ncta * Mp * QC);
+  double* Gl = b.take<double>((size_t)splits * Mp * 2 * QC);
+  double* GL = b.take<double>((size_t)splits * Mp * 2 * QC);
+  double* part = b.take<double>((size_t)nfin * (QC + 1));
+
+  RGP_CUDA(cudaMemsetAsync(dZ, 0, sizeof(double) * M * Q, st));
+  RGP_CUDA(cudaMemsetAsync(dell, 0, sizeof(double) * Q, st));
+  RGP_CUDA(cudaMemsetAsync(dvar, 0, sizeof(double), st));
+  RGP_TRY(static_prep(h, st, s, Z, o, Zt, ZB));
+  RGP_LAUNCH(h, st, "build_C", k_build_C, s.nblocks, 256, 0, M, s.nt, dL2, variance * variance, Ct);
+
+  for (int64_t r0 = 0; r0 < N; r0 += s.rc) {
+    const int64_t rows = std::min(s.rc, N - r0);
+    int Rc, Gc;
+    pick_grid(rows, s.nblocks, h->sm_count, &Rc, &Gc);
+    Rc = std::min(Rc, R);
+    Gc = std::min(Gc, G);
+    const int nc = Rc * Gc;
+    RGP_CUDA(cudaMemsetAsync(lam, 0, sizeof(double) * (size_t)Gc * rows * Mp, st));
+    RGP_CUDA(cudaMemsetAsync(Wq, 0, sizeof(double) * (size_t)Gc * rows * QC, st));
+    RGP_CUDA(cudaMemsetAsync(ACCp, 0, sizeof(double) * (size_t)nc * Mp * QC, st));
+    RGP_LAUNCH(h, st, "rowprep", k_rowprep, ceil_div(rows, 4), 128, 0, rows, Q, QC, mu + r0 * Q,
+               S + r0 * Q, ell, o, w, A2, b2, dL1 ? A1 : (double*)nullptr, dL1 ? b1 : (double*)nullptr);
+    GemmEpi e;
+    e.mode = EPI_HP; e.bias = b2; e.variance = variance; e.scale = nullptr; e.scale_ld = 0; e.M = M;
+    e.out = HP; e.out_ld = rows; e.split_stride = 0;
+    RGP_TRY(gemm_nt(h, st, "hprime_gemm", s, rows, A2, ZB, e));
+    if (dL1) {
+      e.mode = EPI_L1; e.bias = b1; e.scale = dL1 + r0 * M; e.scale_ld = M; e.out = L1; e.out_ld = Mp;
+      RGP_TRY(gemm_nt(h, st, "psi1_L1", s, rows, A1, ZB, e));
+    }
+    if (QC == 16) RGP_TRY(launch_bwd<16>(h, st, s, rows, Rc, Gc, Zt, Ct, w, HP, lam, Wq, ACCp));
+    else if (QC == 32) RGP_TRY(launch_bwd<32>(h, st, s, rows, Rc, Gc, Zt, Ct, w, HP, lam, Wq, ACCp));
+    else RGP_TRY(launch_bwd<64>(h, st, s, rows, Rc, Gc, Zt, Ct, w, HP, lam, Wq, ACCp));
+    if (Gc > 1) {
+      RGP_LAUNCH(h, st, "collapse", k_collapse, ceil_div(rows * Mp, 256), 256, 0, rows * Mp, Gc, lam);
+      RGP_LAUNCH(h, st, "collapse", k_collapse, ceil_div(rows * QC, 256), 256, 0, rows * QC, Gc, Wq);
+    }
+    // R2 = lam [rows x Mp] . ZB [Mp x 2QC]   (U | V);  R1 likewise from L1
+    dim3 gnn(ceil_div(rows, 64), ceil_div(2 * QC, 64), 1);
+    RGP_LAUNCH(h, st, "rows_gemm", (k_gemm<true, false>), gnn, 256, 0, op(lam, Mp, 1, rows),
+               op(ZB, 1, 2 * QC, 2 * QC), (int64_t)Mp, epi_plain(R2, 2 * QC, 0));
+    if (dL1)
+      RGP_LAUNCH(h, st, "rows_gemm", (k_gemm<true, false>), gnn, 256, 0, op(L1, Mp, 1, rows),
+                 op(ZB, 1, 2 * QC, 2 * QC), (int64_t)Mp, epi_plain(R1, 2 * QC, 0));
+    const int nf = (int)std::min<int64_t>(ceil_div(rows, 4), (int64_t)8 * h->sm_count);
+    RGP_LAUNCH(h, st, "rows_finalize", k_rows_finalize, nf, 128, sizeof(double) * 4 * (QC + 1), rows, M, Mp,
+               Q, QC, 1, mu + r0 * Q, S + r0 * Q, ell, o, variance, lam, Wq, R2,
+               dL1 ? L1 : (const double*)nullptr, dL1 ? R1 : (const double*)nullptr,
+               dL0 ? dL0 + r0 : (const double*)nullptr, dL0c, dmu + r0 * Q, dS + r0 * Q, part);
+    // Gl = lam^T [Mp x rows] . A2 [rows x 2QC]  (split over rows);  GL = L1^T . A1
+    const int sp = (int)std::max<int64_t>(1, std::min<int64_t>(splits, (rows + 255) / 256));
+    dim3 gtn(s.nt, ceil_div(2 * QC, 64), sp);
+    RGP_LAUNCH(h, st, "dz_gemm", (k_gemm<false, false>), gtn, 256, 0, op(lam, 1, Mp, Mp),
+               op(A2, 1, 2 * QC, 2 * QC), rows, epi_plain(Gl, 2 * QC, (int64_t)Mp * 2 * QC));
+    if (dL1)
+      RGP_LAUNCH(h, st, "dz_gemm", (k_gemm<false, false>), gtn, 256, 0, op(L1, 1, Mp, Mp),
+                 op(A1, 1, 2 * QC, 2 * QC), rows, epi_plain(GL, 2 * QC, (int64_t)Mp * 2 * QC));
+    RGP_LAUNCH(h, st, "final_small", k_final_small, ceil_div((int64_t)M * Q + Q + 1, 128), 128, 0, M, Mp, Q,
+               QC, ZB, Gl, sp, dL1 ? GL : (const double*)nullptr, sp, ACCp, nc, part, nf, dZ, dell, dvar);
+  }
+  return 0;
+}
+
+}  // namespace fast
+}  // namespace rgp

@@ -1,0 +1,431 @@
+// psi2_kernels.cuh - the two O(N * M^2 * Q) kernels: Psi2 forward and Psi2 backward.
+//
+// Work decomposition.  The M x M pair matrix is cut into 64 x 64 blocks (I <= J, upper
+// triangle).  A CTA owns a contiguous row range [r0, r1) and walks the blocks of its
+// block group; for every block it streams its rows ONE ROW AT A TIME:
+//
+//   stage 1   G[m,m'] = sum_q (w_nq Z'_mq) Z'_m'q                 64 x 64 x Q   (DMMA)
+//   epilogue  p = exp(H_nm + H_nm' - G)                            4096 exps
+//             forward : Psi2 tile += p                (register accumulators)
+//             backward: L = C[m,m'] * p -> shared     (C = s2^2 * sym(dL_dpsi2), registers)
+//   stage 2-I T[m,q]   = sum_m' L[m,m'] Z'_m'q                     64 x Q x 64   (DMMA)
+//             accI[m,q] += w_nq T[m,q];   Wq[n,q] += sum_m Z'_mq T[m,q]
+//   stage 2-J accJ[m',q] += sum_m L[m,m'] (w_nq Z'_mq)             64 x Q x 64   (DMMA)
+//
+// (diagonal blocks skip stage 2-J).  Row sums / column sums of L give lambda_nm.  The
+// O(M*Q)-per-row remainder of the gradient algebra is in fast_prep.cuh.
+//
+// Why mma.sync m8n8k4 f64 (DMMA) and not DFMA register tiles: measured on this B200
+// (profiles/microbench_r01.jsonl) DMMA and DFMA share the FP64 pipe and peak at the
+// same 36.9 TFLOP/s, but an LDS.128 costs >= 2.5 SM-cycles even fully broadcast, so an
+// 8x4 DFMA register tile fed from shared memory needs ~190 B/clk of LSU bandwidth and
+// is LSU-bound; DMMA fragments need 0.5-1 B per FMA.  The arithmetic is still IEEE
+// fp64 on the FP64 pipe; the roofline denominator is the DFMA-chain peak.
+//
+// Shared-memory tiles are [64][QC+4] / [64][68] doubles: row stride == 4 (mod 16)
+// doubles makes every fragment load (rows by lane/4, cols by lane%4, or transposed)
+// hit each bank exactly twice, the minimum for 256 B.
+#pragma once
+#include "common.cuh"
+
+namespace rgp {
+namespace fast {
+
+constexpr int P2_THREADS = 256;
+constexpr int RSL = 68;
+
+template <int QC>
+struct P2Cfg {
+  static constexpr int RS = QC + 4;
+  static constexpr int NJ = QC / 16;        // 8-wide q tiles per warp in stage 2
+  static constexpr int VB = QC + 128;       // per-row vector slot: w[QC] | H_I[64] | H_J[64]
+  static constexpr int FWD_SMEM = (2 * 64 * RS + 3 * VB) * 8;
+  static constexpr int BWD_SMEM =
+      (2 * 64 * RS + 2 * 64 * RSL + 3 * VB + 2 * 4 * QC + 2 * 2 * 64 + 2 * 4 * 64) * 8;
+};
+
+RGP_DEVINL void dmma(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+RGP_DEVINL void red_add(double* addr, double v) {
+  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
+}
+
+RGP_DEVINL void block_ij(int b, int nt, int& I, int& J) {
+  int i = 0, rem = b;
+  while (rem >= nt - i) { rem -= nt - i; ++i; }
+  I = i;
+  J = i + rem;
+}
+
+// copy a [64][RS] tile (contiguous in global) into shared memory, 16 B per thread-step
+template <int COUNT>
+RGP_DEVINL void copy_tile(double* dst, const double* __restrict__ src, int tid) {
+  const double2* s2 = reinterpret_cast<const double2*>(src);
+  double2* d2 = reinterpret_cast<double2*>(dst);
+  for (int i = tid; i < COUNT / 2; i += P2_THREADS) d2[i] = s2[i];
+}
+
+// stage 1: acc[2][4][2] = sum_q (w_q ZI[m][q]) ZJ[m'][q] for this warp's 16 x 32 sub-block
+template <int QC>
+RGP_DEVINL void stage1(const double* __restrict__ sZI, const double* __restrict__ sZJ,
+                       const double* __restrict__ sw, int qk, int wr, int wc, int lane,
+                       double (&acc)[2][4][2]) {
+  constexpr int RS = P2Cfg<QC>::RS;
+  const int g = lane >> 2, t = lane & 3;
+  const double* pa = sZI + (16 * wr + g) * RS + t;
+  const double* pb = sZJ + (32 * wc + g) * RS + t;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll 2
+  for (int k0 = 0; k0 < qk; k0 += 4) {
+    const double wv = sw[k0 + t];
+    double a[2], b[4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) a[i] = pa[i * 8 * RS + k0] * wv;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = pb[j * 8 * RS + k0];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+  }
+}
+
+// =====================================================================================
+// Forward: partial Psi2 tiles.  grid = (R row ranges, G block groups).
+//   P2p[b][r][64][64] = sum_{n in range r} exp(H_nm + H_nm' - G_n[m,m'])     (no s2^2 yet)
+// =====================================================================================
+template <int QC>
+__global__ void __launch_bounds__(P2_THREADS, 2)
+k_psi2_fwd(int64_t rc, int nt, int nblocks, int qk, const double* __restrict__ Zt,
+           const double* __restrict__ wrow, const double* __restrict__ HP,
+           double* __restrict__ P2p) {
+  using C = P2Cfg<QC>;
+  constexpr int RS = C::RS, VB = C::VB;
+  extern __shared__ __align__(16) double smem[];
+  double* sZI = smem;
+  double* sZJ = sZI + 64 * RS;
+  double* sV = sZJ + 64 * RS;                     // 3 slots of VB
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int wr = wid >> 1, wc = wid & 1, g = lane >> 2, t = lane & 3;
+  const int R = gridDim.x, G = gridDim.y;
+  const int64_t per = (rc + R - 1) / R;
+  const int64_t r0 = per * blockIdx.x, r1 = (r0 + per < rc) ? r0 + per : rc;
+
+  int curI = -1, curJ = -1;
+  for (int b = blockIdx.y; b < nblocks; b += G) {
+    int I, J;
+    block_ij(b, nt, I, J);
+    __syncthreads();                              // previous block fully done with smem
+    if (I != curI) copy_tile<64 * RS>(sZI, Zt + (size_t)I * 64 * RS, tid);
+    if (J != curJ) copy_tile<64 * RS>(sZJ, Zt + (size_t)J * 64 * RS, tid);
+    curI = I;
+    curJ = J;
+    const double* hI = HP + (size_t)I * rc * 64;
+    const double* hJ = HP + (size_t)J * rc * 64;
+    auto vec_load = [&](int64_t n) -> double {
+      if (tid >= VB || n >= r1) return 0.0;
+      if (tid < QC) return wrow[n * QC + tid];
+      if (tid < QC + 64) return hI[n * 64 + (tid - QC)];
+      return hJ[n * 64 + (tid - QC - 64)];
+    };
+    if (r0 < r1 && tid < VB) sV[(r0 % 3) * VB + tid] = vec_load(r0);
+    double pacc[2][4][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) pacc[i][j][0] = pacc[i][j][1] = 0.0;
+    __syncthreads();
+
+    for (int64_t n = r0; n < r1; ++n) {
+      const double* v = sV + (n % 3) * VB;
+      double nxt = vec_load(n + 1);               // row n+1 vectors, stored after stage 1
+      double acc[2][4][2];
+      stage1<QC>(sZI, sZJ, v, qk, wr, wc, lane, acc);
+      if (tid < VB) sV[((n + 1) % 3) * VB + tid] = nxt;
+      const double* vI = v + QC + 16 * wr + g;
+      const double* vJ = v + QC + 64 + 32 * wc + 2 * t;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const double hi = vI[8 * i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const double2 hj = *reinterpret_cast<const double2*>(vJ + 8 * j);
+          pacc[i][j][0] += exp_neg(hi + hj.x - acc[i][j][0]);
+          pacc[i][j][1] += exp_neg(hi + hj.y - acc[i][j][1]);
+        }
+      }
+      __syncthreads();                            // slot (n+1)%3 visible; slot n%3 reusable at n+3
+    }
+    // flush this CTA's partial tile
+    double* out = P2p + ((size_t)b * R + blockIdx.x) * 4096;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int m = 16 * wr + 8 * i + g, mp = 32 * wc + 8 * j + 2 * t;
+        *reinterpret_cast<double2*>(out + m * 64 + mp) = make_double2(pacc[i][j][0], pacc[i][j][1]);
+      }
+  }
+}
+
+// =====================================================================================
+// Backward.  grid = (R, G).  Outputs
+//   lam [g][rc][Mp]  += row / column sums of L        (red.global.add, buffers pre-zeroed)
+//   Wq  [g][rc][QC]  += (1 or 2) * sum_m Z'_mq T[m,q]
+//   ACCp[cta][Mp][QC] += sum_n w_nq (L_n Z')[m,q]      (CTA-private, plain RMW)
+// =====================================================================================
+template <int QC>
+__global__ void __launch_bounds__(P2_THREADS, 1)
+k_psi2_bwd(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __restrict__ Zt,
+           const double* __restrict__ Ct, const double* __restrict__ wrow,
+           const double* __restrict__ HP, double* __restrict__ lam, double* __restrict__ Wq,
+           double* __restrict__ ACCp) {
+  using C = P2Cfg<QC>;
+  constexpr int RS = C::RS, VB = C::VB, NJ = C::NJ;
+  extern __shared__ __align__(16) double smem[];
+  double* sZI = smem;
+  double* sZJ = sZI + 64 * RS;
+  double* sL = sZJ + 64 * RS;                     // 2 slots of 64*RSL
+  double* sV = sL + 2 * 64 * RSL;                 // 3 slots of VB
+  double* sWq = sV + 3 * VB;                      // [2][4][QC]
+  double* sLr = sWq + 2 * 4 * QC;                 // [2][2][64]  row-sum partials (per wc)
+  double* sLc = sLr + 2 * 2 * 64;                 // [2][4][64]  col-sum partials (per wr)
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int wr = wid >> 1, wc = wid & 1, g = lane >> 2, t = lane & 3;
+  const int R = gridDim.x, G = gridDim.y;
+  const int64_t per = (rc + R - 1) / R;
+  const int64_t r0 = per * blockIdx.x, r1 = (r0 + per < rc) ? r0 + per : rc;
+  const int cta = blockIdx.y * R + blockIdx.x;
+  double* lamg = lam + (size_t)blockIdx.y * rc * Mp;
+  double* Wqg = Wq + (size_t)blockIdx.y * rc * QC;
+  double* accp = ACCp + (size_t)cta * Mp * QC;
+  const int qbase = wc * (QC / 2);                // this warp's q columns in stage 2
+
+  int curI = -1, curJ = -1;
+  for (int b = blockIdx.y; b < nblocks; b += G) {
+    int I, J;
+    block_ij(b, nt, I, J);
+    const bool diag = (I == J);
+    __syncthreads();
+    if (I != curI) copy_tile<64 * RS>(sZI, Zt + (size_t)I * 64 * RS, tid);
+    if (J != curJ) copy_tile<64 * RS>(sZJ, Zt + (size_t)J * 64 * RS, tid);
+    curI = I;
+    curJ = J;
+    const double* hI = HP + (size_t)I * rc * 64;
+    const double* hJ = HP + (size_t)J * rc * 64;
+    auto vec_load = [&](int64_t n) -> double {
+      if (tid >= VB || n >= r1) return 0.0;
+      if (tid < QC) return wrow[n * QC + tid];
+      if (tid < QC + 64) return hI[n * 64 + (tid - QC)];
+      return hJ[n * 64 + (tid - QC - 64)];
+    };
+    if (r0 < r1 && tid < VB) sV[(r0 % 3) * VB + tid] = vec_load(r0);
+    // C = s2^2 sym(dL_dpsi2) for this thread's 16 pair positions
+    double creg[2][4][2];
+    {
+      const double* cb = Ct + (size_t)b * 4096;
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          double2 c2 = *reinterpret_cast<const double2*>(cb + (16 * wr + 8 * i + g) * 64 + 32 * wc + 8 * j + 2 * t);
+          creg[i][j][0] = c2.x;
+          creg[i][j][1] = c2.y;
+        }
+    }
+    double accI[2][NJ][2], accJ[2][NJ][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) accI[i][j][0] = accI[i][j][1] = accJ[i][j][0] = accJ[i][j][1] = 0.0;
+    __syncthreads();
+
+    // Cross-warp reductions, deferred past a barrier (two slots each, see the hazard
+    // analysis in DESIGN.md "Row pipeline"): lambda partials of row n are complete at the
+    // barrier of row n and flushed right after it; the Wq partials of row n are written
+    // after that barrier and flushed after the barrier of row n+1.
+    auto flush_lam = [&](int64_t n) {
+      const int s = (int)(n & 1);
+      if (tid >= 64 && tid < 128) {
+        const int m = tid - 64;
+        const double* p = sLr + s * 128 + m;
+        red_add(lamg + n * Mp + I * 64 + m, p[0] + p[64]);
+      } else if (tid >= 128 && tid < 192 && !diag) {
+        const int m = tid - 128;
+        const double* p = sLc + s * 256 + m;
+        red_add(lamg + n * Mp + J * 64 + m, p[0] + p[64] + p[128] + p[192]);
+      }
+    };
+    auto flush_wq = [&](int64_t n) {
+      const int s = (int)(n & 1);
+      if (tid < QC) {
+        const double* p = sWq + s * 4 * QC + tid;
+        double v = p[0] + p[QC] + p[2 * QC] + p[3 * QC];
+        red_add(Wqg + n * QC + tid, diag ? v : 2.0 * v);
+      }
+    };
+
+    for (int64_t n = r0; n < r1; ++n) {
+      const int s = (int)(n & 1);
+      const double* v = sV + (n % 3) * VB;
+      double* Lb = sL + s * 64 * RSL;
+      double nxt = vec_load(n + 1);
+      // ---------------- stage 1 + epilogue -> L tile, lambda partials
+      {
+        double acc[2][4][2];
+        stage1<QC>(sZI, sZJ, v, qk, wr, wc, lane, acc);
+        if (tid < VB) sV[((n + 1) % 3) * VB + tid] = nxt;
+        const double* vI = v + QC + 16 * wr + g;
+        const double* vJ = v + QC + 64 + 32 * wc + 2 * t;
+        double rs[2] = {0.0, 0.0};
+        double cs[4][2];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cs[j][0] = cs[j][1] = 0.0;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const double hi = vI[8 * i];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const double2 hj = *reinterpret_cast<const double2*>(vJ + 8 * j);
+            double l0 = creg[i][j][0] * exp_neg(hi + hj.x - acc[i][j][0]);
+            double l1 = creg[i][j][1] * exp_neg(hi + hj.y - acc[i][j][1]);
+            *reinterpret_cast<double2*>(Lb + (16 * wr + 8 * i + g) * RSL + 32 * wc + 8 * j + 2 * t) =
+                make_double2(l0, l1);
+            rs[i] += l0 + l1;
+            cs[j][0] += l0;
+            cs[j][1] += l1;
+          }
+        }
+        // row sums: reduce over the 4 lanes of a quad (t); col sums: over the 8 quads (g)
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], 1);
+          rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], 2);
+        }
+        if (t == 0) {
+          sLr[s * 128 + wc * 64 + 16 * wr + g] = rs[0];
+          sLr[s * 128 + wc * 64 + 16 * wr + 8 + g] = rs[1];
+        }
+        if (!diag) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              double c = cs[j][e];
+              c += __shfl_xor_sync(0xffffffffu, c, 4);
+              c += __shfl_xor_sync(0xffffffffu, c, 8);
+              c += __shfl_xor_sync(0xffffffffu, c, 16);
+              cs[j][e] = c;
+            }
+          if (g == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              sLc[s * 256 + wr * 64 + 32 * wc + 8 * j + 2 * t] = cs[j][0];
+              sLc[s * 256 + wr * 64 + 32 * wc + 8 * j + 2 * t + 1] = cs[j][1];
+            }
+          }
+        }
+      }
+      __syncthreads();   // L tile + partials of row n complete; everything of row n-1 finished
+      flush_lam(n);
+      if (n > r0) flush_wq(n - 1);
+      // ---------------- stage 2-I: T = L ZJ ; accI += w T ; Wq partial
+      {
+        double T[2][NJ][2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) T[i][j][0] = T[i][j][1] = 0.0;
+        const double* pa = Lb + (16 * wr + g) * RSL + t;          // A = L  (rows m, k = m')
+        const double* pb = sZJ + t * RS + qbase + g;              // B = ZJ (k = m', cols q)
+#pragma unroll 2
+        for (int k0 = 0; k0 < 64; k0 += 4) {
+          double a[2], bq[NJ];
+#pragma unroll
+          for (int i = 0; i < 2; ++i) a[i] = pa[i * 8 * RSL + k0];
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) bq[j] = pb[k0 * RS + 8 * j];
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) dmma(T[i][j][0], T[i][j][1], a[i], bq[j]);
+        }
+        // fold into the persistent accumulator and form the Wq partial
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          const int q = qbase + 8 * j + 2 * t;
+          const double2 wq = *reinterpret_cast<const double2*>(v + q);
+          double w0 = 0.0, w1 = 0.0;
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const double2 z = *reinterpret_cast<const double2*>(sZI + (16 * wr + 8 * i + g) * RS + q);
+            accI[i][j][0] = fma(wq.x, T[i][j][0], accI[i][j][0]);
+            accI[i][j][1] = fma(wq.y, T[i][j][1], accI[i][j][1]);
+            w0 = fma(z.x, T[i][j][0], w0);
+            w1 = fma(z.y, T[i][j][1], w1);
+          }
+          w0 += __shfl_xor_sync(0xffffffffu, w0, 4);
+          w1 += __shfl_xor_sync(0xffffffffu, w1, 4);
+          w0 += __shfl_xor_sync(0xffffffffu, w0, 8);
+          w1 += __shfl_xor_sync(0xffffffffu, w1, 8);
+          w0 += __shfl_xor_sync(0xffffffffu, w0, 16);
+          w1 += __shfl_xor_sync(0xffffffffu, w1, 16);
+          if (g == 0) *reinterpret_cast<double2*>(sWq + s * 4 * QC + wr * QC + q) = make_double2(w0, w1);
+        }
+      }
+      // ---------------- stage 2-J: accJ[m',q] += sum_m L[m,m'] (w_q ZI[m,q])
+      if (!diag) {
+        const double* pa = Lb + t * RSL + 16 * wr + g;            // A = L^T (rows m', k = m)
+        const double* pb = sZI + t * RS + qbase + g;              // B = ZI (k = m, cols q)
+        double wq[NJ];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) wq[j] = v[qbase + 8 * j + g];
+#pragma unroll 2
+        for (int k0 = 0; k0 < 64; k0 += 4) {
+          double a[2], bq[NJ];
+#pragma unroll
+          for (int i = 0; i < 2; ++i) a[i] = pa[k0 * RSL + 8 * i];
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) bq[j] = pb[k0 * RS + 8 * j] * wq[j];
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) dmma(accJ[i][j][0], accJ[i][j][1], a[i], bq[j]);
+        }
+      }
+    }
+    __syncthreads();
+    if (r1 > r0) flush_wq(r1 - 1);
+    // flush the CTA-private dZ accumulators of this block
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int q = qbase + 8 * j + 2 * t;
+        double2* pI = reinterpret_cast<double2*>(accp + (size_t)(I * 64 + 16 * wr + 8 * i + g) * QC + q);
+        double2 o = *pI;
+        o.x += accI[i][j][0];
+        o.y += accI[i][j][1];
+        *pI = o;
+        if (!diag) {
+          double2* pJ = reinterpret_cast<double2*>(accp + (size_t)(J * 64 + 16 * wr + 8 * i + g) * QC + q);
+          double2 u = *pJ;
+          u.x += accJ[i][j][0];
+          u.y += accJ[i][j][1];
+          *pJ = u;
+        }
+      }
+  }
+}
+
+}  // namespace fast
+}  // namespace rgp
