@@ -7,8 +7,8 @@
 // e = 1/(S+l^2):
 //   log Psi1[n,m]/s2 = b1_n + sum_q [ (e mu')_q Z'_mq - 1/2 e_q Z'_mq^2 ]
 //        b1_n = -1/2 sum_q log1p(S/l^2) - 1/2 sum_q e mu'^2
-//   log P_n[m,m']/s2^2 = H_nm + H_nm' - sum_q w_nq Z'_mq Z'_m'q
-//        w_nq = -S/(l^2 (2S+l^2))            ( = d/2 - 1/(2 l^2) )
+//   log P_n[m,m']/s2^2 = H_nm + H_nm' + sum_q ws_nq Z'_mq Z'_m'q
+//        ws_nq = S/(l^2 (2S+l^2)) >= 0       ( = -w,  w = d/2 - 1/(2 l^2) )
 //        H_nm = b2_n + sum_q [ (d mu')_q Z'_mq - 1/4 (d_q + 1/l_q^2) Z'_mq^2 ]
 //        b2_n = -1/4 sum_q log1p(2S/l^2) - 1/2 sum_q d mu'^2
 // so the Z-Z' term of SURVEY.md 8(a3) is absorbed into w and H and needs no separate
@@ -65,7 +65,7 @@ __global__ void k_build_C(int M, int nt, const double* __restrict__ dL, double v
   }
 }
 
-// One warp per row.  Writes w[n][QC], A2[n][2QC] = [d mu' | -1/4 (d+1/l2)], b2[n],
+// One warp per row.  Writes ws[n][QC] (= -w), A2[n][2QC] = [d mu' | -1/4 (d+1/l2)], b2[n],
 // and (if A1) A1[n][2QC] = [e mu' | -1/2 e], b1[n].
 __global__ void k_rowprep(int64_t N, int Q, int QC, const double* __restrict__ mu,
                           const double* __restrict__ S, const double* __restrict__ ell,
@@ -82,7 +82,7 @@ __global__ void k_rowprep(int64_t N, int Q, int QC, const double* __restrict__ m
       double l = ell[q], l2 = l * l;
       double s = S[n * Q + q], m = mu[n * Q + q] - o[q];
       double den = 2.0 * s + l2, d = 1.0 / den;
-      wv = -s / (l2 * den);
+      wv = s / (l2 * den);                      // ws = -w >= 0
       a2a = d * m;
       a2b = -0.25 * (d + 1.0 / l2);
       lg2 += log1p(2.0 * s / l2);
@@ -285,7 +285,8 @@ __global__ void __launch_bounds__(128) k_rows_finalize(
 }
 
 // Final small combine for one row chunk (outputs accumulate across chunks):
-//   dZ[m,q]  += 2 Gl[m,q] + 4 Z'[m,q] Gl[m,QC+q] - 2 ACC[m,q]  +  GL[m,q] + 2 Z' GL[m,QC+q]
+//   dZ[m,q]  += 2 Gl[m,q] + 4 Z'[m,q] Gl[m,QC+q] + 2 ACC[m,q]  +  GL[m,q] + 2 Z' GL[m,QC+q]
+//   (ACC = sum_n ws (L_n Z') = -sum_n w (L_n Z'), hence the plus sign)
 //   dell[q]  += sum_cta part[cta][q];   dvar += sum_cta part[cta][QC]
 // Gl / GL are split-K partials [splits][Mp][2QC]; ACC partials [ncta][Mp][QC].
 __global__ void k_final_small(int M, int Mp, int Q, int QC, const double* __restrict__ ZB,
@@ -310,7 +311,7 @@ __global__ void k_final_small(int M, int Mp, int Q, int QC, const double* __rest
         Gb += GL[((int64_t)s * Mp + m) * 2 * QC + QC + q];
       }
     for (int c = 0; c < ncta; ++c) acc += ACCp[((int64_t)c * Mp + m) * QC + q];
-    dZ[idx] += 2.0 * ga + 4.0 * z * gb - 2.0 * acc + Ga + 2.0 * z * Gb;
+    dZ[idx] += 2.0 * ga + 4.0 * z * gb + 2.0 * acc + Ga + 2.0 * z * Gb;
   }
   if (idx < Q + 1) {
     int col = (idx < Q) ? idx : QC;

@@ -4,13 +4,14 @@
 // triangle).  A CTA owns a contiguous row range [r0, r1) and walks the blocks of its
 // block group; for every block it streams its rows ONE ROW AT A TIME:
 //
-//   stage 1   G[m,m'] = sum_q (w_nq Z'_mq) Z'_m'q                 64 x 64 x Q   (DMMA)
-//   epilogue  p = exp(H_nm + H_nm' - G)                            4096 exps
+//   stage 1   E[m,m'] = H_nm + H_nm' + sum_q (ws_nq Z'_mq) Z'_m'q   64 x 64 x Q   (DMMA)
+//             (ws = -w >= 0, so E is the exponent itself)
+//   epilogue  p = exp(E)                                           4096 exps
 //             forward : Psi2 tile += p                (register accumulators)
 //             backward: L = C[m,m'] * p -> shared     (C = s2^2 * sym(dL_dpsi2), registers)
 //   stage 2-I T[m,q]   = sum_m' L[m,m'] Z'_m'q                     64 x Q x 64   (DMMA)
-//             accI[m,q] += w_nq T[m,q];   Wq[n,q] += sum_m Z'_mq T[m,q]
-//   stage 2-J accJ[m',q] += sum_m L[m,m'] (w_nq Z'_mq)             64 x Q x 64   (DMMA)
+//             accI[m,q] += ws_nq T[m,q];   Wq[n,q] += sum_m Z'_mq T[m,q]
+//   stage 2-J accJ[m',q] += sum_m L[m,m'] (ws_nq Z'_mq)             64 x Q x 64   (DMMA)
 //
 // (diagonal blocks skip stage 2-J).  Row sums / column sums of L give lambda_nm.  The
 // O(M*Q)-per-row remainder of the gradient algebra is in fast_prep.cuh.
@@ -69,19 +70,29 @@ RGP_DEVINL void copy_tile(double* dst, const double* __restrict__ src, int tid) 
   for (int i = tid; i < COUNT / 2; i += P2_THREADS) d2[i] = s2[i];
 }
 
-// stage 1: acc[2][4][2] = sum_q (w_q ZI[m][q]) ZJ[m'][q] for this warp's 16 x 32 sub-block
+// stage 1: acc[2][4][2] = H_m + H_m' + sum_q (ws_q ZI[m][q]) ZJ[m'][q]  (= the exponent) for this
+// warp's 16 x 32 sub-block; ws = -w = S/(l^2 (2S+l^2)) >= 0 is what the row vector holds.
 template <int QC>
 RGP_DEVINL void stage1(const double* __restrict__ sZI, const double* __restrict__ sZJ,
-                       const double* __restrict__ sw, int qk, int wr, int wc, int lane,
+                       const double* __restrict__ v, int qk, int wr, int wc, int lane,
                        double (&acc)[2][4][2]) {
   constexpr int RS = P2Cfg<QC>::RS;
   const int g = lane >> 2, t = lane & 3;
   const double* pa = sZI + (16 * wr + g) * RS + t;
   const double* pb = sZJ + (32 * wc + g) * RS + t;
+  const double* sw = v;
+  const double* vI = v + QC + 16 * wr + g;
+  const double* vJ = v + QC + 64 + 32 * wc + 2 * t;
 #pragma unroll
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < 2; ++i) {
+    const double hi = vI[8 * i];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < 4; ++j) {
+      const double2 hj = *reinterpret_cast<const double2*>(vJ + 8 * j);
+      acc[i][j][0] = hi + hj.x;
+      acc[i][j][1] = hi + hj.y;
+    }
+  }
 #pragma unroll 2
   for (int k0 = 0; k0 < qk; k0 += 4) {
     const double wv = sw[k0 + t];
@@ -150,18 +161,13 @@ k_psi2_fwd(int64_t rc, int nt, int nblocks, int qk, const double* __restrict__ Z
       double acc[2][4][2];
       stage1<QC>(sZI, sZJ, v, qk, wr, wc, lane, acc);
       if (tid < VB) sV[((n + 1) % 3) * VB + tid] = nxt;
-      const double* vI = v + QC + 16 * wr + g;
-      const double* vJ = v + QC + 64 + 32 * wc + 2 * t;
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const double hi = vI[8 * i];
+      for (int i = 0; i < 2; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const double2 hj = *reinterpret_cast<const double2*>(vJ + 8 * j);
-          pacc[i][j][0] += exp_neg(hi + hj.x - acc[i][j][0]);
-          pacc[i][j][1] += exp_neg(hi + hj.y - acc[i][j][1]);
+          pacc[i][j][0] += exp_neg(acc[i][j][0]);
+          pacc[i][j][1] += exp_neg(acc[i][j][1]);
         }
-      }
       __syncthreads();                            // slot (n+1)%3 visible; slot n%3 reusable at n+3
     }
     // flush this CTA's partial tile
@@ -180,7 +186,7 @@ k_psi2_fwd(int64_t rc, int nt, int nblocks, int qk, const double* __restrict__ Z
 // Backward.  grid = (R, G).  Outputs
 //   lam [g][rc][Mp]  += row / column sums of L        (red.global.add, buffers pre-zeroed)
 //   Wq  [g][rc][QC]  += (1 or 2) * sum_m Z'_mq T[m,q]
-//   ACCp[cta][Mp][QC] += sum_n w_nq (L_n Z')[m,q]      (CTA-private, plain RMW)
+//   ACCp[cta][Mp][QC] += sum_n ws_nq (L_n Z')[m,q]     (CTA-private, plain RMW)
 // =====================================================================================
 template <int QC>
 __global__ void __launch_bounds__(P2_THREADS, 1)
@@ -284,20 +290,16 @@ k_psi2_bwd(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __rest
         double acc[2][4][2];
         stage1<QC>(sZI, sZJ, v, qk, wr, wc, lane, acc);
         if (tid < VB) sV[((n + 1) % 3) * VB + tid] = nxt;
-        const double* vI = v + QC + 16 * wr + g;
-        const double* vJ = v + QC + 64 + 32 * wc + 2 * t;
         double rs[2] = {0.0, 0.0};
         double cs[4][2];
 #pragma unroll
         for (int j = 0; j < 4; ++j) cs[j][0] = cs[j][1] = 0.0;
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-          const double hi = vI[8 * i];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const double2 hj = *reinterpret_cast<const double2*>(vJ + 8 * j);
-            double l0 = creg[i][j][0] * exp_neg(hi + hj.x - acc[i][j][0]);
-            double l1 = creg[i][j][1] * exp_neg(hi + hj.y - acc[i][j][1]);
+            double l0 = creg[i][j][0] * exp_neg(acc[i][j][0]);
+            double l1 = creg[i][j][1] * exp_neg(acc[i][j][1]);
             *reinterpret_cast<double2*>(Lb + (16 * wr + 8 * i + g) * RSL + 32 * wc + 8 * j + 2 * t) =
                 make_double2(l0, l1);
             rs[i] += l0 + l1;

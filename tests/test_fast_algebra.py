@@ -16,7 +16,7 @@ def fast_model(variance, ell, Z, mu, S, dL0, dL1, dL2):
     o = Z.mean(axis=0)                                    # k_center
     Zc, mc = Z - o, mu - o
     d, e = 1.0 / (2 * S + l2), 1.0 / (S + l2)             # k_rowprep
-    w = -S / (l2 * (2 * S + l2))
+    ws = S / (l2 * (2 * S + l2))                          # = -w >= 0
     A2 = np.hstack([d * mc, -0.25 * (d + 1 / l2)])
     A1 = np.hstack([e * mc, -0.5 * e])
     b2 = -0.25 * np.log1p(2 * S / l2).sum(1) - 0.5 * (d * mc * mc).sum(1)
@@ -30,13 +30,13 @@ def fast_model(variance, ell, Z, mu, S, dL0, dL1, dL2):
     psi2 = np.zeros((M, M))
     lam = np.zeros((N, M)); Wq = np.zeros((N, Q)); ACC = np.zeros((M, Q))
     for n in range(N):                                    # k_psi2_fwd / k_psi2_bwd, one row at a time
-        G = (Zc * w[n]) @ Zc.T                            # stage 1
-        P = np.exp(H[n][:, None] + H[n][None, :] - G)     # epilogue
+        E = H[n][:, None] + H[n][None, :] + (Zc * ws[n]) @ Zc.T   # stage 1 (accumulator init + DMMA)
+        P = np.exp(E)                                     # epilogue
         psi2 += P
         L = C * P
         lam[n] = L.sum(1)
         T = L @ Zc                                        # stage 2
-        ACC += w[n] * T
+        ACC += ws[n] * T
         Wq[n] = (Zc * T).sum(0)
     psi2 *= variance ** 2                                 # k_psi2_reduce
     R2, R1 = lam @ ZB, L1 @ ZB                            # rows_gemm
@@ -50,7 +50,7 @@ def fast_model(variance, ell, Z, mu, S, dL0, dL1, dL2):
           + ell * e * (e * B1 + (S / l2) * Lam1)).sum(0)
     dvar = ((2 * Lam + Lam1) / variance).sum() + dL0.sum()
     Gl, GL = lam.T @ A2, L1.T @ A1                        # dz_gemm
-    dZ = 2 * Gl[:, :Q] + 4 * Zc * Gl[:, Q:] - 2 * ACC + GL[:, :Q] + 2 * Zc * GL[:, Q:]   # k_final_small
+    dZ = 2 * Gl[:, :Q] + 4 * Zc * Gl[:, Q:] + 2 * ACC + GL[:, :Q] + 2 * Zc * GL[:, Q:]   # k_final_small
     return (np.full(N, variance), psi1, psi2), (dvar, dl, dZ, dmu, dS)
 
 
