@@ -108,9 +108,50 @@ RGP_DEVINL void stage1(const double* __restrict__ sZI, const double* __restrict_
   }
 }
 
+// Diagonal blocks (I == J) are symmetric: only the 36 upper-triangle 8x8 tiles of the 8x8
+// tile grid are computed (warps 0-3 own 5 tiles, warps 4-7 own 4) and mirrored on store.
+RGP_DEVINL void diag_tiles(int wid, int (&ti)[5], int (&tj)[5], int& cnt) {
+  const int first = wid < 4 ? 5 * wid : 20 + 4 * (wid - 4);
+  cnt = wid < 4 ? 5 : 4;
+#pragma unroll
+  for (int s = 0; s < 5; ++s) {
+    int idx = first + (s < cnt ? s : cnt - 1);
+    int r = 0, off = 0;
+    while (idx >= off + 8 - r) { off += 8 - r; ++r; }
+    ti[s] = r;
+    tj[s] = r + idx - off;
+  }
+}
+
+template <int QC>
+RGP_DEVINL void stage1_diag(const double* __restrict__ sZ, const double* __restrict__ v, int qk,
+                            const int (&ti)[5], const int (&tj)[5], int cnt, int lane,
+                            double (&acc)[5][2]) {
+  constexpr int RS = P2Cfg<QC>::RS;
+  const int g = lane >> 2, t = lane & 3;
+  const double* pa[5];
+  const double* pb[5];
+#pragma unroll
+  for (int s = 0; s < 5; ++s) {
+    pa[s] = sZ + (8 * ti[s] + g) * RS + t;
+    pb[s] = sZ + (8 * tj[s] + g) * RS + t;
+    const double hi = v[QC + 8 * ti[s] + g];
+    const double2 hj = *reinterpret_cast<const double2*>(v + QC + 8 * tj[s] + 2 * t);
+    acc[s][0] = hi + hj.x;
+    acc[s][1] = hi + hj.y;
+  }
+#pragma unroll 2
+  for (int k0 = 0; k0 < qk; k0 += 4) {
+    const double wv = v[k0 + t];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) dmma(acc[s][0], acc[s][1], pa[s][k0] * wv, pb[s][k0]);
+    if (cnt == 5) dmma(acc[4][0], acc[4][1], pa[4][k0] * wv, pb[4][k0]);
+  }
+}
+
 // =====================================================================================
 // Forward: partial Psi2 tiles.  grid = (R row ranges, G block groups).
-//   P2p[b][r][64][64] = sum_{n in range r} exp(H_nm + H_nm' - G_n[m,m'])     (no s2^2 yet)
+//   P2p[b][r][64][64] = sum_{n in range r} exp(E_n[m,m'])                    (no s2^2 yet)
 // =====================================================================================
 template <int QC>
 __global__ void __launch_bounds__(P2_THREADS, 2)
@@ -134,6 +175,7 @@ k_psi2_fwd(int64_t rc, int nt, int nblocks, int qk, const double* __restrict__ Z
   for (int b = blockIdx.y; b < nblocks; b += G) {
     int I, J;
     block_ij(b, nt, I, J);
+    const bool diag = (I == J);
     __syncthreads();                              // previous block fully done with smem
     if (I != curI) copy_tile<64 * RS>(sZI, Zt + (size_t)I * 64 * RS, tid);
     if (J != curJ) copy_tile<64 * RS>(sZJ, Zt + (size_t)J * 64 * RS, tid);
@@ -148,37 +190,68 @@ k_psi2_fwd(int64_t rc, int nt, int nblocks, int qk, const double* __restrict__ Z
       return hJ[n * 64 + (tid - QC - 64)];
     };
     if (r0 < r1 && tid < VB) sV[(r0 % 3) * VB + tid] = vec_load(r0);
-    double pacc[2][4][2];
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) pacc[i][j][0] = pacc[i][j][1] = 0.0;
     __syncthreads();
+    double* out = P2p + ((size_t)b * R + blockIdx.x) * 4096;
 
-    for (int64_t n = r0; n < r1; ++n) {
-      const double* v = sV + (n % 3) * VB;
-      double nxt = vec_load(n + 1);               // row n+1 vectors, stored after stage 1
-      double acc[2][4][2];
-      stage1<QC>(sZI, sZJ, v, qk, wr, wc, lane, acc);
-      if (tid < VB) sV[((n + 1) % 3) * VB + tid] = nxt;
+    if (!diag) {
+      double pacc[2][4][2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pacc[i][j][0] = pacc[i][j][1] = 0.0;
+      for (int64_t n = r0; n < r1; ++n) {
+        const double* v = sV + (n % 3) * VB;
+        double nxt = vec_load(n + 1);             // row n+1 vectors, stored after stage 1
+        double acc[2][4][2];
+        stage1<QC>(sZI, sZJ, v, qk, wr, wc, lane, acc);
+        if (tid < VB) sV[((n + 1) % 3) * VB + tid] = nxt;
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            pacc[i][j][0] += exp_neg(acc[i][j][0]);
+            pacc[i][j][1] += exp_neg(acc[i][j][1]);
+          }
+        __syncthreads();                          // slot (n+1)%3 visible
+      }
 #pragma unroll
       for (int i = 0; i < 2; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          pacc[i][j][0] += exp_neg(acc[i][j][0]);
-          pacc[i][j][1] += exp_neg(acc[i][j][1]);
+          int m = 16 * wr + 8 * i + g, mp = 32 * wc + 8 * j + 2 * t;
+          *reinterpret_cast<double2*>(out + m * 64 + mp) = make_double2(pacc[i][j][0], pacc[i][j][1]);
         }
-      __syncthreads();                            // slot (n+1)%3 visible; slot n%3 reusable at n+3
-    }
-    // flush this CTA's partial tile
-    double* out = P2p + ((size_t)b * R + blockIdx.x) * 4096;
+    } else {
+      int ti[5], tj[5], cnt;
+      diag_tiles(wid, ti, tj, cnt);
+      double pacc[5][2];
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
+      for (int s = 0; s < 5; ++s) pacc[s][0] = pacc[s][1] = 0.0;
+      for (int64_t n = r0; n < r1; ++n) {
+        const double* v = sV + (n % 3) * VB;
+        double nxt = vec_load(n + 1);
+        double acc[5][2];
+        stage1_diag<QC>(sZI, v, qk, ti, tj, cnt, lane, acc);
+        if (tid < VB) sV[((n + 1) % 3) * VB + tid] = nxt;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        int m = 16 * wr + 8 * i + g, mp = 32 * wc + 8 * j + 2 * t;
-        *reinterpret_cast<double2*>(out + m * 64 + mp) = make_double2(pacc[i][j][0], pacc[i][j][1]);
+        for (int s = 0; s < 5; ++s)
+          if (s < cnt) {
+            pacc[s][0] += exp_neg(acc[s][0]);
+            pacc[s][1] += exp_neg(acc[s][1]);
+          }
+        __syncthreads();
       }
+#pragma unroll
+      for (int s = 0; s < 5; ++s)
+        if (s < cnt) {
+          const int m = 8 * ti[s] + g, mp = 8 * tj[s] + 2 * t;
+          *reinterpret_cast<double2*>(out + m * 64 + mp) = make_double2(pacc[s][0], pacc[s][1]);
+          if (ti[s] != tj[s]) {
+            out[mp * 64 + m] = pacc[s][0];
+            out[(mp + 1) * 64 + m] = pacc[s][1];
+          }
+        }
+    }
   }
 }
 
@@ -228,6 +301,7 @@ k_psi2_bwd(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __rest
     curJ = J;
     const double* hI = HP + (size_t)I * rc * 64;
     const double* hJ = HP + (size_t)J * rc * 64;
+    const double* cb = Ct + (size_t)b * 4096;     // C = s2^2 sym(dL_dpsi2) on this block
     auto vec_load = [&](int64_t n) -> double {
       if (tid >= VB || n >= r1) return 0.0;
       if (tid < QC) return wrow[n * QC + tid];
@@ -235,19 +309,6 @@ k_psi2_bwd(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __rest
       return hJ[n * 64 + (tid - QC - 64)];
     };
     if (r0 < r1 && tid < VB) sV[(r0 % 3) * VB + tid] = vec_load(r0);
-    // C = s2^2 sym(dL_dpsi2) for this thread's 16 pair positions
-    double creg[2][4][2];
-    {
-      const double* cb = Ct + (size_t)b * 4096;
-#pragma unroll
-      for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          double2 c2 = *reinterpret_cast<const double2*>(cb + (16 * wr + 8 * i + g) * 64 + 32 * wc + 8 * j + 2 * t);
-          creg[i][j][0] = c2.x;
-          creg[i][j][1] = c2.y;
-        }
-    }
     double accI[2][NJ][2], accJ[2][NJ][2];
 #pragma unroll
     for (int i = 0; i < 2; ++i)
@@ -255,22 +316,8 @@ k_psi2_bwd(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __rest
       for (int j = 0; j < NJ; ++j) accI[i][j][0] = accI[i][j][1] = accJ[i][j][0] = accJ[i][j][1] = 0.0;
     __syncthreads();
 
-    // Cross-warp reductions, deferred past a barrier (two slots each, see the hazard
-    // analysis in DESIGN.md "Row pipeline"): lambda partials of row n are complete at the
-    // barrier of row n and flushed right after it; the Wq partials of row n are written
-    // after that barrier and flushed after the barrier of row n+1.
-    auto flush_lam = [&](int64_t n) {
-      const int s = (int)(n & 1);
-      if (tid >= 64 && tid < 128) {
-        const int m = tid - 64;
-        const double* p = sLr + s * 128 + m;
-        red_add(lamg + n * Mp + I * 64 + m, p[0] + p[64]);
-      } else if (tid >= 128 && tid < 192 && !diag) {
-        const int m = tid - 128;
-        const double* p = sLc + s * 256 + m;
-        red_add(lamg + n * Mp + J * 64 + m, p[0] + p[64] + p[128] + p[192]);
-      }
-    };
+    // Wq partials of row n are written after the barrier of row n and flushed after the
+    // barrier of row n+1 (two slots; hazard analysis in DESIGN.md "Row pipeline").
     auto flush_wq = [&](int64_t n) {
       const int s = (int)(n & 1);
       if (tid < QC) {
@@ -280,44 +327,97 @@ k_psi2_bwd(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __rest
       }
     };
 
-    for (int64_t n = r0; n < r1; ++n) {
-      const int s = (int)(n & 1);
-      const double* v = sV + (n % 3) * VB;
-      double* Lb = sL + s * 64 * RSL;
-      double nxt = vec_load(n + 1);
-      // ---------------- stage 1 + epilogue -> L tile, lambda partials
-      {
-        double acc[2][4][2];
-        stage1<QC>(sZI, sZJ, v, qk, wr, wc, lane, acc);
-        if (tid < VB) sV[((n + 1) % 3) * VB + tid] = nxt;
-        double rs[2] = {0.0, 0.0};
-        double cs[4][2];
+    // stage 2-I: T = L ZJ ; accI += ws T ; Wq partial.  A = L (rows m, k = m'), B = ZJ (k = m', cols q)
+    auto stage2I = [&](const double* v, const double* Lb, int s) {
+      double T[2][NJ][2];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) cs[j][0] = cs[j][1] = 0.0;
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) T[i][j][0] = T[i][j][1] = 0.0;
+      const double* pa = Lb + (16 * wr + g) * RSL + t;
+      const double* pb = sZJ + t * RS + qbase + g;
+#pragma unroll 2
+      for (int k0 = 0; k0 < 64; k0 += 4) {
+        double a[2], bq[NJ];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) a[i] = pa[i * 8 * RSL + k0];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) bq[j] = pb[k0 * RS + 8 * j];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) dmma(T[i][j][0], T[i][j][1], a[i], bq[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int q = qbase + 8 * j + 2 * t;
+        const double2 wq = *reinterpret_cast<const double2*>(v + q);
+        double w0 = 0.0, w1 = 0.0;
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
+          const double2 z = *reinterpret_cast<const double2*>(sZI + (16 * wr + 8 * i + g) * RS + q);
+          accI[i][j][0] = fma(wq.x, T[i][j][0], accI[i][j][0]);
+          accI[i][j][1] = fma(wq.y, T[i][j][1], accI[i][j][1]);
+          w0 = fma(z.x, T[i][j][0], w0);
+          w1 = fma(z.y, T[i][j][1], w1);
+        }
+        w0 += __shfl_xor_sync(0xffffffffu, w0, 4);
+        w1 += __shfl_xor_sync(0xffffffffu, w1, 4);
+        w0 += __shfl_xor_sync(0xffffffffu, w0, 8);
+        w1 += __shfl_xor_sync(0xffffffffu, w1, 8);
+        w0 += __shfl_xor_sync(0xffffffffu, w0, 16);
+        w1 += __shfl_xor_sync(0xffffffffu, w1, 16);
+        if (g == 0) *reinterpret_cast<double2*>(sWq + s * 4 * QC + wr * QC + q) = make_double2(w0, w1);
+      }
+    };
+
+    if (!diag) {
+      // ------------------------------------------------------------ off-diagonal block
+      double creg[2][4][2];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            double l0 = creg[i][j][0] * exp_neg(acc[i][j][0]);
-            double l1 = creg[i][j][1] * exp_neg(acc[i][j][1]);
-            *reinterpret_cast<double2*>(Lb + (16 * wr + 8 * i + g) * RSL + 32 * wc + 8 * j + 2 * t) =
-                make_double2(l0, l1);
-            rs[i] += l0 + l1;
-            cs[j][0] += l0;
-            cs[j][1] += l1;
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          double2 c2 = *reinterpret_cast<const double2*>(cb + (16 * wr + 8 * i + g) * 64 + 32 * wc + 8 * j + 2 * t);
+          creg[i][j][0] = c2.x;
+          creg[i][j][1] = c2.y;
+        }
+      for (int64_t n = r0; n < r1; ++n) {
+        const int s = (int)(n & 1);
+        const double* v = sV + (n % 3) * VB;
+        double* Lb = sL + s * 64 * RSL;
+        double nxt = vec_load(n + 1);
+        {
+          double acc[2][4][2];
+          stage1<QC>(sZI, sZJ, v, qk, wr, wc, lane, acc);
+          if (tid < VB) sV[((n + 1) % 3) * VB + tid] = nxt;
+          double rs[2] = {0.0, 0.0};
+          double cs[4][2];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) cs[j][0] = cs[j][1] = 0.0;
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              double l0 = creg[i][j][0] * exp_neg(acc[i][j][0]);
+              double l1 = creg[i][j][1] * exp_neg(acc[i][j][1]);
+              *reinterpret_cast<double2*>(Lb + (16 * wr + 8 * i + g) * RSL + 32 * wc + 8 * j + 2 * t) =
+                  make_double2(l0, l1);
+              rs[i] += l0 + l1;
+              cs[j][0] += l0;
+              cs[j][1] += l1;
+            }
           }
-        }
-        // row sums: reduce over the 4 lanes of a quad (t); col sums: over the 8 quads (g)
+          // row sums: reduce over the 4 lanes of a quad (t); col sums: over the 8 quads (g)
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], 1);
-          rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], 2);
-        }
-        if (t == 0) {
-          sLr[s * 128 + wc * 64 + 16 * wr + g] = rs[0];
-          sLr[s * 128 + wc * 64 + 16 * wr + 8 + g] = rs[1];
-        }
-        if (!diag) {
+          for (int i = 0; i < 2; ++i) {
+            rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], 1);
+            rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], 2);
+          }
+          if (t == 0) {
+            sLr[s * 128 + wc * 64 + 16 * wr + g] = rs[0];
+            sLr[s * 128 + wc * 64 + 16 * wr + 8 + g] = rs[1];
+          }
 #pragma unroll
           for (int j = 0; j < 4; ++j)
 #pragma unroll
@@ -330,79 +430,92 @@ k_psi2_bwd(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __rest
             }
           if (g == 0) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              sLc[s * 256 + wr * 64 + 32 * wc + 8 * j + 2 * t] = cs[j][0];
-              sLc[s * 256 + wr * 64 + 32 * wc + 8 * j + 2 * t + 1] = cs[j][1];
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<double2*>(sLc + s * 256 + wr * 64 + 32 * wc + 8 * j + 2 * t) =
+                  make_double2(cs[j][0], cs[j][1]);
+          }
+        }
+        __syncthreads();   // L tile + lambda partials of row n complete; row n-1 fully finished
+        if (tid >= 64 && tid < 128) {
+          const int m = tid - 64;
+          const double* p = sLr + s * 128 + m;
+          red_add(lamg + n * Mp + I * 64 + m, p[0] + p[64]);
+        } else if (tid >= 128 && tid < 192) {
+          const int m = tid - 128;
+          const double* p = sLc + s * 256 + m;
+          red_add(lamg + n * Mp + J * 64 + m, p[0] + p[64] + p[128] + p[192]);
+        }
+        if (n > r0) flush_wq(n - 1);
+        stage2I(v, Lb, s);
+        // stage 2-J: accJ[m',q] += sum_m L[m,m'] (ws_q ZI[m,q]).  A = L^T, B = ws * ZI
+        {
+          const double* pa = Lb + t * RSL + 16 * wr + g;
+          const double* pb = sZI + t * RS + qbase + g;
+          double wq[NJ];
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) wq[j] = v[qbase + 8 * j + g];
+#pragma unroll 2
+          for (int k0 = 0; k0 < 64; k0 += 4) {
+            double a[2], bq[NJ];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) a[i] = pa[k0 * RSL + 8 * i];
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) bq[j] = pb[k0 * RS + 8 * j] * wq[j];
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+              for (int j = 0; j < NJ; ++j) dmma(accJ[i][j][0], accJ[i][j][1], a[i], bq[j]);
+          }
+        }
+      }
+    } else {
+      // ---------------------------------------------------------------- diagonal block
+      int ti[5], tj[5], cnt;
+      diag_tiles(wid, ti, tj, cnt);
+      double creg[5][2];
+#pragma unroll
+      for (int s5 = 0; s5 < 5; ++s5) {
+        double2 c2 = *reinterpret_cast<const double2*>(cb + (8 * ti[s5] + g) * 64 + 8 * tj[s5] + 2 * t);
+        creg[s5][0] = c2.x;
+        creg[s5][1] = c2.y;
+      }
+      for (int64_t n = r0; n < r1; ++n) {
+        const int s = (int)(n & 1);
+        const double* v = sV + (n % 3) * VB;
+        double* Lb = sL + s * 64 * RSL;
+        double nxt = vec_load(n + 1);
+        {
+          double acc[5][2];
+          stage1_diag<QC>(sZI, v, qk, ti, tj, cnt, lane, acc);
+          if (tid < VB) sV[((n + 1) % 3) * VB + tid] = nxt;
+#pragma unroll
+          for (int s5 = 0; s5 < 5; ++s5)
+            if (s5 < cnt) {
+              const double l0 = creg[s5][0] * exp_neg(acc[s5][0]);
+              const double l1 = creg[s5][1] * exp_neg(acc[s5][1]);
+              const int m = 8 * ti[s5] + g, mp = 8 * tj[s5] + 2 * t;
+              *reinterpret_cast<double2*>(Lb + m * RSL + mp) = make_double2(l0, l1);
+              if (ti[s5] != tj[s5]) {
+                Lb[mp * RSL + m] = l0;
+                Lb[(mp + 1) * RSL + m] = l1;
+              }
             }
+        }
+        __syncthreads();
+        if (tid >= 64 && tid < 128) {             // lambda_m = full row sum of the symmetric tile
+          const int m = tid - 64;
+          const double2* row = reinterpret_cast<const double2*>(Lb + m * RSL);
+          double s0 = 0.0, s1 = 0.0;
+#pragma unroll 8
+          for (int k = 0; k < 32; ++k) {
+            const double2 x = row[k];
+            s0 += x.x;
+            s1 += x.y;
           }
+          red_add(lamg + n * Mp + I * 64 + m, s0 + s1);
         }
-      }
-      __syncthreads();   // L tile + partials of row n complete; everything of row n-1 finished
-      flush_lam(n);
-      if (n > r0) flush_wq(n - 1);
-      // ---------------- stage 2-I: T = L ZJ ; accI += w T ; Wq partial
-      {
-        double T[2][NJ][2];
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-#pragma unroll
-          for (int j = 0; j < NJ; ++j) T[i][j][0] = T[i][j][1] = 0.0;
-        const double* pa = Lb + (16 * wr + g) * RSL + t;          // A = L  (rows m, k = m')
-        const double* pb = sZJ + t * RS + qbase + g;              // B = ZJ (k = m', cols q)
-#pragma unroll 2
-        for (int k0 = 0; k0 < 64; k0 += 4) {
-          double a[2], bq[NJ];
-#pragma unroll
-          for (int i = 0; i < 2; ++i) a[i] = pa[i * 8 * RSL + k0];
-#pragma unroll
-          for (int j = 0; j < NJ; ++j) bq[j] = pb[k0 * RS + 8 * j];
-#pragma unroll
-          for (int i = 0; i < 2; ++i)
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) dmma(T[i][j][0], T[i][j][1], a[i], bq[j]);
-        }
-        // fold into the persistent accumulator and form the Wq partial
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-          const int q = qbase + 8 * j + 2 * t;
-          const double2 wq = *reinterpret_cast<const double2*>(v + q);
-          double w0 = 0.0, w1 = 0.0;
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const double2 z = *reinterpret_cast<const double2*>(sZI + (16 * wr + 8 * i + g) * RS + q);
-            accI[i][j][0] = fma(wq.x, T[i][j][0], accI[i][j][0]);
-            accI[i][j][1] = fma(wq.y, T[i][j][1], accI[i][j][1]);
-            w0 = fma(z.x, T[i][j][0], w0);
-            w1 = fma(z.y, T[i][j][1], w1);
-          }
-          w0 += __shfl_xor_sync(0xffffffffu, w0, 4);
-          w1 += __shfl_xor_sync(0xffffffffu, w1, 4);
-          w0 += __shfl_xor_sync(0xffffffffu, w0, 8);
-          w1 += __shfl_xor_sync(0xffffffffu, w1, 8);
-          w0 += __shfl_xor_sync(0xffffffffu, w0, 16);
-          w1 += __shfl_xor_sync(0xffffffffu, w1, 16);
-          if (g == 0) *reinterpret_cast<double2*>(sWq + s * 4 * QC + wr * QC + q) = make_double2(w0, w1);
-        }
-      }
-      // ---------------- stage 2-J: accJ[m',q] += sum_m L[m,m'] (w_q ZI[m,q])
-      if (!diag) {
-        const double* pa = Lb + t * RSL + 16 * wr + g;            // A = L^T (rows m', k = m)
-        const double* pb = sZI + t * RS + qbase + g;              // B = ZI (k = m, cols q)
-        double wq[NJ];
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) wq[j] = v[qbase + 8 * j + g];
-#pragma unroll 2
-        for (int k0 = 0; k0 < 64; k0 += 4) {
-          double a[2], bq[NJ];
-#pragma unroll
-          for (int i = 0; i < 2; ++i) a[i] = pa[k0 * RSL + 8 * i];
-#pragma unroll
-          for (int j = 0; j < NJ; ++j) bq[j] = pb[k0 * RS + 8 * j] * wq[j];
-#pragma unroll
-          for (int i = 0; i < 2; ++i)
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) dmma(accJ[i][j][0], accJ[i][j][1], a[i], bq[j]);
-        }
+        if (n > r0) flush_wq(n - 1);
+        stage2I(v, Lb, s);
       }
     }
     __syncthreads();
