@@ -123,16 +123,15 @@ RGP_DEVINL void diag_tiles(int wid, int (&ti)[5], int (&tj)[5], int& cnt) {
   }
 }
 
-template <int QC>
-RGP_DEVINL void stage1_diag(const double* __restrict__ sZ, const double* __restrict__ v, int qk,
-                            const int (&ti)[5], const int (&tj)[5], int cnt, int lane,
-                            double (&acc)[5][2]) {
+template <int QC, int CNT>
+RGP_DEVINL void stage1_diag_n(const double* __restrict__ sZ, const double* __restrict__ v, int qk,
+                              const int (&ti)[5], const int (&tj)[5], int lane, double (&acc)[5][2]) {
   constexpr int RS = P2Cfg<QC>::RS;
   const int g = lane >> 2, t = lane & 3;
-  const double* pa[5];
-  const double* pb[5];
+  const double* pa[CNT];
+  const double* pb[CNT];
 #pragma unroll
-  for (int s = 0; s < 5; ++s) {
+  for (int s = 0; s < CNT; ++s) {
     pa[s] = sZ + (8 * ti[s] + g) * RS + t;
     pb[s] = sZ + (8 * tj[s] + g) * RS + t;
     const double hi = v[QC + 8 * ti[s] + g];
@@ -143,10 +142,25 @@ RGP_DEVINL void stage1_diag(const double* __restrict__ sZ, const double* __restr
 #pragma unroll 2
   for (int k0 = 0; k0 < qk; k0 += 4) {
     const double wv = v[k0 + t];
+    double a[CNT], b[CNT];
 #pragma unroll
-    for (int s = 0; s < 4; ++s) dmma(acc[s][0], acc[s][1], pa[s][k0] * wv, pb[s][k0]);
-    if (cnt == 5) dmma(acc[4][0], acc[4][1], pa[4][k0] * wv, pb[4][k0]);
+    for (int s = 0; s < CNT; ++s) {
+      a[s] = pa[s][k0] * wv;
+      b[s] = pb[s][k0];
+    }
+#pragma unroll
+    for (int s = 0; s < CNT; ++s) dmma(acc[s][0], acc[s][1], a[s], b[s]);
   }
+}
+
+// the tile count is warp-uniform; branching outside the k loop keeps it a straight-line,
+// software-pipelined loop
+template <int QC>
+RGP_DEVINL void stage1_diag(const double* __restrict__ sZ, const double* __restrict__ v, int qk,
+                            const int (&ti)[5], const int (&tj)[5], int cnt, int lane,
+                            double (&acc)[5][2]) {
+  if (cnt == 5) stage1_diag_n<QC, 5>(sZ, v, qk, ti, tj, lane, acc);
+  else stage1_diag_n<QC, 4>(sZ, v, qk, ti, tj, lane, acc);
 }
 
 // =====================================================================================
