@@ -291,3 +291,18 @@ def test_psi2_is_symmetric_psd_and_bounded():
     # Cauchy-Schwarz / Jensen: Psi2 - Psi1^T Psi1 is PSD summed over rows
     gap = p2 - p1.T @ p1
     assert float(torch.linalg.eigvalsh(0.5 * (gap + gap.T)).min()) > -1e-8 * float(p2.abs().max())
+
+
+def test_sharded_nccl_matches_single_gpu():
+    """>= 2 GPUs only: torchrun the NCCL shard check (scripts/check_sharded_nccl.py)."""
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(min(n, 4)),
+           "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(root, "scripts", "check_sharded_nccl.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
