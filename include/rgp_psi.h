@@ -104,6 +104,22 @@ int rgp_psi_backward_host(rgp_psi_handle_t h, int64_t N, int M, int Q,
                           double* dmu_out, double* dS_out, double* dZ_out,
                           double* dell_out, double* dvar_out);
 
+/* ---- lag-window gather / scatter-add (the callers either side of the path) ----------
+ * Builds the layer input rows from the stacked latent sequences and adds X-row gradients
+ * back onto latent steps: autoreg/layers.py:510-526 (_update_conv via get_conv_1D,
+ * autoreg/util.py:6-12) and :552-571 (update_latent_gradients).
+ *   seq_desc: device int64 [nseq][6] = {row_start, nrows, lat_start, lat_len, ctl_start,
+ *             ctl_len}; ctl_start includes the reference's -N-U_win+1 alignment offset.
+ *   lat [lat_total, Dx], ctl [ctl_total, Du] (ctl may be NULL when Uwin == 0), X [N, Q],
+ *   Q = Xwin*Dx + Uwin*Du.  Call gather once for the means and once for the variances.
+ *   scatter ACCUMULATES into lat_grad / ctl_grad (the reference uses +=). */
+int rgp_lag_gather_dev(rgp_psi_handle_t h, void* stream, int nseq, const int64_t* seq_desc,
+                       int64_t N, int Xwin, int Dx, int Uwin, int Du, const double* lat,
+                       const double* ctl, double* X_out);
+int rgp_lag_scatter_dev(rgp_psi_handle_t h, void* stream, int nseq, const int64_t* seq_desc,
+                        int64_t N, int Xwin, int Dx, int Uwin, int Du, const double* dX,
+                        int64_t lat_total, double* lat_grad, int64_t ctl_total, double* ctl_grad);
+
 /* ---- measurement support ------------------------------------------------------- */
 /* Kernel launches issued through this handle since creation (or the last reset). */
 int64_t rgp_psi_launch_count(rgp_psi_handle_t h);

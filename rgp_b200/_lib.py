@@ -35,6 +35,11 @@ SIGNATURES = {
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                         C.c_void_p, C.c_double, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rgp_lag_gather_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int,
+                                     C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rgp_lag_scatter_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int,
+                                      C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                      C.c_void_p]),
     "rgp_psi_launch_count": (C.c_int64, [C.c_void_p]),
     "rgp_psi_reset_counters": (C.c_int, [C.c_void_p]),
     "rgp_psi_kernel_times": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), c_double_p,
@@ -168,6 +173,15 @@ class Handle:
         check(load().rgp_psi_backward_dev(self._ensure(), C.c_void_p(stream), N, M, Q, mu, S, Z, ell,
                                           float(variance), dL0, float(dL0c), dL1, dL2,
                                           dmu, dS, dZ, dell, dvar))
+
+    def lag_gather(self, stream, nseq, seq_desc, N, Xwin, Dx, Uwin, Du, lat, ctl, out) -> None:
+        check(load().rgp_lag_gather_dev(self._ensure(), C.c_void_p(stream), nseq, seq_desc, N, Xwin, Dx, Uwin, Du,
+                                        lat, ctl, out))
+
+    def lag_scatter(self, stream, nseq, seq_desc, N, Xwin, Dx, Uwin, Du, dX, lat_total, lat_grad,
+                    ctl_total, ctl_grad) -> None:
+        check(load().rgp_lag_scatter_dev(self._ensure(), C.c_void_p(stream), nseq, seq_desc, N, Xwin, Dx, Uwin, Du,
+                                         dX, lat_total, lat_grad, ctl_total, ctl_grad))
 
     def forward_host(self, N, M, Q, mu, S, Z, ell, variance, psi0, psi1, psi2) -> None:
         check(load().rgp_psi_forward_host(self._ensure(), N, M, Q, mu, S, Z, ell, float(variance),

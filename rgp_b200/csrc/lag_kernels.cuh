@@ -1,0 +1,73 @@
+// lag_kernels.cuh - lag-window gather / scatter-add.
+//
+// The layer input matrix X (N x Q) is a strided view of the latent sequences: row n of
+// sequence s is [x_n ... x_{n+Xwin-1}] (lag major, then latent dim) followed by the Uwin
+// control / upper-layer lags (autoreg/layers.py:510-526 via get_conv_1D, autoreg/util.py:6-12),
+// sequences stacked row-wise (layers.py:481-489).  The backward direction adds each X-row
+// gradient back onto the Xwin (Uwin) latent steps it was built from
+// (update_latent_gradients, layers.py:552-571: a Python double loop in the reference).
+// Both are pure HBM traffic; the scatter is written as a gather over the <= Xwin rows that
+// touch a latent step, so it needs no atomics and is deterministic.
+//
+// seq[s] = {row_start, nrows, lat_start, lat_len, ctl_start, ctl_len}; ctl_start already
+// includes the reference's "-N-U_win+1" alignment offset.
+#pragma once
+#include "common.cuh"
+
+namespace rgp {
+namespace lag {
+
+constexpr int DESC = 6;
+
+__device__ __forceinline__ int find_seq(const int64_t* __restrict__ seq, int nseq, int field, int64_t x) {
+  int lo = 0, hi = nseq - 1;             // last s with seq[s][field] <= x
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (seq[mid * DESC + field] <= x) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+__global__ void k_gather(int nseq, const int64_t* __restrict__ seq, int64_t N, int Xwin, int Dx, int Uwin,
+                         int Du, const double* __restrict__ lat, const double* __restrict__ ctl,
+                         double* __restrict__ out) {
+  const int Qx = Xwin * Dx, Q = Qx + Uwin * Du;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * Q) return;
+  int64_t row = idx / Q;
+  int c = (int)(idx - row * Q);
+  int s = find_seq(seq, nseq, 0, row);
+  int64_t n = row - seq[s * DESC + 0];
+  double v;
+  if (c < Qx) {
+    int w = c / Dx, j = c - w * Dx;
+    v = lat[(seq[s * DESC + 2] + n + w) * Dx + j];
+  } else {
+    int cc = c - Qx, w = cc / Du, j = cc - w * Du;
+    v = ctl[(seq[s * DESC + 4] + n + w) * Du + j];
+  }
+  out[idx] = v;
+}
+
+// grad[t, j] += sum_{w} dX[row_start + (t - w), colbase + w*D + j] over 0 <= t - w < nrows
+__global__ void k_scatter(int nseq, const int64_t* __restrict__ seq, int win, int D, int colbase, int Q,
+                          int start_field, const double* __restrict__ dX, int64_t total,
+                          double* __restrict__ grad) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total * D) return;
+  int64_t tg = idx / D;
+  int j = (int)(idx - tg * D);
+  int s = find_seq(seq, nseq, start_field, tg);
+  int64_t t = tg - seq[s * DESC + start_field];
+  if (t >= seq[s * DESC + start_field + 1]) return;       // padding between sequences / unused tail
+  const int64_t row0 = seq[s * DESC + 0], nrows = seq[s * DESC + 1];
+  double acc = 0.0;
+  for (int w = 0; w < win; ++w) {
+    int64_t n = t - w;
+    if (n >= 0 && n < nrows) acc += dX[(row0 + n) * Q + colbase + w * D + j];
+  }
+  grad[idx] += acc;
+}
+
+}  // namespace lag
+}  // namespace rgp

@@ -10,6 +10,7 @@
 #include "ref_kernels.cuh"
 #include "fast_path.cuh"
 #include "fp64_peak.cuh"
+#include "lag_kernels.cuh"
 
 namespace rgp {
 
@@ -332,6 +333,41 @@ int rgp_psi_backward_host(rgp_psi_handle_t h, int64_t N, int M, int Q, const dou
   RGP_CUDA(cudaMemcpyAsync(dell_out, d_dell, (size_t)Q * 8, cudaMemcpyDeviceToHost, st));
   RGP_CUDA(cudaMemcpyAsync(dvar_out, d_dvar, 8, cudaMemcpyDeviceToHost, st));
   RGP_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// ------------------------------------------------------------------ lag window
+int rgp_lag_gather_dev(rgp_psi_handle_t h, void* stream, int nseq, const int64_t* seq_desc, int64_t N,
+                       int Xwin, int Dx, int Uwin, int Du, const double* lat, const double* ctl,
+                       double* X_out) {
+  if (!h) return set_error(RGP_PSI_ERR_INVALID, "null handle");
+  if (nseq <= 0 || N <= 0 || !seq_desc || !X_out || Xwin < 0 || Uwin < 0 || Dx < 0 || Du < 0)
+    return set_error(RGP_PSI_ERR_INVALID, "bad lag-window arguments");
+  if ((Xwin > 0 && (!lat || Dx <= 0)) || (Uwin > 0 && (!ctl || Du <= 0)) || Xwin * Dx + Uwin * Du <= 0)
+    return set_error(RGP_PSI_ERR_INVALID, "window / source mismatch");
+  RGP_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t total = N * (int64_t)(Xwin * Dx + Uwin * Du);
+  RGP_LAUNCH(h, st, "lag_gather", lag::k_gather, ceil_div(total, 256), 256, 0, nseq, seq_desc, N, Xwin, Dx,
+             Uwin, Du, lat, ctl, X_out);
+  return 0;
+}
+
+int rgp_lag_scatter_dev(rgp_psi_handle_t h, void* stream, int nseq, const int64_t* seq_desc, int64_t N,
+                        int Xwin, int Dx, int Uwin, int Du, const double* dX, int64_t lat_total,
+                        double* lat_grad, int64_t ctl_total, double* ctl_grad) {
+  if (!h) return set_error(RGP_PSI_ERR_INVALID, "null handle");
+  if (nseq <= 0 || N <= 0 || !seq_desc || !dX || Xwin < 0 || Uwin < 0)
+    return set_error(RGP_PSI_ERR_INVALID, "bad lag-window arguments");
+  RGP_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Q = Xwin * Dx + Uwin * Du;
+  if (Xwin > 0 && lat_grad && lat_total > 0)
+    RGP_LAUNCH(h, st, "lag_scatter", lag::k_scatter, ceil_div(lat_total * Dx, 256), 256, 0, nseq, seq_desc,
+               Xwin, Dx, 0, Q, 2, dX, lat_total, lat_grad);
+  if (Uwin > 0 && ctl_grad && ctl_total > 0)
+    RGP_LAUNCH(h, st, "lag_scatter", lag::k_scatter, ceil_div(ctl_total * Du, 256), 256, 0, nseq, seq_desc,
+               Uwin, Du, Xwin * Dx, Q, 4, dX, ctl_total, ctl_grad);
   return 0;
 }
 

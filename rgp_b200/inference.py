@@ -1,0 +1,182 @@
+"""Device-resident sparse variational bounds around the psi path.
+
+The reference evaluates the bound on the host between the two psi phases
+(``VarDTC.inference`` autoreg/inference/vardtc.py:88-208, ``SVI_VarDTC.inference``
+autoreg/inference/svi_vardtc.py:70-195, ``comp_KL_qU`` :197-215), which forces Psi1 and
+dL_dpsi1 (N x M, 17 GB each at the headline shape) across PCIe twice per evaluation.
+Here the same algebra runs on the GPU: the M x M Cholesky / triangular solves go to
+cuSOLVER / cuBLAS through ``torch.linalg`` (off the hot path, per the north star), the
+N x M products (psi1^T Y, Y v) are cuBLAS GEMMs, and Psi1 / dL_dpsi1 never leave HBM.
+The psi statistics themselves come from librgp_psi (``DevicePsi``).
+
+GPy helpers restated on the device: jitchol (growing jitter), dtrtrs, backsub_both_sides
+('left' = L^-T X L^-1, 'right' = L^-1 X L^-T), tdot.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from .device import DevicePsi
+
+LOG_2_PI = math.log(2.0 * math.pi)
+CONST_JITTER = 1e-6            # vardtc.py:28, svi_vardtc.py:28
+
+
+def jitchol(A: torch.Tensor, maxtries: int = 5) -> torch.Tensor:
+    L, info = torch.linalg.cholesky_ex(A)
+    if int(info) == 0:
+        return L
+    diag = torch.diagonal(A)
+    if bool((diag <= 0).any()):
+        raise RuntimeError("not pd: non-positive diagonal elements")
+    jitter = float(diag.mean()) * 1e-6
+    eye = torch.eye(A.shape[0], dtype=A.dtype, device=A.device)
+    for _ in range(maxtries):
+        L, info = torch.linalg.cholesky_ex(A + eye * jitter)
+        if int(info) == 0:
+            return L
+        jitter *= 10.0
+    raise RuntimeError("not positive definite, even with jitter.")
+
+
+def dtrtrs(L: torch.Tensor, B: torch.Tensor, trans: int = 0) -> torch.Tensor:
+    if trans:
+        return torch.linalg.solve_triangular(L.mT, B, upper=True)
+    return torch.linalg.solve_triangular(L, B, upper=False)
+
+
+def backsub_both_sides(L: torch.Tensor, X: torch.Tensor, transpose: str = "left") -> torch.Tensor:
+    t = 1 if transpose == "left" else 0
+    tmp = dtrtrs(L, X, trans=t)
+    return dtrtrs(L, tmp.mT, trans=t).mT
+
+
+def tdot(A: torch.Tensor) -> torch.Tensor:
+    return A @ A.mT
+
+
+def rbf_K(variance: float, ell: torch.Tensor, Z: torch.Tensor) -> torch.Tensor:
+    Zs = Z / ell
+    r2 = (Zs[:, None, :] - Zs[None, :, :]).square().sum(-1)
+    return variance * torch.exp(-0.5 * r2)
+
+
+def rbf_K_grads(dL_dK: torch.Tensor, variance: float, ell: torch.Tensor, Z: torch.Tensor):
+    """GPy ``update_gradients_full(dL_dKmm, Z)`` + ``gradients_X(dL_dKmm, Z)``
+    (autoreg/layers.py:105, :134) on the device (M x M x Q, independent of N)."""
+    W = dL_dK * rbf_K(variance, ell, Z)
+    diff = Z[:, None, :] - Z[None, :, :]
+    dvar = W.sum() / variance
+    dl = torch.einsum("ab,abq->q", W, diff.square()) / ell ** 3
+    dZ = -torch.einsum("ab,abq->aq", W + W.mT, diff) / ell ** 2
+    return dvar, dl, dZ
+
+
+class DeviceBound:
+    """One sparse-GP layer with uncertain inputs, evaluated entirely on one GPU:
+    psi forward -> bound algebra -> psi backward (+ the K(Z,Z) terms the layer adds,
+    layers.py:98-134, 574-580)."""
+
+    def __init__(self, device: Optional[int] = None, psi: Optional[DevicePsi] = None):
+        self.psi = psi if psi is not None else DevicePsi(device)
+
+    # ------------------------------------------------------------------ VarDTC
+    def vardtc(self, variance: float, ell, Z, mu, S, Y, noise_variance: float
+               ) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
+        """autoreg/inference/vardtc.py:88-208 (uncertain inputs, certain outputs)."""
+        N, D = Y.shape
+        M = Z.shape[0]
+        beta = 1.0 / max(float(noise_variance), 1e-6)                         # :102
+        _, psi1, psi2 = self.psi.forward(mu, S, Z, ell, variance)
+        psi0b = variance * N * beta                                           # :68
+        psi2b = psi2 * beta
+        psi1Y = (Y.mT @ psi1) * beta                                          # :79  D x M
+        YRY = Y.square().sum() * beta                                         # :81-82
+        eye = torch.eye(M, dtype=Z.dtype, device=Z.device)
+        Kmm = rbf_K(variance, ell, Z) + eye * CONST_JITTER                    # :110-114
+        Lm = jitchol(Kmm)
+        A = backsub_both_sides(Lm, psi2b, "right")                            # :120
+        LL = jitchol(eye + A)                                                 # :124-125
+        LmLL = Lm @ LL
+        logdet_L = 2.0 * torch.log(torch.diagonal(LL)).sum()
+        b = dtrtrs(LmLL, psi1Y.mT).mT                                         # :131
+        bbt = b.square().sum()
+        v = dtrtrs(LmLL, b.mT, trans=1).mT                                    # :133
+        C = tdot(b.mT)
+        tmp = -backsub_both_sides(LL, C + D * eye)                            # :141
+        dL_dpsi2R = backsub_both_sides(Lm, tmp + D * eye) / 2.0               # :142
+        logL_R = -N * math.log(beta)
+        logL = -(D * (N * LOG_2_PI + logL_R + psi0b - torch.trace(A)) + YRY - bbt) / 2.0 \
+            - D * logdet_L / 2.0                                              # :150
+        dL_dKmm = dL_dpsi2R - D * backsub_both_sides(Lm, A) / 2.0             # :156
+        dL_dthetaL = (YRY * beta + beta * D * psi0b - N * D * beta) / 2.0 \
+            - beta * (dL_dpsi2R * psi2b).sum() - beta * torch.trace(C)        # :169
+        dL_dpsi0 = -D * beta / 2.0                                            # :175 (constant over rows)
+        dL_dpsi1 = (Y @ v) * beta                                             # :181
+        dL_dpsi2 = dL_dpsi2R * beta                                           # :184
+        return logL, self._finish(variance, ell, Z, mu, S, dL_dpsi0, dL_dpsi1, dL_dpsi2, dL_dKmm,
+                                  {"dL_dthetaL": dL_dthetaL, "woodbury_vector": v.mT})
+
+    # -------------------------------------------------------------------- SVI
+    def svi(self, variance: float, ell, Z, mu, S, Y, noise_variance: float, qU_mean, qU_var,
+            qU_ratio: float = 1.0) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
+        """autoreg/inference/svi_vardtc.py:70-215 plus the KL scaling of layers.py:75-79."""
+        N, D = Y.shape
+        M = Z.shape[0]
+        beta = 1.0 / float(noise_variance)                                    # :80
+        _, psi1, psi2 = self.psi.forward(mu, S, Z, ell, variance)
+        psi0b = variance * N * beta
+        psi2b = psi2 * beta
+        psi1Y = (Y.mT @ psi1) * beta
+        YRY = Y.square().sum() * beta
+        eye = torch.eye(M, dtype=Z.dtype, device=Z.device)
+        Lm = jitchol(rbf_K(variance, ell, Z) + eye * CONST_JITTER)            # :88-93
+        Ls = jitchol(qU_var)                                                  # :96
+        LinvLs = dtrtrs(Lm, Ls)
+        Linvmu = dtrtrs(Lm, qU_mean)
+        psi1YLinvT = dtrtrs(Lm, psi1Y.mT).mT                                  # :99
+        A = backsub_both_sides(Lm, psi2b, "right")                            # :108
+        B = tdot(LinvLs) * D + tdot(Linvmu)                                   # :112
+        logL_R = -N * math.log(beta)
+        core = -D * psi0b / 2.0 - YRY / 2.0 - (B * A).sum() / 2.0 + torch.trace(A) * D / 2.0 \
+            + (Linvmu * psi1YLinvT.mT).sum()
+        logL = -N * D * LOG_2_PI / 2.0 - D * logL_R / 2.0 + core              # :122-123
+        tmp1 = backsub_both_sides(Lm, B @ A, "left")                          # :129
+        tmp2 = Linvmu @ psi1YLinvT
+        tmp3 = backsub_both_sides(Lm, -D * A - tmp2 - tmp2.mT, "left") / 2.0
+        dL_dKmm = (tmp1 + tmp1.mT) / 2.0 + tmp3                               # :133
+        dL_dthetaL = -D * N * beta / 2.0 - core * beta                        # :139
+        t1 = backsub_both_sides(Lm, -A, "left")                               # :145
+        KuuInvmu = dtrtrs(Lm, Linvmu, trans=1)
+        dL_dqU_mean = t1 @ qU_mean + dtrtrs(Lm, psi1YLinvT.mT, trans=1)       # :146
+        dL_dqU_var = D / 2.0 * t1                                             # :147
+        dL_dpsi0 = -D * beta / 2.0                                            # :162
+        dL_dpsi1 = (Y @ KuuInvmu.mT) * beta                                   # :167
+        dL_dpsi2 = beta * backsub_both_sides(Lm, D * eye - B, "left") / 2.0   # :169
+        # KL(q(U) || p(U)), svi_vardtc.py:197-215, scaled by qU_ratio (layers.py:76-79)
+        Linv = dtrtrs(Lm, eye)
+        KuuInv = Linv.mT @ Linv
+        LuInv = dtrtrs(Ls, eye)
+        KL = D * M / -2.0 - torch.log(torch.diagonal(Ls)).sum() * D + torch.log(torch.diagonal(Lm)).sum() * D \
+            + LinvLs.square().sum() / 2.0 * D + Linvmu.square().sum() / 2.0
+        dKL_dqU_mean = dtrtrs(Lm, Linvmu, trans=1)
+        dKL_dqU_var = (tdot(LuInv.mT) / -2.0 + KuuInv / 2.0) * D
+        dKL_dKuu = KuuInv * D / 2.0 - KuuInv @ (tdot(qU_mean) + qU_var * D) @ KuuInv / 2.0
+        logL = logL - KL * qU_ratio
+        extra = {"dL_dthetaL": dL_dthetaL,
+                 "dL_dqU_mean": dL_dqU_mean - dKL_dqU_mean * qU_ratio,
+                 "dL_dqU_var": dL_dqU_var - dKL_dqU_var * qU_ratio}
+        return logL, self._finish(variance, ell, Z, mu, S, dL_dpsi0, dL_dpsi1, dL_dpsi2,
+                                  dL_dKmm - dKL_dKuu * qU_ratio, extra)
+
+    # ------------------------------------------------------------ shared tail
+    def _finish(self, variance, ell, Z, mu, S, dL_dpsi0, dL_dpsi1, dL_dpsi2, dL_dKmm, extra):
+        dvar, dl, dZ, dmu, dS = self.psi.backward(mu, S, Z, ell, variance, dL_dpsi0, dL_dpsi1, dL_dpsi2)
+        kvar, kl, kZ = rbf_K_grads(dL_dKmm, variance, ell, Z)
+        out = {"variance": dvar.reshape(()) + kvar, "lengthscale": dl + kl, "Z": dZ + kZ, "mu": dmu, "S": dS,
+               "dL_dKmm": dL_dKmm, "dL_dpsi1": dL_dpsi1, "dL_dpsi2": dL_dpsi2}
+        out.update(extra)
+        return out
