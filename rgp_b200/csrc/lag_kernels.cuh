@@ -66,7 +66,7 @@ __global__ void k_scatter(int nseq, const int64_t* __restrict__ seq, int win, in
   if (t >= seq[s * DESC + start_field + 1]) return;       // padding between sequences / unused tail
   const int64_t row0 = seq[s * DESC + 0], nrows = seq[s * DESC + 1];
   double acc = 0.0;
-  for (int w = 0; w < win; ++w) {
+  for (int w = win - 1; w >= 0; --w) {      // rows in increasing n: the reference's += order, bit for bit
     int64_t n = t - w;
     if (n >= 0 && n < nrows) acc += dX[(row0 + n) * Q + colbase + w * D + j];
   }
