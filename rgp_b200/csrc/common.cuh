@@ -42,6 +42,56 @@ RGP_DEVINL double exp_neg(double x) {
   return (x < -708.0) ? 0.0 : res;
 }
 
+// Table-assisted variant for the two O(N M^2 Q) kernels: x = (256 k + j) ln2/256 + r with
+// |r| <= ln2/512, exp(x) = 2^k * T[j] * e^r, T[j] = 2^(j/256) from a 2 KB shared-memory table
+// (filled once per CTA with exp2()), e^r by a degree-4 Taylor polynomial (remainder
+// r^5/120 < 4e-17).  8 FP64-pipe ops and one LDS; the underflow test is an integer compare
+// on the high word (x < ~-708 -> 0), so it costs the FP64 pipe nothing.
+RGP_DEVINL void exp_table_init(double* tab, int tid) {
+  if (tid < 256) tab[tid] = exp2((double)tid * (1.0 / 256.0));
+}
+
+RGP_DEVINL double exp_tab(double x, const double* __restrict__ tab) {
+  const double INV = 369.32993046757463;                // 256 / ln2
+  const double STEP = 2.7076061740622863e-03;           // ln2 / 256
+  const double MAGIC = 6755399441055744.0;              // 2^52 + 2^51
+  double kd = fma(x, INV, MAGIC);
+  int n = __double2loint(kd);
+  double nf = kd - MAGIC;
+  double r = fma(nf, -STEP, x);
+  double p = fma(r, 4.16666666666666666667e-02, 1.66666666666666666667e-01);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  double res = tab[n & 255] * p;
+  int hi = __double2hiint(res) + ((n >> 8) << 20);
+  res = __hiloint2double(hi, __double2loint(res));
+  return ((unsigned)__double2hiint(x) > 0xC0862000u) ? 0.0 : res;
+}
+
+// Sum `v[0..7]` over the 8 lanes that differ in lane bits 2..4 (recursive halving: 7 shuffles
+// instead of 24).  Returns, in every lane, the total of element c = 4*b4 + 2*b3 + b2 where
+// b4,b3,b2 are that lane's bits 4,3,2.
+RGP_DEVINL double reduce8_over_g(const double (&v)[8], int lane) {
+  const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4;
+  double u[4], w[2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const double send = h4 ? v[i] : v[i + 4];
+    const double keep = h4 ? v[i + 4] : v[i];
+    u[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const double send = h3 ? u[i] : u[i + 2];
+    const double keep = h3 ? u[i + 2] : u[i];
+    w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  const double send = h2 ? w[0] : w[1];
+  const double keep = h2 ? w[1] : w[0];
+  return keep + __shfl_xor_sync(0xffffffffu, send, 4);
+}
+
 RGP_DEVINL double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -15,7 +15,7 @@ static inline int qc_for(int Q) { return Q <= 16 ? 16 : (Q <= 32 ? 32 : 64); }
 static int init(rgp_psi_ctx*) {
   RGP_CUDA(cudaFuncSetAttribute(k_psi2_fwd<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<16>::FWD_SMEM));
   RGP_CUDA(cudaFuncSetAttribute(k_psi2_fwd<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<32>::FWD_SMEM));
-  RGP_CUDA(cudaFuncSetAttribute(k_psi2_fwd<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<64>::FWD_SMEM));
+  RGP_CUDA(cudaFuncSetAttribute(k_psi2_fwd<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<64>::FWD_SMEM + 65536));
   RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwd<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<16>::BWD_SMEM));
   RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwd<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<32>::BWD_SMEM));
   RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwd<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<64>::BWD_SMEM));
@@ -80,7 +80,7 @@ static GemmEpi epi_plain(double* out, int64_t ld, int64_t split_stride) {
 template <int QC>
 static int launch_fwd(rgp_psi_ctx* h, cudaStream_t st, const Shape& s, int64_t rows, int R, int G,
                       const double* Zt, const double* w, const double* HP, double* P2p) {
-  RGP_LAUNCH(h, st, "psi2_fwd", (k_psi2_fwd<QC>), dim3(R, G), P2_THREADS, P2Cfg<QC>::FWD_SMEM, rows,
+  RGP_LAUNCH(h, st, "psi2_fwd", (k_psi2_fwd<QC>), dim3(R, G), P2_THREADS, P2Cfg<QC>::FWD_SMEM + h->fwd_smem_pad, rows,
              s.nt, s.nblocks, s.qk, Zt, w, HP, P2p);
   return 0;
 }

@@ -40,9 +40,9 @@ struct P2Cfg {
   static constexpr int RS = QC + 4;
   static constexpr int NJ = QC / 16;        // 8-wide q tiles per warp in stage 2
   static constexpr int VB = QC + 128;       // per-row vector slot: w[QC] | H_I[64] | H_J[64]
-  static constexpr int FWD_SMEM = (2 * 64 * RS + 3 * VB) * 8;
+  static constexpr int FWD_SMEM = (2 * 64 * RS + 3 * VB + 256) * 8;
   static constexpr int BWD_SMEM =
-      (2 * 64 * RS + 2 * 64 * RSL + 3 * VB + 2 * 4 * QC + 2 * 2 * 64 + 2 * 4 * 64) * 8;
+      (2 * 64 * RS + 2 * 64 * RSL + 3 * VB + 2 * 4 * QC + 2 * 2 * 64 + 2 * 4 * 64 + 256) * 8;
 };
 
 RGP_DEVINL void dmma(double& d0, double& d1, double a, double b) {
@@ -178,12 +178,14 @@ k_psi2_fwd(int64_t rc, int nt, int nblocks, int qk, const double* __restrict__ Z
   double* sZI = smem;
   double* sZJ = sZI + 64 * RS;
   double* sV = sZJ + 64 * RS;                     // 3 slots of VB
+  double* sT = sV + 3 * VB;                       // exp table, 256 entries
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int wr = wid >> 1, wc = wid & 1, g = lane >> 2, t = lane & 3;
   const int R = gridDim.x, G = gridDim.y;
   const int64_t per = (rc + R - 1) / R;
   const int64_t r0 = per * blockIdx.x, r1 = (r0 + per < rc) ? r0 + per : rc;
+  exp_table_init(sT, tid);
 
   int curI = -1, curJ = -1;
   for (int b = blockIdx.y; b < nblocks; b += G) {
@@ -223,8 +225,8 @@ k_psi2_fwd(int64_t rc, int nt, int nblocks, int qk, const double* __restrict__ Z
         for (int i = 0; i < 2; ++i)
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            pacc[i][j][0] += exp_neg(acc[i][j][0]);
-            pacc[i][j][1] += exp_neg(acc[i][j][1]);
+            pacc[i][j][0] += exp_tab(acc[i][j][0], sT);
+            pacc[i][j][1] += exp_tab(acc[i][j][1], sT);
           }
         __syncthreads();                          // slot (n+1)%3 visible
       }
@@ -250,8 +252,8 @@ k_psi2_fwd(int64_t rc, int nt, int nblocks, int qk, const double* __restrict__ Z
 #pragma unroll
         for (int s = 0; s < 5; ++s)
           if (s < cnt) {
-            pacc[s][0] += exp_neg(acc[s][0]);
-            pacc[s][1] += exp_neg(acc[s][1]);
+            pacc[s][0] += exp_tab(acc[s][0], sT);
+            pacc[s][1] += exp_tab(acc[s][1], sT);
           }
         __syncthreads();
       }
@@ -291,6 +293,7 @@ k_psi2_bwd(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __rest
   double* sWq = sV + 3 * VB;                      // [2][4][QC]
   double* sLr = sWq + 2 * 4 * QC;                 // [2][2][64]  row-sum partials (per wc)
   double* sLc = sLr + 2 * 2 * 64;                 // [2][4][64]  col-sum partials (per wr)
+  double* sT = sLc + 2 * 4 * 64;                  // exp table, 256 entries
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int wr = wid >> 1, wc = wid & 1, g = lane >> 2, t = lane & 3;
@@ -302,6 +305,7 @@ k_psi2_bwd(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __rest
   double* Wqg = Wq + (size_t)blockIdx.y * rc * QC;
   double* accp = ACCp + (size_t)cta * Mp * QC;
   const int qbase = wc * (QC / 2);                // this warp's q columns in stage 2
+  exp_table_init(sT, tid);
 
   int curI = -1, curJ = -1;
   for (int b = blockIdx.y; b < nblocks; b += G) {
@@ -362,6 +366,7 @@ k_psi2_bwd(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __rest
 #pragma unroll
           for (int j = 0; j < NJ; ++j) dmma(T[i][j][0], T[i][j][1], a[i], bq[j]);
       }
+      double wp[2 * NJ];                           // Wq partials, index c = 2 j + e
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
         const int q = qbase + 8 * j + 2 * t;
@@ -375,13 +380,22 @@ k_psi2_bwd(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __rest
           w0 = fma(z.x, T[i][j][0], w0);
           w1 = fma(z.y, T[i][j][1], w1);
         }
-        w0 += __shfl_xor_sync(0xffffffffu, w0, 4);
-        w1 += __shfl_xor_sync(0xffffffffu, w1, 4);
-        w0 += __shfl_xor_sync(0xffffffffu, w0, 8);
-        w1 += __shfl_xor_sync(0xffffffffu, w1, 8);
-        w0 += __shfl_xor_sync(0xffffffffu, w0, 16);
-        w1 += __shfl_xor_sync(0xffffffffu, w1, 16);
-        if (g == 0) *reinterpret_cast<double2*>(sWq + s * 4 * QC + wr * QC + q) = make_double2(w0, w1);
+        wp[2 * j] = w0;
+        wp[2 * j + 1] = w1;
+      }
+      if constexpr (NJ == 4) {
+        const double tot = reduce8_over_g(wp, lane);
+        const int c = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+        sWq[s * 4 * QC + wr * QC + qbase + 8 * (c >> 1) + 2 * t + (c & 1)] = tot;
+      } else {
+#pragma unroll
+        for (int c = 0; c < 2 * NJ; ++c) {
+          double x = wp[c];
+          x += __shfl_xor_sync(0xffffffffu, x, 4);
+          x += __shfl_xor_sync(0xffffffffu, x, 8);
+          x += __shfl_xor_sync(0xffffffffu, x, 16);
+          if (g == 0) sWq[s * 4 * QC + wr * QC + qbase + 8 * (c >> 1) + 2 * t + (c & 1)] = x;
+        }
       }
     };
 
@@ -406,20 +420,20 @@ k_psi2_bwd(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __rest
           stage1<QC>(sZI, sZJ, v, qk, wr, wc, lane, acc);
           if (tid < VB) sV[((n + 1) % 3) * VB + tid] = nxt;
           double rs[2] = {0.0, 0.0};
-          double cs[4][2];
+          double cs[8];                            // column partials, index c = 2 j + e
 #pragma unroll
-          for (int j = 0; j < 4; ++j) cs[j][0] = cs[j][1] = 0.0;
+          for (int c = 0; c < 8; ++c) cs[c] = 0.0;
 #pragma unroll
           for (int i = 0; i < 2; ++i) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              double l0 = creg[i][j][0] * exp_neg(acc[i][j][0]);
-              double l1 = creg[i][j][1] * exp_neg(acc[i][j][1]);
+              double l0 = creg[i][j][0] * exp_tab(acc[i][j][0], sT);
+              double l1 = creg[i][j][1] * exp_tab(acc[i][j][1], sT);
               *reinterpret_cast<double2*>(Lb + (16 * wr + 8 * i + g) * RSL + 32 * wc + 8 * j + 2 * t) =
                   make_double2(l0, l1);
               rs[i] += l0 + l1;
-              cs[j][0] += l0;
-              cs[j][1] += l1;
+              cs[2 * j] += l0;
+              cs[2 * j + 1] += l1;
             }
           }
           // row sums: reduce over the 4 lanes of a quad (t); col sums: over the 8 quads (g)
@@ -432,21 +446,10 @@ k_psi2_bwd(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __rest
             sLr[s * 128 + wc * 64 + 16 * wr + g] = rs[0];
             sLr[s * 128 + wc * 64 + 16 * wr + 8 + g] = rs[1];
           }
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              double c = cs[j][e];
-              c += __shfl_xor_sync(0xffffffffu, c, 4);
-              c += __shfl_xor_sync(0xffffffffu, c, 8);
-              c += __shfl_xor_sync(0xffffffffu, c, 16);
-              cs[j][e] = c;
-            }
-          if (g == 0) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              *reinterpret_cast<double2*>(sLc + s * 256 + wr * 64 + 32 * wc + 8 * j + 2 * t) =
-                  make_double2(cs[j][0], cs[j][1]);
+          {
+            const double tot = reduce8_over_g(cs, lane);
+            const int c = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+            sLc[s * 256 + wr * 64 + 32 * wc + 8 * (c >> 1) + 2 * t + (c & 1)] = tot;
           }
         }
         __syncthreads();   // L tile + lambda partials of row n complete; row n-1 fully finished
@@ -505,8 +508,8 @@ k_psi2_bwd(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __rest
 #pragma unroll
           for (int s5 = 0; s5 < 5; ++s5)
             if (s5 < cnt) {
-              const double l0 = creg[s5][0] * exp_neg(acc[s5][0]);
-              const double l1 = creg[s5][1] * exp_neg(acc[s5][1]);
+              const double l0 = creg[s5][0] * exp_tab(acc[s5][0], sT);
+              const double l1 = creg[s5][1] * exp_tab(acc[s5][1], sT);
               const int m = 8 * ti[s5] + g, mp = 8 * tj[s5] + 2 * t;
               *reinterpret_cast<double2*>(Lb + m * RSL + mp) = make_double2(l0, l1);
               if (ti[s5] != tj[s5]) {

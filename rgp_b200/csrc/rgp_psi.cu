@@ -220,6 +220,8 @@ int rgp_psi_set_option(rgp_psi_handle_t h, const char* key, int64_t value) {
     h->row_chunk = value;
   } else if (!strcmp(key, "profile")) {
     h->profile = value != 0;
+  } else if (!strcmp(key, "fwd_smem_pad")) {
+    h->fwd_smem_pad = (int)value;
   } else {
     return set_error(RGP_PSI_ERR_INVALID, "unknown option '%s'", key);
   }
