@@ -5,6 +5,7 @@
 #include "context.cuh"
 #include "fast_prep.cuh"
 #include "psi2_kernels.cuh"
+#include "psi2_bwd16.cuh"
 
 namespace rgp {
 namespace fast {
@@ -19,6 +20,8 @@ static int init(rgp_psi_ctx*) {
   RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwd<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<16>::BWD_SMEM));
   RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwd<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<32>::BWD_SMEM));
   RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwd<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<64>::BWD_SMEM));
+  RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwd16<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg16<32>::BWD_SMEM));
+  RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwd16<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg16<64>::BWD_SMEM));
   return 0;
 }
 
@@ -89,6 +92,13 @@ template <int QC>
 static int launch_bwd(rgp_psi_ctx* h, cudaStream_t st, const Shape& s, int64_t rows, int R, int G,
                       const double* Zt, const double* Ct, const double* w, const double* HP,
                       double* lam, double* Wq, double* ACCp) {
+  if constexpr (QC >= 32) {
+    if (h->bwd_warps == 16) {
+      RGP_LAUNCH(h, st, "psi2_bwd", (k_psi2_bwd16<QC>), dim3(R, G), P2_THREADS16, P2Cfg16<QC>::BWD_SMEM, rows,
+                 s.Mp, s.nt, s.nblocks, s.qk, Zt, Ct, w, HP, lam, Wq, ACCp);
+      return 0;
+    }
+  }
   RGP_LAUNCH(h, st, "psi2_bwd", (k_psi2_bwd<QC>), dim3(R, G), P2_THREADS, P2Cfg<QC>::BWD_SMEM, rows,
              s.Mp, s.nt, s.nblocks, s.qk, Zt, Ct, w, HP, lam, Wq, ACCp);
   return 0;

@@ -25,8 +25,10 @@ IMPLS = ["reference", "fast"]
 @pytest.fixture(scope="module")
 def plugins():
     from rgp_b200.psicomp import PSICOMP_RBF_B200
+    p8 = PSICOMP_RBF_B200(impl="auto", cache=False)
+    p8.handle.set_option("bwd_warps", 8)             # the 8-warp backward kernel (default is 16)
     return {"reference": PSICOMP_RBF_B200(impl="reference", cache=False),
-            "fast": PSICOMP_RBF_B200(impl="auto", cache=False)}
+            "fast": PSICOMP_RBF_B200(impl="auto", cache=False), "fast8": p8}
 
 
 def _kern(pc, var, ell, ard=True):
@@ -68,7 +70,7 @@ SHAPES = [
 ]
 
 
-@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("impl", IMPLS + ["fast8"])
 @pytest.mark.parametrize("N,M,Q,nc", SHAPES)
 def test_forward_and_backward_match_oracle(plugins, impl, N, M, Q, nc):
     var, ell, Z, mu, S = make_inputs(N, M, Q, seed=100 + N + M + Q, n_control=nc)
