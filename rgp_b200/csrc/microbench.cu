@@ -126,6 +126,50 @@ __global__ void __launch_bounds__(256) k_exp(int outer, double* out) {
   if (s == 123.456) out[0] = s;
 }
 
+// DMMA throughput versus independent accumulators in flight: NACC accumulators per warp,
+// blockDim/32 warps per CTA, one CTA per SM (so warps per scheduler = blockDim/128).
+template <int NACC>
+__global__ void k_dmma_inflight(int iters, double* out) {
+  double c[NACC][2];
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) c[i][0] = c[i][1] = 0.0;
+  double a = 1e-3 * threadIdx.x, b = 1.0 + 1e-4 * threadIdx.x;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+      for (int i = 0; i < NACC; ++i) dmma884(c[i][0], c[i][1], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) s += c[i][0] + c[i][1];
+  if (s == 123.456) out[0] = s;
+}
+
+template <int NACC>
+static void probe_inflight(int sms, double* out) {
+  for (int warps_per_sched : {1, 2, 4, 8}) {
+    int threads = 128 * warps_per_sched;
+    int iters = 4096 / NACC;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    k_dmma_inflight<NACC><<<sms, threads>>>(iters, out);
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(e0));
+    k_dmma_inflight<NACC><<<sms, threads>>>(iters, out);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    double dmma_per_sched = (double)iters * 8 * NACC * warps_per_sched;
+    double cycles = ms * 1e-3 * 1.965e9;
+    printf("{\"probe\": \"dmma_inflight\", \"acc_per_warp\": %d, \"warps_per_scheduler\": %d, \"in_flight\": %d, "
+           "\"cycles_per_dmma_per_scheduler\": %.2f, \"frac_of_peak\": %.3f}\n",
+           NACC, warps_per_sched, NACC * warps_per_sched, cycles / dmma_per_sched, 16.0 / (cycles / dmma_per_sched));
+  }
+}
+
 template <typename F>
 static float time_ms(F f, int reps = 5) {
   cudaEvent_t e0, e1;
@@ -214,6 +258,11 @@ int main() {
       }
     }
   }
+  // 5. DMMA latency / accumulators in flight
+  probe_inflight<1>(sms, out);
+  probe_inflight<2>(sms, out);
+  probe_inflight<4>(sms, out);
+  probe_inflight<8>(sms, out);
   // 4. exp
   {
     int blocks = sms * 8, outer = 16;

@@ -141,7 +141,10 @@ k_psi2_bwd16(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __re
       if (tid < QC + 64) return hI[n * 64 + (tid - QC)];
       return hJ[n * 64 + (tid - QC - 64)];
     };
-    if (r0 < r1 && tid < VB) sV[(r0 % 3) * VB + tid] = vec_load(r0);
+    if (tid < VB) {                                // vectors of the first two rows
+      if (r0 < r1) sV[(r0 % 3) * VB + tid] = vec_load(r0);
+      if (r0 + 1 < r1) sV[((r0 + 1) % 3) * VB + tid] = vec_load(r0 + 1);
+    }
     double accI[2][NJ][2], accJ[2][NJ][2];
 #pragma unroll
     for (int i = 0; i < 2; ++i)
@@ -212,6 +215,13 @@ k_psi2_bwd16(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __re
       }
     };
 
+    // Row pipeline with skewed warp groups.  Between barrier n and barrier n+1 every warp runs
+    //   S2(n)   = stage 2-I + fold + stage 2-J on the L tile of row n        (DMMA heavy)
+    //   S1E(n+1)= stage 1 + exp epilogue of row n+1 -> L tile (n+1)&1         (DMMA, then DFMA/SHFL/STS)
+    // group A (warps 0-3, 8-11) in that order, group B (4-7, 12-15) in the opposite order, so each
+    // scheduler (2 A + 2 B warps) always has warps in both kinds of phase.
+    const bool groupB = (wid >> 2) & 1;
+
     if (!diag) {
       double creg[2][2][2];
 #pragma unroll
@@ -222,69 +232,92 @@ k_psi2_bwd16(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __re
           creg[i][j][0] = c2.x;
           creg[i][j][1] = c2.y;
         }
-      for (int64_t n = r0; n < r1; ++n) {
+      auto s1e = [&](int64_t n) {
         const int s = (int)(n & 1);
         const double* v = sV + (n % 3) * VB;
         double* Lb = sL + s * 64 * RSL;
-        double nxt = vec_load(n + 1);
-        {
-          // stage 1 on this warp's 16 x 16 sub-block
-          double acc[2][2][2];
-          const double* pa = sZI + (16 * wr + g) * RS + t;
-          const double* pb = sZJ + (16 * wc + g) * RS + t;
-          const double* vI = v + QC + 16 * wr + g;
-          const double* vJ = v + QC + 64 + 16 * wc + 2 * t;
+        double acc[2][2][2];
+        const double* pa = sZI + (16 * wr + g) * RS + t;
+        const double* pb = sZJ + (16 * wc + g) * RS + t;
+        const double* vI = v + QC + 16 * wr + g;
+        const double* vJ = v + QC + 64 + 16 * wc + 2 * t;
 #pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const double hi = vI[8 * i];
+        for (int i = 0; i < 2; ++i) {
+          const double hi = vI[8 * i];
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const double2 hj = *reinterpret_cast<const double2*>(vJ + 8 * j);
-              acc[i][j][0] = hi + hj.x;
-              acc[i][j][1] = hi + hj.y;
-            }
+          for (int j = 0; j < 2; ++j) {
+            const double2 hj = *reinterpret_cast<const double2*>(vJ + 8 * j);
+            acc[i][j][0] = hi + hj.x;
+            acc[i][j][1] = hi + hj.y;
           }
+        }
 #pragma unroll 4
-          for (int k0 = 0; k0 < qk; k0 += 4) {
-            const double wv = v[k0 + t];
-            double a[2], bb[2];
+        for (int k0 = 0; k0 < qk; k0 += 4) {
+          const double wv = v[k0 + t];
+          double a[2], bb[2];
 #pragma unroll
-            for (int i = 0; i < 2; ++i) a[i] = pa[i * 8 * RS + k0] * wv;
+          for (int i = 0; i < 2; ++i) a[i] = pa[i * 8 * RS + k0] * wv;
 #pragma unroll
-            for (int j = 0; j < 2; ++j) bb[j] = pb[j * 8 * RS + k0];
-#pragma unroll
-            for (int i = 0; i < 2; ++i)
-#pragma unroll
-              for (int j = 0; j < 2; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], bb[j]);
-          }
-          if (tid < VB) sV[((n + 1) % 3) * VB + tid] = nxt;
-          double rs[2] = {0.0, 0.0};
-          double cs[4] = {0.0, 0.0, 0.0, 0.0};
+          for (int j = 0; j < 2; ++j) bb[j] = pb[j * 8 * RS + k0];
 #pragma unroll
           for (int i = 0; i < 2; ++i)
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const double l0 = creg[i][j][0] * exp_tab(acc[i][j][0], sT);
-              const double l1 = creg[i][j][1] * exp_tab(acc[i][j][1], sT);
-              *reinterpret_cast<double2*>(Lb + (16 * wr + 8 * i + g) * RSL + 16 * wc + 8 * j + 2 * t) =
-                  make_double2(l0, l1);
-              rs[i] += l0 + l1;
-              cs[2 * j] += l0;
-              cs[2 * j + 1] += l1;
-            }
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], 1);
-            rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], 2);
-          }
-          if (t == 0) {
-            sLr[s * 256 + wc * 64 + 16 * wr + g] = rs[0];
-            sLr[s * 256 + wc * 64 + 16 * wr + 8 + g] = rs[1];
-          }
-          const double tot = reduce4_over_g(cs, lane);
-          if (!(lane & 4)) sLc[s * 256 + wr * 64 + 16 * wc + 8 * (cidx >> 1) + 2 * t + (cidx & 1)] = tot;
+            for (int j = 0; j < 2; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], bb[j]);
         }
-        __syncthreads();
+        double rs[2] = {0.0, 0.0};
+        double cs[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const double l0 = creg[i][j][0] * exp_tab(acc[i][j][0], sT);
+            const double l1 = creg[i][j][1] * exp_tab(acc[i][j][1], sT);
+            *reinterpret_cast<double2*>(Lb + (16 * wr + 8 * i + g) * RSL + 16 * wc + 8 * j + 2 * t) =
+                make_double2(l0, l1);
+            rs[i] += l0 + l1;
+            cs[2 * j] += l0;
+            cs[2 * j + 1] += l1;
+          }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], 1);
+          rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], 2);
+        }
+        if (t == 0) {
+          sLr[s * 256 + wc * 64 + 16 * wr + g] = rs[0];
+          sLr[s * 256 + wc * 64 + 16 * wr + 8 + g] = rs[1];
+        }
+        const double tot = reduce4_over_g(cs, lane);
+        if (!(lane & 4)) sLc[s * 256 + wr * 64 + 16 * wc + 8 * (cidx >> 1) + 2 * t + (cidx & 1)] = tot;
+      };
+      auto s2 = [&](int64_t n) {
+        const int s = (int)(n & 1);
+        const double* v = sV + (n % 3) * VB;
+        const double* Lb = sL + s * 64 * RSL;
+        stage2I(v, Lb, s);
+        // stage 2-J: accJ[m',q] += sum_m L[m,m'] (ws_q ZI[m,q])
+        const double* pa = Lb + t * RSL + 16 * wr + g;
+        const double* pb = sZI + t * RS + qbase + g;
+        double wq[NJ];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) wq[j] = v[qbase + 8 * j + g];
+#pragma unroll 4
+        for (int k0 = 0; k0 < 64; k0 += 4) {
+          double a[2], bq[NJ];
+#pragma unroll
+          for (int i = 0; i < 2; ++i) a[i] = pa[k0 * RSL + 8 * i];
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) bq[j] = pb[k0 * RS + 8 * j] * wq[j];
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) dmma(accJ[i][j][0], accJ[i][j][1], a[i], bq[j]);
+        }
+      };
+      if (r0 < r1) s1e(r0);
+      __syncthreads();
+      for (int64_t n = r0; n < r1; ++n) {
+        const int s = (int)(n & 1);
         if (tid >= 64 && tid < 128) {
           const int m = tid - 64;
           const double* p = sLr + s * 256 + m;
@@ -295,27 +328,16 @@ k_psi2_bwd16(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __re
           red_add(lamg + n * Mp + J * 64 + m, p[0] + p[64] + p[128] + p[192]);
         }
         if (n > r0) flush_wq(n - 1);
-        stage2I(v, Lb, s);
-        {
-          // stage 2-J: accJ[m',q] += sum_m L[m,m'] (ws_q ZI[m,q])
-          const double* pa = Lb + t * RSL + 16 * wr + g;
-          const double* pb = sZI + t * RS + qbase + g;
-          double wq[NJ];
-#pragma unroll
-          for (int j = 0; j < NJ; ++j) wq[j] = v[qbase + 8 * j + g];
-#pragma unroll 4
-          for (int k0 = 0; k0 < 64; k0 += 4) {
-            double a[2], bq[NJ];
-#pragma unroll
-            for (int i = 0; i < 2; ++i) a[i] = pa[k0 * RSL + 8 * i];
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) bq[j] = pb[k0 * RS + 8 * j] * wq[j];
-#pragma unroll
-            for (int i = 0; i < 2; ++i)
-#pragma unroll
-              for (int j = 0; j < NJ; ++j) dmma(accJ[i][j][0], accJ[i][j][1], a[i], bq[j]);
-          }
+        const double nxt = vec_load(n + 2);
+        if (groupB) {
+          if (n + 1 < r1) s1e(n + 1);
+          s2(n);
+        } else {
+          s2(n);
+          if (n + 1 < r1) s1e(n + 1);
         }
+        if (tid < VB) sV[((n + 2) % 3) * VB + tid] = nxt;
+        __syncthreads();
       }
     } else {
       int ti[3], tj[3], cnt;
@@ -327,31 +349,33 @@ k_psi2_bwd16(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __re
         creg[s3][0] = c2.x;
         creg[s3][1] = c2.y;
       }
-      for (int64_t n = r0; n < r1; ++n) {
+      auto s1e = [&](int64_t n) {
         const int s = (int)(n & 1);
         const double* v = sV + (n % 3) * VB;
         double* Lb = sL + s * 64 * RSL;
-        double nxt = vec_load(n + 1);
-        {
-          double acc[3][2];
-          if (cnt == 3) stage1_diag16_n<QC, 3>(sZI, v, qk, ti, tj, lane, acc);
-          else stage1_diag16_n<QC, 2>(sZI, v, qk, ti, tj, lane, acc);
-          if (tid < VB) sV[((n + 1) % 3) * VB + tid] = nxt;
+        double acc[3][2];
+        if (cnt == 3) stage1_diag16_n<QC, 3>(sZI, v, qk, ti, tj, lane, acc);
+        else stage1_diag16_n<QC, 2>(sZI, v, qk, ti, tj, lane, acc);
 #pragma unroll
-          for (int s3 = 0; s3 < 3; ++s3)
-            if (s3 < cnt) {
-              const double l0 = creg[s3][0] * exp_tab(acc[s3][0], sT);
-              const double l1 = creg[s3][1] * exp_tab(acc[s3][1], sT);
-              const int m = 8 * ti[s3] + g, mp = 8 * tj[s3] + 2 * t;
-              *reinterpret_cast<double2*>(Lb + m * RSL + mp) = make_double2(l0, l1);
-              if (ti[s3] != tj[s3]) {
-                Lb[mp * RSL + m] = l0;
-                Lb[(mp + 1) * RSL + m] = l1;
-              }
+        for (int s3 = 0; s3 < 3; ++s3)
+          if (s3 < cnt) {
+            const double l0 = creg[s3][0] * exp_tab(acc[s3][0], sT);
+            const double l1 = creg[s3][1] * exp_tab(acc[s3][1], sT);
+            const int m = 8 * ti[s3] + g, mp = 8 * tj[s3] + 2 * t;
+            *reinterpret_cast<double2*>(Lb + m * RSL + mp) = make_double2(l0, l1);
+            if (ti[s3] != tj[s3]) {
+              Lb[mp * RSL + m] = l0;
+              Lb[(mp + 1) * RSL + m] = l1;
             }
-        }
-        __syncthreads();
-        if (tid >= 64 && tid < 128) {
+          }
+      };
+      if (r0 < r1) s1e(r0);
+      __syncthreads();
+      for (int64_t n = r0; n < r1; ++n) {
+        const int s = (int)(n & 1);
+        const double* v = sV + (n % 3) * VB;
+        const double* Lb = sL + s * 64 * RSL;
+        if (tid >= 64 && tid < 128) {             // lambda_m = full row sum of the symmetric tile
           const int m = tid - 64;
           const double2* row = reinterpret_cast<const double2*>(Lb + m * RSL);
           double s0 = 0.0, s1 = 0.0;
@@ -364,11 +388,19 @@ k_psi2_bwd16(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __re
           red_add(lamg + n * Mp + I * 64 + m, s0 + s1);
         }
         if (n > r0) flush_wq(n - 1);
-        stage2I(v, Lb, s);
+        const double nxt = vec_load(n + 2);
+        if (groupB) {
+          if (n + 1 < r1) s1e(n + 1);
+          stage2I(v, Lb, s);
+        } else {
+          stage2I(v, Lb, s);
+          if (n + 1 < r1) s1e(n + 1);
+        }
+        if (tid < VB) sV[((n + 2) % 3) * VB + tid] = nxt;
+        __syncthreads();
       }
     }
-    __syncthreads();
-    if (r1 > r0) flush_wq(r1 - 1);
+    if (r1 > r0) flush_wq(r1 - 1);               // the loop ended with a barrier
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
