@@ -170,6 +170,67 @@ static void probe_inflight(int sms, double* out) {
   }
 }
 
+// DMMA throughput while fragments stream from shared memory: per iteration NA + NB LDS.64
+// fragment loads (conflict-free [64][68] tile pattern) feed NA x NB DMMAs.
+template <int NA, int NB>
+__global__ void k_dmma_lds(int iters, double* out) {
+  extern __shared__ double smd[];
+  for (int i = threadIdx.x; i < 2 * 64 * 68; i += blockDim.x) smd[i] = 1e-3 * (i % 97);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const double* pa = smd + ((wid * 8) % 32 + g) * 68 + t;
+  const double* pb = smd + 64 * 68 + ((wid * 8) % 32 + g) * 68 + t;
+  double c[NA][NB][2];
+#pragma unroll
+  for (int i = 0; i < NA; ++i)
+#pragma unroll
+    for (int j = 0; j < NB; ++j) c[i][j][0] = c[i][j][1] = 0.0;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll 4
+    for (int k0 = 0; k0 < 64; k0 += 4) {
+      double a[NA], b[NB];
+#pragma unroll
+      for (int i = 0; i < NA; ++i) a[i] = pa[(i * 8 % 32) * 68 + k0];
+#pragma unroll
+      for (int j = 0; j < NB; ++j) b[j] = pb[(j * 8 % 32) * 68 + k0];
+#pragma unroll
+      for (int i = 0; i < NA; ++i)
+#pragma unroll
+        for (int j = 0; j < NB; ++j) dmma884(c[i][j][0], c[i][j][1], a[i], b[j]);
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < NA; ++i)
+#pragma unroll
+    for (int j = 0; j < NB; ++j) s += c[i][j][0] + c[i][j][1];
+  if (s == 123.456) out[0] = s;
+}
+
+template <int NA, int NB>
+static void probe_dmma_lds(int sms, double* out) {
+  CK(cudaFuncSetAttribute(k_dmma_lds<NA, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 64 * 68 * 8));
+  for (int warps : {8, 16}) {
+    int iters = 4000 / (NA * NB);
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    k_dmma_lds<NA, NB><<<sms, warps * 32, 2 * 64 * 68 * 8>>>(iters, out);
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(e0));
+    k_dmma_lds<NA, NB><<<sms, warps * 32, 2 * 64 * 68 * 8>>>(iters, out);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    double dmma_per_sched = (double)iters * 16 * NA * NB * warps / 4.0;
+    double cycles = ms * 1e-3 * 1.965e9;
+    printf("{\"probe\": \"dmma_lds\", \"tile\": \"%dx%d\", \"lds_per_dmma\": %.3f, \"warps_per_sm\": %d, "
+           "\"frac_of_dmma_peak\": %.3f}\n", NA, NB, (double)(NA + NB) / (NA * NB), warps,
+           16.0 / (cycles / dmma_per_sched));
+  }
+}
+
 template <typename F>
 static float time_ms(F f, int reps = 5) {
   cudaEvent_t e0, e1;
@@ -258,6 +319,11 @@ int main() {
       }
     }
   }
+  // 6. DMMA fed from shared memory
+  probe_dmma_lds<1, 1>(sms, out);
+  probe_dmma_lds<2, 2>(sms, out);
+  probe_dmma_lds<2, 4>(sms, out);
+  probe_dmma_lds<4, 4>(sms, out);
   // 5. DMMA latency / accumulators in flight
   probe_inflight<1>(sms, out);
   probe_inflight<2>(sms, out);

@@ -18,7 +18,7 @@ struct P2Cfg16 {
   static constexpr int NJ = QC / 32;        // 8-wide q tiles per warp in stage 2
   static constexpr int VB = QC + 128;
   static constexpr int BWD_SMEM =
-      (2 * 64 * RS + 2 * 64 * RSL + 3 * VB + 2 * 4 * QC + 2 * 4 * 64 + 2 * 4 * 64 + 256) * 8;
+      (4 * 64 * RS + 2 * 64 * RSL + 3 * VB + 2 * 4 * QC + 2 * 4 * 64 + 2 * 4 * 64 + 256) * 8;
 };
 
 // Sum v[0..3] over the 8 lanes that differ in lane bits 2..4.  Every lane ends with the total
@@ -62,7 +62,8 @@ RGP_DEVINL void diag_tiles16(int wid, int (&ti)[3], int (&tj)[3], int& cnt) {
 }
 
 template <int QC, int CNT>
-RGP_DEVINL void stage1_diag16_n(const double* __restrict__ sZ, const double* __restrict__ v, int qk,
+RGP_DEVINL void stage1_diag16_n(const double* __restrict__ sZ, const double* __restrict__ sZw,
+                                const double* __restrict__ v, int qk,
                                 const int (&ti)[3], const int (&tj)[3], int lane, double (&acc)[3][2]) {
   constexpr int RS = P2Cfg16<QC>::RS;
   const int g = lane >> 2, t = lane & 3;
@@ -70,7 +71,7 @@ RGP_DEVINL void stage1_diag16_n(const double* __restrict__ sZ, const double* __r
   const double* pb[CNT];
 #pragma unroll
   for (int s = 0; s < CNT; ++s) {
-    pa[s] = sZ + (8 * ti[s] + g) * RS + t;
+    pa[s] = sZw + (8 * ti[s] + g) * RS + t;
     pb[s] = sZ + (8 * tj[s] + g) * RS + t;
     const double hi = v[QC + 8 * ti[s] + g];
     const double2 hj = *reinterpret_cast<const double2*>(v + QC + 8 * tj[s] + 2 * t);
@@ -79,11 +80,10 @@ RGP_DEVINL void stage1_diag16_n(const double* __restrict__ sZ, const double* __r
   }
 #pragma unroll 2
   for (int k0 = 0; k0 < qk; k0 += 4) {
-    const double wv = v[k0 + t];
     double a[CNT], b[CNT];
 #pragma unroll
     for (int s = 0; s < CNT; ++s) {
-      a[s] = pa[s][k0] * wv;
+      a[s] = pa[s][k0];
       b[s] = pb[s][k0];
     }
 #pragma unroll
@@ -108,6 +108,7 @@ k_psi2_bwd16(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __re
   double* sLr = sWq + 2 * 4 * QC;                 // [2][4 wc][64]
   double* sLc = sLr + 2 * 4 * 64;                 // [2][4 wr][64]
   double* sT = sLc + 2 * 4 * 64;                  // exp table
+  double* sZW = sT + 256;                         // 2 slots of 64*RS: ws(n) * Z'_I, built one row ahead
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int wr = wid >> 2, wc = wid & 3, g = lane >> 2, t = lane & 3;
@@ -150,6 +151,23 @@ k_psi2_bwd16(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __re
     for (int i = 0; i < 2; ++i)
 #pragma unroll
       for (int j = 0; j < NJ; ++j) accI[i][j][0] = accI[i][j][1] = accJ[i][j][0] = accJ[i][j][1] = 0.0;
+    __syncthreads();
+
+    // Pre-weighted stage-1 operand: sZW[n & 1][m][q] = ws_nq * Z'_I[m][q].  Keeping the multiply out
+    // of the DMMA loops matters: ncu showed warps stalled at in-loop DMULs waiting for an FP64
+    // pipe that other warps' 16-cycle DMMAs keep busy (30 % of all stall samples).  Thread t owns
+    // column q = t % QC of every row it touches, so it needs a single ws value per row.
+    auto ws_of = [&](int64_t n) -> double { return n < r1 ? wrow[n * QC + (tid & (QC - 1))] : 0.0; };
+    auto build_zw = [&](int64_t n, double wsq) {
+      double* dst = sZW + (n & 1) * 64 * RS;
+#pragma unroll
+      for (int e = tid; e < 64 * QC; e += P2_THREADS16) {
+        const int m = e / QC, q = e & (QC - 1);
+        dst[m * RS + q] = sZI[m * RS + q] * wsq;
+      }
+    };
+    if (r0 < r1) build_zw(r0, ws_of(r0));
+    if (r0 + 1 < r1) build_zw(r0 + 1, ws_of(r0 + 1));
     __syncthreads();
 
     auto flush_wq = [&](int64_t n) {
@@ -237,7 +255,7 @@ k_psi2_bwd16(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __re
         const double* v = sV + (n % 3) * VB;
         double* Lb = sL + s * 64 * RSL;
         double acc[2][2][2];
-        const double* pa = sZI + (16 * wr + g) * RS + t;
+        const double* pa = sZW + s * 64 * RS + (16 * wr + g) * RS + t;
         const double* pb = sZJ + (16 * wc + g) * RS + t;
         const double* vI = v + QC + 16 * wr + g;
         const double* vJ = v + QC + 64 + 16 * wc + 2 * t;
@@ -253,10 +271,9 @@ k_psi2_bwd16(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __re
         }
 #pragma unroll 4
         for (int k0 = 0; k0 < qk; k0 += 4) {
-          const double wv = v[k0 + t];
           double a[2], bb[2];
 #pragma unroll
-          for (int i = 0; i < 2; ++i) a[i] = pa[i * 8 * RS + k0] * wv;
+          for (int i = 0; i < 2; ++i) a[i] = pa[i * 8 * RS + k0];
 #pragma unroll
           for (int j = 0; j < 2; ++j) bb[j] = pb[j * 8 * RS + k0];
 #pragma unroll
@@ -295,23 +312,34 @@ k_psi2_bwd16(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __re
         const double* v = sV + (n % 3) * VB;
         const double* Lb = sL + s * 64 * RSL;
         stage2I(v, Lb, s);
-        // stage 2-J: accJ[m',q] += sum_m L[m,m'] (ws_q ZI[m,q])
+        // stage 2-J: TJ[m',q] = sum_m L[m,m'] ZI[m,q];  accJ += ws_q TJ   (weight applied after the MMA)
         const double* pa = Lb + t * RSL + 16 * wr + g;
         const double* pb = sZI + t * RS + qbase + g;
-        double wq[NJ];
+        double TJ[2][NJ][2];
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) wq[j] = v[qbase + 8 * j + g];
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) TJ[i][j][0] = TJ[i][j][1] = 0.0;
 #pragma unroll 4
         for (int k0 = 0; k0 < 64; k0 += 4) {
           double a[2], bq[NJ];
 #pragma unroll
           for (int i = 0; i < 2; ++i) a[i] = pa[k0 * RSL + 8 * i];
 #pragma unroll
-          for (int j = 0; j < NJ; ++j) bq[j] = pb[k0 * RS + 8 * j] * wq[j];
+          for (int j = 0; j < NJ; ++j) bq[j] = pb[k0 * RS + 8 * j];
 #pragma unroll
           for (int i = 0; i < 2; ++i)
 #pragma unroll
-            for (int j = 0; j < NJ; ++j) dmma(accJ[i][j][0], accJ[i][j][1], a[i], bq[j]);
+            for (int j = 0; j < NJ; ++j) dmma(TJ[i][j][0], TJ[i][j][1], a[i], bq[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          const double2 wq = *reinterpret_cast<const double2*>(v + qbase + 8 * j + 2 * t);
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            accJ[i][j][0] = fma(wq.x, TJ[i][j][0], accJ[i][j][0]);
+            accJ[i][j][1] = fma(wq.y, TJ[i][j][1], accJ[i][j][1]);
+          }
         }
       };
       if (r0 < r1) s1e(r0);
@@ -329,6 +357,7 @@ k_psi2_bwd16(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __re
         }
         if (n > r0) flush_wq(n - 1);
         const double nxt = vec_load(n + 2);
+        const double wsn = ws_of(n + 2);
         if (groupB) {
           if (n + 1 < r1) s1e(n + 1);
           s2(n);
@@ -337,6 +366,7 @@ k_psi2_bwd16(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __re
           if (n + 1 < r1) s1e(n + 1);
         }
         if (tid < VB) sV[((n + 2) % 3) * VB + tid] = nxt;
+        if (n + 2 < r1) build_zw(n + 2, wsn);     // slot n&1: last read by S1E(n), before barrier n
         __syncthreads();
       }
     } else {
@@ -354,8 +384,8 @@ k_psi2_bwd16(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __re
         const double* v = sV + (n % 3) * VB;
         double* Lb = sL + s * 64 * RSL;
         double acc[3][2];
-        if (cnt == 3) stage1_diag16_n<QC, 3>(sZI, v, qk, ti, tj, lane, acc);
-        else stage1_diag16_n<QC, 2>(sZI, v, qk, ti, tj, lane, acc);
+        if (cnt == 3) stage1_diag16_n<QC, 3>(sZI, sZW + s * 64 * RS, v, qk, ti, tj, lane, acc);
+        else stage1_diag16_n<QC, 2>(sZI, sZW + s * 64 * RS, v, qk, ti, tj, lane, acc);
 #pragma unroll
         for (int s3 = 0; s3 < 3; ++s3)
           if (s3 < cnt) {
@@ -389,6 +419,7 @@ k_psi2_bwd16(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __re
         }
         if (n > r0) flush_wq(n - 1);
         const double nxt = vec_load(n + 2);
+        const double wsn = ws_of(n + 2);
         if (groupB) {
           if (n + 1 < r1) s1e(n + 1);
           stage2I(v, Lb, s);
@@ -397,6 +428,7 @@ k_psi2_bwd16(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __re
           if (n + 1 < r1) s1e(n + 1);
         }
         if (tid < VB) sV[((n + 2) % 3) * VB + tid] = nxt;
+        if (n + 2 < r1) build_zw(n + 2, wsn);     // slot n&1: last read by S1E(n), before barrier n
         __syncthreads();
       }
     }
