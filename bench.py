@@ -268,8 +268,18 @@ def ours(args):
             fl = None
         if fl is not None:
             ach = fl * rows_per_launch / (per_launch_ms * 1e-3) / 1e12
+            traffic = None
+            try:                # dram bytes/row of this kernel from the committed ncu capture, scaled to this launch
+                with open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")) as f:
+                    tr = json.load(f).get(name)
+                if tr and (M, Q) == (512, 64):
+                    traffic = tr["bytes_per_row"] * rows_per_launch
+            except Exception:
+                traffic = None
             roof = {"bound": "fp64", "kernel": name, "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-                    "frac": ach / peak_tf if peak_tf else None, "traffic": None,
+                    "frac": ach / peak_tf if peak_tf else None, "traffic": traffic,
+                    "traffic_note": "dram bytes/launch = ncu dram__bytes per row at a 65536-row capture "
+                                    "(profiles/ncu_traffic_r01.json) x rows per launch",
                     "peak_source": "DFMA-chain microbenchmark run in this process (rgp_psi_fp64_peak); "
                                    "MEASURED_PEAKS.json has no fp64 entry",
                     "launch_ms": per_launch_ms, "launches": cnt,

@@ -95,7 +95,7 @@ static int launch_bwd(rgp_psi_ctx* h, cudaStream_t st, const Shape& s, int64_t r
   if constexpr (QC >= 32) {
     if (h->bwd_warps == 16) {
       RGP_LAUNCH(h, st, "psi2_bwd", (k_psi2_bwd16<QC>), dim3(R, G), P2_THREADS16, P2Cfg16<QC>::BWD_SMEM, rows,
-                 s.Mp, s.nt, s.nblocks, s.qk, Zt, Ct, w, HP, lam, Wq, ACCp);
+                 s.Mp, s.nt, s.nblocks, s.qk, Zt, Ct, w, HP, lam, Wq, ACCp, h->debug_skip);
       return 0;
     }
   }

@@ -96,7 +96,10 @@ __global__ void __launch_bounds__(P2_THREADS16, 1)
 k_psi2_bwd16(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __restrict__ Zt,
              const double* __restrict__ Ct, const double* __restrict__ wrow,
              const double* __restrict__ HP, double* __restrict__ lam, double* __restrict__ Wq,
-             double* __restrict__ ACCp) {
+             double* __restrict__ ACCp, int dbg) {
+  // dbg: timing-experiment mask (0 in production; results are wrong when non-zero):
+  // 1 skip exp, 2 skip lambda sums, 4 skip Wq reduce, 8 skip folds, 16 skip L store, 32 skip flushes,
+  // 64 skip pre-weighted tile build, 128 skip the per-row barrier
   using C = P2Cfg16<QC>;
   constexpr int RS = C::RS, VB = C::VB, NJ = C::NJ;
   extern __shared__ __align__(16) double smem[];
@@ -188,8 +191,9 @@ k_psi2_bwd16(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __re
         for (int j = 0; j < NJ; ++j) T[i][j][0] = T[i][j][1] = 0.0;
       const double* pa = Lb + (16 * wr + g) * RSL + t;
       const double* pb = sZJ + t * RS + qbase + g;
+      const int kend2i = (dbg & 256) ? 0 : 64;
 #pragma unroll 4
-      for (int k0 = 0; k0 < 64; k0 += 4) {
+      for (int k0 = 0; k0 < kend2i; k0 += 4) {
         double a[2], bq[NJ];
 #pragma unroll
         for (int i = 0; i < 2; ++i) a[i] = pa[i * 8 * RSL + k0];
@@ -216,6 +220,10 @@ k_psi2_bwd16(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __re
         }
         wp[2 * j] = w0;
         wp[2 * j + 1] = w1;
+      }
+      if (dbg & 4) {
+        if (wp[0] == 1.2345e-300) sWq[0] = 1.0;
+        return;
       }
       if constexpr (NJ == 2) {
         const double tot = reduce4_over_g(wp, lane);
@@ -269,8 +277,9 @@ k_psi2_bwd16(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __re
             acc[i][j][1] = hi + hj.y;
           }
         }
+        const int kend1 = (dbg & 1024) ? 0 : qk;
 #pragma unroll 4
-        for (int k0 = 0; k0 < qk; k0 += 4) {
+        for (int k0 = 0; k0 < kend1; k0 += 4) {
           double a[2], bb[2];
 #pragma unroll
           for (int i = 0; i < 2; ++i) a[i] = pa[i * 8 * RS + k0];
@@ -287,14 +296,19 @@ k_psi2_bwd16(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __re
         for (int i = 0; i < 2; ++i)
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
-            const double l0 = creg[i][j][0] * exp_tab(acc[i][j][0], sT);
-            const double l1 = creg[i][j][1] * exp_tab(acc[i][j][1], sT);
-            *reinterpret_cast<double2*>(Lb + (16 * wr + 8 * i + g) * RSL + 16 * wc + 8 * j + 2 * t) =
-                make_double2(l0, l1);
+            const double l0 = creg[i][j][0] * ((dbg & 1) ? acc[i][j][0] : exp_tab(acc[i][j][0], sT));
+            const double l1 = creg[i][j][1] * ((dbg & 1) ? acc[i][j][1] : exp_tab(acc[i][j][1], sT));
+            if (!(dbg & 16))
+              *reinterpret_cast<double2*>(Lb + (16 * wr + 8 * i + g) * RSL + 16 * wc + 8 * j + 2 * t) =
+                  make_double2(l0, l1);
             rs[i] += l0 + l1;
             cs[2 * j] += l0;
             cs[2 * j + 1] += l1;
           }
+        if (dbg & 2) {
+          if (rs[0] + cs[0] == 1.2345e-300) sLr[0] = 1.0;
+          return;
+        }
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], 1);
@@ -320,8 +334,9 @@ k_psi2_bwd16(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __re
         for (int i = 0; i < 2; ++i)
 #pragma unroll
           for (int j = 0; j < NJ; ++j) TJ[i][j][0] = TJ[i][j][1] = 0.0;
+        const int kend2j = (dbg & 512) ? 0 : 64;
 #pragma unroll 4
-        for (int k0 = 0; k0 < 64; k0 += 4) {
+        for (int k0 = 0; k0 < kend2j; k0 += 4) {
           double a[2], bq[NJ];
 #pragma unroll
           for (int i = 0; i < 2; ++i) a[i] = pa[k0 * RSL + 8 * i];
@@ -346,7 +361,8 @@ k_psi2_bwd16(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __re
       __syncthreads();
       for (int64_t n = r0; n < r1; ++n) {
         const int s = (int)(n & 1);
-        if (tid >= 64 && tid < 128) {
+        if (dbg & 32) {
+        } else if (tid >= 64 && tid < 128) {
           const int m = tid - 64;
           const double* p = sLr + s * 256 + m;
           red_add(lamg + n * Mp + I * 64 + m, p[0] + p[64] + p[128] + p[192]);
@@ -355,7 +371,7 @@ k_psi2_bwd16(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __re
           const double* p = sLc + s * 256 + m;
           red_add(lamg + n * Mp + J * 64 + m, p[0] + p[64] + p[128] + p[192]);
         }
-        if (n > r0) flush_wq(n - 1);
+        if (n > r0 && !(dbg & 32)) flush_wq(n - 1);
         const double nxt = vec_load(n + 2);
         const double wsn = ws_of(n + 2);
         if (groupB) {
@@ -366,8 +382,8 @@ k_psi2_bwd16(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __re
           if (n + 1 < r1) s1e(n + 1);
         }
         if (tid < VB) sV[((n + 2) % 3) * VB + tid] = nxt;
-        if (n + 2 < r1) build_zw(n + 2, wsn);     // slot n&1: last read by S1E(n), before barrier n
-        __syncthreads();
+        if (n + 2 < r1 && !(dbg & 64)) build_zw(n + 2, wsn);   // slot n&1: last read by S1E(n), before barrier n
+        if (!(dbg & 128)) __syncthreads();
       }
     } else {
       int ti[3], tj[3], cnt;
@@ -428,8 +444,8 @@ k_psi2_bwd16(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __re
           if (n + 1 < r1) s1e(n + 1);
         }
         if (tid < VB) sV[((n + 2) % 3) * VB + tid] = nxt;
-        if (n + 2 < r1) build_zw(n + 2, wsn);     // slot n&1: last read by S1E(n), before barrier n
-        __syncthreads();
+        if (n + 2 < r1 && !(dbg & 64)) build_zw(n + 2, wsn);   // slot n&1: last read by S1E(n), before barrier n
+        if (!(dbg & 128)) __syncthreads();
       }
     }
     if (r1 > r0) flush_wq(r1 - 1);               // the loop ended with a barrier
