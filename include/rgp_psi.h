@@ -54,7 +54,7 @@ typedef enum {
 } rgp_psi_status;
 
 /* Which kernels serve a call.  AUTO picks FAST when the shape is supported
- * (Q <= 64) and REFERENCE otherwise.  REFERENCE = the simple one-thread-per-output
+ * (Q <= 128) and REFERENCE otherwise.  REFERENCE = the simple one-thread-per-output
  * kernels kept as an on-device cross-check. */
 typedef enum { RGP_PSI_IMPL_AUTO = 0, RGP_PSI_IMPL_FAST = 1, RGP_PSI_IMPL_REFERENCE = 2 } rgp_psi_impl;
 

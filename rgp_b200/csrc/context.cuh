@@ -36,6 +36,7 @@ struct rgp_psi_ctx {
   int64_t row_chunk = 0;
   int profile = 0;
   int bwd_warps = 16;     // 8 or 16 warps per CTA in the Psi2 backward kernel (QC >= 32)
+  long long* trace = nullptr;   // optional device buffer for the bwd16 timeline trace (16*16*8 int64)
   int debug_skip = 0;     // timing experiments only (see psi2_bwd16.cuh); 0 in production
   int fwd_smem_pad = 0;   // tuning knob: extra dynamic smem for k_psi2_fwd (forces 1 CTA/SM)
   // device workspace arena (grow-only) and a bump pointer valid for one call

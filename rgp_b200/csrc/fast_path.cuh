@@ -10,8 +10,8 @@
 namespace rgp {
 namespace fast {
 
-static inline bool supported(int M, int Q) { return Q >= 1 && Q <= 64 && M >= 1; }
-static inline int qc_for(int Q) { return Q <= 16 ? 16 : (Q <= 32 ? 32 : 64); }
+static inline bool supported(int M, int Q) { return Q >= 1 && Q <= 128 && M >= 1; }
+static inline int qc_for(int Q) { return Q <= 16 ? 16 : (Q <= 32 ? 32 : (Q <= 64 ? 64 : 128)); }
 
 static int init(rgp_psi_ctx*) {
   RGP_CUDA(cudaFuncSetAttribute(k_psi2_fwd<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<16>::FWD_SMEM));
@@ -20,6 +20,8 @@ static int init(rgp_psi_ctx*) {
   RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwd<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<16>::BWD_SMEM));
   RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwd<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<32>::BWD_SMEM));
   RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwd<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<64>::BWD_SMEM));
+  RGP_CUDA(cudaFuncSetAttribute(k_psi2_fwd<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<128>::FWD_SMEM));
+  RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwd<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<128>::BWD_SMEM));
   RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwd16<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg16<32>::BWD_SMEM));
   RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwd16<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg16<64>::BWD_SMEM));
   return 0;
@@ -92,15 +94,16 @@ template <int QC>
 static int launch_bwd(rgp_psi_ctx* h, cudaStream_t st, const Shape& s, int64_t rows, int R, int G,
                       const double* Zt, const double* Ct, const double* w, const double* HP,
                       double* lam, double* Wq, double* ACCp) {
-  if constexpr (QC >= 32) {
+  if constexpr (QC == 32 || QC == 64) {
     if (h->bwd_warps == 16) {
       RGP_LAUNCH(h, st, "psi2_bwd", (k_psi2_bwd16<QC>), dim3(R, G), P2_THREADS16, P2Cfg16<QC>::BWD_SMEM, rows,
-                 s.Mp, s.nt, s.nblocks, s.qk, Zt, Ct, w, HP, lam, Wq, ACCp, h->debug_skip);
+                 s.Mp, s.nt, s.nblocks, s.qk, Zt, Ct, w, HP, lam, Wq, ACCp, h->debug_skip, h->trace);
       return 0;
     }
   }
-  RGP_LAUNCH(h, st, "psi2_bwd", (k_psi2_bwd<QC>), dim3(R, G), P2_THREADS, P2Cfg<QC>::BWD_SMEM, rows,
-             s.Mp, s.nt, s.nblocks, s.qk, Zt, Ct, w, HP, lam, Wq, ACCp);
+  for (int qoff = 0; qoff < QC; qoff += P2Cfg<QC>::QS)   // two passes for QC = 128
+    RGP_LAUNCH(h, st, "psi2_bwd", (k_psi2_bwd<QC>), dim3(R, G), P2_THREADS, P2Cfg<QC>::BWD_SMEM, rows,
+               s.Mp, s.nt, s.nblocks, s.qk, Zt, Ct, w, HP, lam, Wq, ACCp, qoff);
   return 0;
 }
 
@@ -173,7 +176,8 @@ static int forward(rgp_psi_ctx* h, cudaStream_t st, int64_t N, int M, int Q, con
     Rc = std::min(Rc, R);
     if (QC == 16) RGP_TRY(launch_fwd<16>(h, st, s, rows, Rc, Gc, Zt, w, HP, P2p));
     else if (QC == 32) RGP_TRY(launch_fwd<32>(h, st, s, rows, Rc, Gc, Zt, w, HP, P2p));
-    else RGP_TRY(launch_fwd<64>(h, st, s, rows, Rc, Gc, Zt, w, HP, P2p));
+    else if (QC == 64) RGP_TRY(launch_fwd<64>(h, st, s, rows, Rc, Gc, Zt, w, HP, P2p));
+    else RGP_TRY(launch_fwd<128>(h, st, s, rows, Rc, Gc, Zt, w, HP, P2p));
     RGP_LAUNCH(h, st, "psi2_reduce", k_psi2_reduce, s.nblocks, 256, 0, M, s.nt, Rc, variance * variance,
                P2p, chunk > 0 ? 1 : 0, psi2);
   }
@@ -249,7 +253,8 @@ static int backward(rgp_psi_ctx* h, cudaStream_t st, int64_t N, int M, int Q, co
     }
     if (QC == 16) RGP_TRY(launch_bwd<16>(h, st, s, rows, Rc, Gc, Zt, Ct, w, HP, lam, Wq, ACCp));
     else if (QC == 32) RGP_TRY(launch_bwd<32>(h, st, s, rows, Rc, Gc, Zt, Ct, w, HP, lam, Wq, ACCp));
-    else RGP_TRY(launch_bwd<64>(h, st, s, rows, Rc, Gc, Zt, Ct, w, HP, lam, Wq, ACCp));
+    else if (QC == 64) RGP_TRY(launch_bwd<64>(h, st, s, rows, Rc, Gc, Zt, Ct, w, HP, lam, Wq, ACCp));
+    else RGP_TRY(launch_bwd<128>(h, st, s, rows, Rc, Gc, Zt, Ct, w, HP, lam, Wq, ACCp));
     if (Gc > 1) {
       RGP_LAUNCH(h, st, "collapse", k_collapse, ceil_div(rows * Mp, 256), 256, 0, rows * Mp, Gc, lam);
       RGP_LAUNCH(h, st, "collapse", k_collapse, ceil_div(rows * QC, 256), 256, 0, rows * QC, Gc, Wq);

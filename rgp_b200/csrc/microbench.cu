@@ -231,6 +231,83 @@ static void probe_dmma_lds(int sms, double* out) {
   }
 }
 
+// Row-loop mimic of the backward kernel: per "row" LOOPS short MMA loops of KSTEPS k-steps on a
+// 2x2 tile, accumulators reset per loop and folded into persistent registers with a few DFMAs;
+// optional __syncthreads per row.  Isolates the cost of short loops / phase boundaries.
+template <int LOOPS, int KSTEPS, bool SYNC>
+__global__ void k_rowloop(int rows, double* out) {
+  extern __shared__ double smd[];
+  for (int i = threadIdx.x; i < 3 * 64 * 68; i += blockDim.x) smd[i] = 1e-3 * (i % 97);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int wr = wid >> 2, wc = wid & 3;
+  double keep[2][2][2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) keep[i][j][0] = keep[i][j][1] = 0.0;
+  for (int n = 0; n < rows; ++n) {
+#pragma unroll
+    for (int l = 0; l < LOOPS; ++l) {
+      const double* pa = smd + (l % 3) * 64 * 68 + (16 * wr + g) * 68 + t;
+      const double* pb = smd + ((l + 1) % 3) * 64 * 68 + (16 * wc + g) * 68 + t;
+      double c[2][2][2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) c[i][j][0] = c[i][j][1] = 0.0;
+#pragma unroll 4
+      for (int k0 = 0; k0 < 4 * KSTEPS; k0 += 4) {
+        double a[2], b[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) a[i] = pa[i * 8 * 68 + k0];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) b[j] = pb[j * 8 * 68 + k0];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) dmma884(c[i][j][0], c[i][j][1], a[i], b[j]);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          keep[i][j][0] = fma(c[i][j][0], 0.5, keep[i][j][0]);
+          keep[i][j][1] = fma(c[i][j][1], 0.5, keep[i][j][1]);
+        }
+    }
+    if (SYNC) __syncthreads();
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) s += keep[i][j][0] + keep[i][j][1];
+  if (s == 123.456) out[0] = s;
+}
+
+template <int LOOPS, int KSTEPS, bool SYNC>
+static void probe_rowloop(int sms, double* out) {
+  const int smem = 3 * 64 * 68 * 8;
+  CK(cudaFuncSetAttribute(k_rowloop<LOOPS, KSTEPS, SYNC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  int rows = 6000 * 3 * 16 / (LOOPS * KSTEPS);
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  k_rowloop<LOOPS, KSTEPS, SYNC><<<sms, 512, smem>>>(rows, out);
+  CK(cudaDeviceSynchronize());
+  CK(cudaEventRecord(e0));
+  k_rowloop<LOOPS, KSTEPS, SYNC><<<sms, 512, smem>>>(rows, out);
+  CK(cudaEventRecord(e1));
+  CK(cudaEventSynchronize(e1));
+  float ms;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  double dmma_per_sched = (double)rows * LOOPS * KSTEPS * 4 * 4;   // 4 warps/scheduler, 4 DMMA per k-step
+  double cycles = ms * 1e-3 * 1.965e9;
+  printf("{\"probe\": \"rowloop\", \"loops_per_row\": %d, \"ksteps\": %d, \"sync\": %d, \"frac_of_dmma_peak\": %.3f}\n",
+         LOOPS, KSTEPS, (int)SYNC, 16.0 / (cycles / dmma_per_sched));
+}
+
 template <typename F>
 static float time_ms(F f, int reps = 5) {
   cudaEvent_t e0, e1;
@@ -319,6 +396,13 @@ int main() {
       }
     }
   }
+  // 7. short-loop / phase-boundary cost
+  probe_rowloop<3, 16, false>(sms, out);
+  probe_rowloop<3, 16, true>(sms, out);
+  probe_rowloop<1, 48, false>(sms, out);
+  probe_rowloop<1, 48, true>(sms, out);
+  probe_rowloop<6, 8, false>(sms, out);
+  probe_rowloop<3, 64, false>(sms, out);
   // 6. DMMA fed from shared memory
   probe_dmma_lds<1, 1>(sms, out);
   probe_dmma_lds<2, 2>(sms, out);

@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(P2_THREADS16, 1)
 k_psi2_bwd16(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __restrict__ Zt,
              const double* __restrict__ Ct, const double* __restrict__ wrow,
              const double* __restrict__ HP, double* __restrict__ lam, double* __restrict__ Wq,
-             double* __restrict__ ACCp, int dbg) {
+             double* __restrict__ ACCp, int dbg, long long* __restrict__ trace) {
   // dbg: timing-experiment mask (0 in production; results are wrong when non-zero):
   // 1 skip exp, 2 skip lambda sums, 4 skip Wq reduce, 8 skip folds, 16 skip L store, 32 skip flushes,
   // 64 skip pre-weighted tile build, 128 skip the per-row barrier
@@ -163,10 +163,17 @@ k_psi2_bwd16(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __re
     auto ws_of = [&](int64_t n) -> double { return n < r1 ? wrow[n * QC + (tid & (QC - 1))] : 0.0; };
     auto build_zw = [&](int64_t n, double wsq) {
       double* dst = sZW + (n & 1) * 64 * RS;
+      constexpr int PER = 64 * QC / P2_THREADS16;
+      double tmp[PER];                               // batch the loads: dst may alias sZI for the compiler
 #pragma unroll
-      for (int e = tid; e < 64 * QC; e += P2_THREADS16) {
-        const int m = e / QC, q = e & (QC - 1);
-        dst[m * RS + q] = sZI[m * RS + q] * wsq;
+      for (int u = 0; u < PER; ++u) {
+        const int e = tid + u * P2_THREADS16;
+        tmp[u] = sZI[(e / QC) * RS + (e & (QC - 1))];
+      }
+#pragma unroll
+      for (int u = 0; u < PER; ++u) {
+        const int e = tid + u * P2_THREADS16;
+        dst[(e / QC) * RS + (e & (QC - 1))] = tmp[u] * wsq;
       }
     };
     if (r0 < r1) build_zw(r0, ws_of(r0));
@@ -372,18 +379,31 @@ k_psi2_bwd16(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __re
           red_add(lamg + n * Mp + J * 64 + m, p[0] + p[64] + p[128] + p[192]);
         }
         if (n > r0 && !(dbg & 32)) flush_wq(n - 1);
+        // optional timeline trace (profiling builds of the bench only): CTA 0, block 1, rows 8..23
+        const bool tr = trace && blockIdx.x == 0 && blockIdx.y == 0 && b == 1 && n >= r0 + 8 && n < r0 + 24 && lane == 0;
+        long long* tp = trace + ((n - r0 - 8) * 16 + wid) * 8;
+        if (tr) tp[0] = clock64();
         const double nxt = vec_load(n + 2);
         const double wsn = ws_of(n + 2);
+        // the pre-weighted tile of row n+2 (slot n&1, last read by S1E(n) before barrier n) is built
+        // between the two phases, while the other warp group is inside an MMA loop
         if (groupB) {
           if (n + 1 < r1) s1e(n + 1);
+          if (tr) tp[1] = clock64();
+          if (n + 2 < r1 && !(dbg & 64)) build_zw(n + 2, wsn);
+          if (tr) tp[2] = clock64();
           s2(n);
         } else {
           s2(n);
+          if (tr) tp[1] = clock64();
+          if (n + 2 < r1 && !(dbg & 64)) build_zw(n + 2, wsn);
+          if (tr) tp[2] = clock64();
           if (n + 1 < r1) s1e(n + 1);
         }
         if (tid < VB) sV[((n + 2) % 3) * VB + tid] = nxt;
-        if (n + 2 < r1 && !(dbg & 64)) build_zw(n + 2, wsn);   // slot n&1: last read by S1E(n), before barrier n
+        if (tr) tp[3] = clock64();
         if (!(dbg & 128)) __syncthreads();
+        if (tr) tp[4] = clock64();
       }
     } else {
       int ti[3], tj[3], cnt;
@@ -438,13 +458,14 @@ k_psi2_bwd16(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __re
         const double wsn = ws_of(n + 2);
         if (groupB) {
           if (n + 1 < r1) s1e(n + 1);
+          if (n + 2 < r1 && !(dbg & 64)) build_zw(n + 2, wsn);
           stage2I(v, Lb, s);
         } else {
           stage2I(v, Lb, s);
+          if (n + 2 < r1 && !(dbg & 64)) build_zw(n + 2, wsn);
           if (n + 1 < r1) s1e(n + 1);
         }
         if (tid < VB) sV[((n + 2) % 3) * VB + tid] = nxt;
-        if (n + 2 < r1 && !(dbg & 64)) build_zw(n + 2, wsn);   // slot n&1: last read by S1E(n), before barrier n
         if (!(dbg & 128)) __syncthreads();
       }
     }

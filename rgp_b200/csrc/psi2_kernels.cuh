@@ -38,11 +38,14 @@ constexpr int RSL = 68;
 template <int QC>
 struct P2Cfg {
   static constexpr int RS = QC + 4;
-  static constexpr int NJ = QC / 16;        // 8-wide q tiles per warp in stage 2
+  // stage-2 output width per pass: Q in (64, 128] runs the backward kernel twice, once per 64-wide
+  // q half (stage 1 + exp are recomputed; registers cannot hold 128-wide dZ accumulators)
+  static constexpr int QS = QC > 64 ? 64 : QC;
+  static constexpr int NJ = QS / 16;        // 8-wide q tiles per warp in stage 2
   static constexpr int VB = QC + 128;       // per-row vector slot: w[QC] | H_I[64] | H_J[64]
   static constexpr int FWD_SMEM = (2 * 64 * RS + 3 * VB + 256) * 8;
   static constexpr int BWD_SMEM =
-      (2 * 64 * RS + 2 * 64 * RSL + 3 * VB + 2 * 4 * QC + 2 * 2 * 64 + 2 * 4 * 64 + 256) * 8;
+      (2 * 64 * RS + 2 * 64 * RSL + 3 * VB + 2 * 4 * QS + 2 * 2 * 64 + 2 * 4 * 64 + 256) * 8;
 };
 
 RGP_DEVINL void dmma(double& d0, double& d1, double a, double b) {
@@ -282,16 +285,18 @@ __global__ void __launch_bounds__(P2_THREADS, 1)
 k_psi2_bwd(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __restrict__ Zt,
            const double* __restrict__ Ct, const double* __restrict__ wrow,
            const double* __restrict__ HP, double* __restrict__ lam, double* __restrict__ Wq,
-           double* __restrict__ ACCp) {
+           double* __restrict__ ACCp, int qoff) {
+  // qoff: first q column of this pass's stage-2 outputs (0, or 64 for the second pass of QC = 128);
+  // lambda is flushed by the qoff == 0 pass only.
   using C = P2Cfg<QC>;
-  constexpr int RS = C::RS, VB = C::VB, NJ = C::NJ;
+  constexpr int RS = C::RS, VB = C::VB, NJ = C::NJ, QS = C::QS;
   extern __shared__ __align__(16) double smem[];
   double* sZI = smem;
   double* sZJ = sZI + 64 * RS;
   double* sL = sZJ + 64 * RS;                     // 2 slots of 64*RSL
   double* sV = sL + 2 * 64 * RSL;                 // 3 slots of VB
-  double* sWq = sV + 3 * VB;                      // [2][4][QC]
-  double* sLr = sWq + 2 * 4 * QC;                 // [2][2][64]  row-sum partials (per wc)
+  double* sWq = sV + 3 * VB;                      // [2][4][QS]
+  double* sLr = sWq + 2 * 4 * QS;                 // [2][2][64]  row-sum partials (per wc)
   double* sLc = sLr + 2 * 2 * 64;                 // [2][4][64]  col-sum partials (per wr)
   double* sT = sLc + 2 * 4 * 64;                  // exp table, 256 entries
 
@@ -304,7 +309,7 @@ k_psi2_bwd(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __rest
   double* lamg = lam + (size_t)blockIdx.y * rc * Mp;
   double* Wqg = Wq + (size_t)blockIdx.y * rc * QC;
   double* accp = ACCp + (size_t)cta * Mp * QC;
-  const int qbase = wc * (QC / 2);                // this warp's q columns in stage 2
+  const int qbase = wc * (QS / 2);                // this warp's q columns in stage 2 (relative to qoff)
   exp_table_init(sT, tid);
 
   int curI = -1, curJ = -1;
@@ -338,10 +343,10 @@ k_psi2_bwd(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __rest
     // barrier of row n+1 (two slots; hazard analysis in DESIGN.md "Row pipeline").
     auto flush_wq = [&](int64_t n) {
       const int s = (int)(n & 1);
-      if (tid < QC) {
-        const double* p = sWq + s * 4 * QC + tid;
-        double v = p[0] + p[QC] + p[2 * QC] + p[3 * QC];
-        red_add(Wqg + n * QC + tid, diag ? v : 2.0 * v);
+      if (tid < QS) {
+        const double* p = sWq + s * 4 * QS + tid;
+        double v = p[0] + p[QS] + p[2 * QS] + p[3 * QS];
+        red_add(Wqg + n * QC + qoff + tid, diag ? v : 2.0 * v);
       }
     };
 
@@ -353,7 +358,7 @@ k_psi2_bwd(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __rest
 #pragma unroll
         for (int j = 0; j < NJ; ++j) T[i][j][0] = T[i][j][1] = 0.0;
       const double* pa = Lb + (16 * wr + g) * RSL + t;
-      const double* pb = sZJ + t * RS + qbase + g;
+      const double* pb = sZJ + t * RS + qoff + qbase + g;
 #pragma unroll 2
       for (int k0 = 0; k0 < 64; k0 += 4) {
         double a[2], bq[NJ];
@@ -369,7 +374,7 @@ k_psi2_bwd(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __rest
       double wp[2 * NJ];                           // Wq partials, index c = 2 j + e
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
-        const int q = qbase + 8 * j + 2 * t;
+        const int q = qoff + qbase + 8 * j + 2 * t;
         const double2 wq = *reinterpret_cast<const double2*>(v + q);
         double w0 = 0.0, w1 = 0.0;
 #pragma unroll
@@ -386,7 +391,7 @@ k_psi2_bwd(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __rest
       if constexpr (NJ == 4) {
         const double tot = reduce8_over_g(wp, lane);
         const int c = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-        sWq[s * 4 * QC + wr * QC + qbase + 8 * (c >> 1) + 2 * t + (c & 1)] = tot;
+        sWq[s * 4 * QS + wr * QS + qbase + 8 * (c >> 1) + 2 * t + (c & 1)] = tot;
       } else {
 #pragma unroll
         for (int c = 0; c < 2 * NJ; ++c) {
@@ -394,7 +399,7 @@ k_psi2_bwd(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __rest
           x += __shfl_xor_sync(0xffffffffu, x, 4);
           x += __shfl_xor_sync(0xffffffffu, x, 8);
           x += __shfl_xor_sync(0xffffffffu, x, 16);
-          if (g == 0) sWq[s * 4 * QC + wr * QC + qbase + 8 * (c >> 1) + 2 * t + (c & 1)] = x;
+          if (g == 0) sWq[s * 4 * QS + wr * QS + qbase + 8 * (c >> 1) + 2 * t + (c & 1)] = x;
         }
       }
     };
@@ -453,7 +458,8 @@ k_psi2_bwd(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __rest
           }
         }
         __syncthreads();   // L tile + lambda partials of row n complete; row n-1 fully finished
-        if (tid >= 64 && tid < 128) {
+        if (qoff != 0) {
+        } else if (tid >= 64 && tid < 128) {
           const int m = tid - 64;
           const double* p = sLr + s * 128 + m;
           red_add(lamg + n * Mp + I * 64 + m, p[0] + p[64]);
@@ -467,10 +473,10 @@ k_psi2_bwd(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __rest
         // stage 2-J: accJ[m',q] += sum_m L[m,m'] (ws_q ZI[m,q]).  A = L^T, B = ws * ZI
         {
           const double* pa = Lb + t * RSL + 16 * wr + g;
-          const double* pb = sZI + t * RS + qbase + g;
+          const double* pb = sZI + t * RS + qoff + qbase + g;
           double wq[NJ];
 #pragma unroll
-          for (int j = 0; j < NJ; ++j) wq[j] = v[qbase + 8 * j + g];
+          for (int j = 0; j < NJ; ++j) wq[j] = v[qoff + qbase + 8 * j + g];
 #pragma unroll 2
           for (int k0 = 0; k0 < 64; k0 += 4) {
             double a[2], bq[NJ];
@@ -519,7 +525,7 @@ k_psi2_bwd(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __rest
             }
         }
         __syncthreads();
-        if (tid >= 64 && tid < 128) {             // lambda_m = full row sum of the symmetric tile
+        if (qoff == 0 && tid >= 64 && tid < 128) { // lambda_m = full row sum of the symmetric tile
           const int m = tid - 64;
           const double2* row = reinterpret_cast<const double2*>(Lb + m * RSL);
           double s0 = 0.0, s1 = 0.0;
@@ -542,7 +548,7 @@ k_psi2_bwd(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __rest
     for (int i = 0; i < 2; ++i)
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
-        const int q = qbase + 8 * j + 2 * t;
+        const int q = qoff + qbase + 8 * j + 2 * t;
         double2* pI = reinterpret_cast<double2*>(accp + (size_t)(I * 64 + 16 * wr + 8 * i + g) * QC + q);
         double2 o = *pI;
         o.x += accI[i][j][0];

@@ -3,7 +3,7 @@
 // Z-Z' term, tails through the summed Psi2.  They share NO algebra with the fast path
 // (psi2_fwd.cuh / psi2_bwd.cuh use the factorised exponent), so they double as an
 // on-device cross-check at sizes the CPU oracle cannot reach, and they serve shapes
-// the fast path does not cover yet (Q > 64).  Still CUDA: there is no CPU fallback.
+// the fast path does not cover (Q > 128).  Still CUDA: there is no CPU fallback.
 #pragma once
 #include "common.cuh"
 

@@ -67,6 +67,8 @@ SHAPES = [
     (2048, 128, 16, 0),      # sweep corner
     (1024, 256, 32, 0),
     (640, 192, 64, 16),      # headline Q, M not a power of two
+    (300, 70, 100, 10),      # 64 < Q <= 128: two-pass backward
+    (257, 130, 128, 0),      # sweep corner Q
 ]
 
 
