@@ -310,3 +310,30 @@ def test_sharded_nccl_matches_single_gpu():
            "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(root, "scripts", "check_sharded_nccl.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+@pytest.mark.parametrize("chunk", [1000, 4096])
+def test_row_chunking_accumulates_exactly_like_one_pass(chunk):
+    """The library streams rows in chunks (<= 2^20 by default; the headline run uses four).
+    Force small chunks and compare with the oracle and with the single-chunk result."""
+    from rgp_b200.gpy_compat import RBF, NormalPosterior
+    from rgp_b200.psicomp import PSICOMP_RBF_B200
+    N, M, Q = 2500, 70, 12
+    var, ell, Z, mu, S = make_inputs(N, M, Q, seed=77, n_control=3)
+    dL0, dL1, dL2 = make_upstream(N, M, seed=78)
+    dL0 = np.random.default_rng(1).normal(size=N)                 # non-constant dL_dpsi0 across chunks
+    pc = PSICOMP_RBF_B200(cache=False)
+    pc.handle.set_option("row_chunk", chunk)
+    fwd, bwd = _run(pc, var, ell, Z, mu, S, dL0, dL1, dL2)
+    _compare(fwd, bwd, psi_forward(var, ell, Z, mu, S), psi_backward(dL0, dL1, dL2, var, ell, Z, mu, S), TIGHT)
+
+
+def test_options_are_validated():
+    from rgp_b200 import PsiError
+    from rgp_b200._lib import Handle
+    h = Handle(0)
+    h._ensure()
+    for key, val in (("impl", 7), ("bwd_warps", 12), ("row_chunk", -1), ("no_such_option", 1)):
+        with pytest.raises(PsiError):
+            h.set_option(key, val)
+        h._options.pop(key, None)
