@@ -135,9 +135,9 @@ class Handle:
 
     # -- options / measurement
     def set_option(self, key: str, value: int) -> None:
-        self._options[key] = int(value)
         if self._h is not None:
             check(load().rgp_psi_set_option(self._h, key.encode(), int(value)))
+        self._options[key] = int(value)          # remembered only once accepted (or until first use)
 
     def launch_count(self) -> int:
         return int(load().rgp_psi_launch_count(self._ensure()))

@@ -336,4 +336,4 @@ def test_options_are_validated():
     for key, val in (("impl", 7), ("bwd_warps", 12), ("row_chunk", -1), ("no_such_option", 1)):
         with pytest.raises(PsiError):
             h.set_option(key, val)
-        h._options.pop(key, None)
+        assert key not in h._options
