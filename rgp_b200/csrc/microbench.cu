@@ -286,6 +286,107 @@ __global__ void k_rowloop(int rows, double* out) {
   if (s == 123.456) out[0] = s;
 }
 
+// Same row loop plus a scalar FP64 "epilogue" per row: NEXP table-assisted exps per lane on the
+// accumulators of the first loop (8 FP64 ops + 1 LDS each, like the real kernel), a multiply and
+// two adds per element.  Measures how much DMMA throughput a realistic DMMA/DFMA mix can reach.
+template <int NEXP, bool SKEW>
+__global__ void k_rowloop_mix(int rows, double* out) {
+  extern __shared__ double smd[];
+  double* tab = smd + 3 * 64 * 68;
+  for (int i = threadIdx.x; i < 3 * 64 * 68; i += blockDim.x) smd[i] = 1e-3 * (i % 97);
+  rgp::exp_table_init(tab, threadIdx.x);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int wr = wid >> 2, wc = wid & 3;
+  const bool grpB = SKEW && ((wid >> 2) & 1);
+  double keep[2][2][2], sums = 0.0;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) keep[i][j][0] = keep[i][j][1] = 0.0;
+  auto mma_loop = [&](int l, double (&c)[2][2][2]) {
+    const double* pa = smd + (l % 3) * 64 * 68 + (16 * wr + g) * 68 + t;
+    const double* pb = smd + ((l + 1) % 3) * 64 * 68 + (16 * wc + g) * 68 + t;
+#pragma unroll 4
+    for (int k0 = 0; k0 < 64; k0 += 4) {
+      double a[2], b[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) a[i] = pa[i * 8 * 68 + k0];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) b[j] = pb[j * 8 * 68 + k0];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) dmma884(c[i][j][0], c[i][j][1], a[i], b[j]);
+    }
+  };
+  auto epilogue = [&](double (&c)[2][2][2]) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+          if (i * 4 + j * 2 + e < NEXP) {
+            double l = 1.0001 * rgp::exp_tab(-1e-3 * c[i][j][e] - 0.5, tab);
+            sums += l;
+            keep[i][j][e] += l;
+          }
+  };
+  for (int n = 0; n < rows; ++n) {
+    double c0[2][2][2], c1[2][2][2], c2[2][2][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) c0[i][j][e] = c1[i][j][e] = c2[i][j][e] = 0.0;
+    if (!grpB) {
+      mma_loop(0, c0); epilogue(c0); mma_loop(1, c1); mma_loop(2, c2);
+    } else {
+      mma_loop(1, c1); mma_loop(0, c0); epilogue(c0); mma_loop(2, c2);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        keep[i][j][0] = fma(c1[i][j][0], 0.5, keep[i][j][0]) + c2[i][j][0];
+        keep[i][j][1] = fma(c1[i][j][1], 0.5, keep[i][j][1]) + c2[i][j][1];
+      }
+    __syncthreads();
+  }
+  double s = sums;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) s += keep[i][j][0] + keep[i][j][1];
+  if (s == 123.456) out[0] = s;
+}
+
+template <int NEXP, bool SKEW>
+static void probe_rowloop_mix(int sms, double* out) {
+  const int smem = (3 * 64 * 68 + 256) * 8;
+  CK(cudaFuncSetAttribute(k_rowloop_mix<NEXP, SKEW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  int rows = 6000;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  k_rowloop_mix<NEXP, SKEW><<<sms, 512, smem>>>(rows, out);
+  CK(cudaDeviceSynchronize());
+  CK(cudaEventRecord(e0));
+  k_rowloop_mix<NEXP, SKEW><<<sms, 512, smem>>>(rows, out);
+  CK(cudaEventRecord(e1));
+  CK(cudaEventSynchronize(e1));
+  float ms;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  double dmma_per_sched = (double)rows * 3 * 16 * 4 * 4;
+  double cycles = ms * 1e-3 * 1.965e9;
+  double scalar_cycles = (double)rows * 4 * (NEXP * 11 + 16) * 2;     // per scheduler: 4 warps x FP64 scalar instrs x 2 cycles
+  printf("{\"probe\": \"rowloop_mix\", \"exps_per_lane\": %d, \"skew\": %d, \"dmma_frac_of_peak\": %.3f, "
+         "\"dmma_plus_scalar_frac\": %.3f}\n", NEXP, (int)SKEW, 16.0 / (cycles / dmma_per_sched),
+         (dmma_per_sched * 16.0 + scalar_cycles) / cycles);
+}
+
 template <int LOOPS, int KSTEPS, bool SYNC>
 static void probe_rowloop(int sms, double* out) {
   const int smem = 3 * 64 * 68 * 8;
@@ -396,13 +497,17 @@ int main() {
       }
     }
   }
+  // 8. realistic DMMA + scalar-epilogue mix
+  probe_rowloop_mix<0, false>(sms, out);
+  probe_rowloop_mix<4, false>(sms, out);
+  probe_rowloop_mix<8, false>(sms, out);
+  probe_rowloop_mix<8, true>(sms, out);
   // 7. short-loop / phase-boundary cost
   probe_rowloop<3, 16, false>(sms, out);
   probe_rowloop<3, 16, true>(sms, out);
   probe_rowloop<1, 48, false>(sms, out);
   probe_rowloop<1, 48, true>(sms, out);
   probe_rowloop<6, 8, false>(sms, out);
-  probe_rowloop<3, 64, false>(sms, out);
   // 6. DMMA fed from shared memory
   probe_dmma_lds<1, 1>(sms, out);
   probe_dmma_lds<2, 2>(sms, out);

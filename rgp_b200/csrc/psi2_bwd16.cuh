@@ -328,11 +328,14 @@ k_psi2_bwd16(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __re
         const double tot = reduce4_over_g(cs, lane);
         if (!(lane & 4)) sLc[s * 256 + wr * 64 + 16 * wc + 8 * (cidx >> 1) + 2 * t + (cidx & 1)] = tot;
       };
-      auto s2 = [&](int64_t n) {
+      auto s2i = [&](int64_t n) {
+        const int s = (int)(n & 1);
+        stage2I(sV + (n % 3) * VB, sL + s * 64 * RSL, s);
+      };
+      auto s2j = [&](int64_t n) {
         const int s = (int)(n & 1);
         const double* v = sV + (n % 3) * VB;
         const double* Lb = sL + s * 64 * RSL;
-        stage2I(v, Lb, s);
         // stage 2-J: TJ[m',q] = sum_m L[m,m'] ZI[m,q];  accJ += ws_q TJ   (weight applied after the MMA)
         const double* pa = Lb + t * RSL + 16 * wr + g;
         const double* pb = sZI + t * RS + qbase + g;
@@ -385,20 +388,24 @@ k_psi2_bwd16(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __re
         if (tr) tp[0] = clock64();
         const double nxt = vec_load(n + 2);
         const double wsn = ws_of(n + 2);
-        // the pre-weighted tile of row n+2 (slot n&1, last read by S1E(n) before barrier n) is built
-        // between the two phases, while the other warp group is inside an MMA loop
+        // Both groups start and end the iteration inside an MMA loop; the scalar exp epilogue (E) and
+        // the build of the pre-weighted tile of row n+2 (slot n&1, last read by S1E(n) before
+        // barrier n) sit in the middle, at different times for the two groups:
+        //   A: S1 E build | S2I | S2J          B: S2I | S1 E build | S2J
         if (groupB) {
-          if (n + 1 < r1) s1e(n + 1);
+          s2i(n);
           if (tr) tp[1] = clock64();
+          if (n + 1 < r1) s1e(n + 1);
           if (n + 2 < r1 && !(dbg & 64)) build_zw(n + 2, wsn);
           if (tr) tp[2] = clock64();
-          s2(n);
+          s2j(n);
         } else {
-          s2(n);
-          if (tr) tp[1] = clock64();
-          if (n + 2 < r1 && !(dbg & 64)) build_zw(n + 2, wsn);
-          if (tr) tp[2] = clock64();
           if (n + 1 < r1) s1e(n + 1);
+          if (n + 2 < r1 && !(dbg & 64)) build_zw(n + 2, wsn);
+          if (tr) tp[1] = clock64();
+          s2i(n);
+          if (tr) tp[2] = clock64();
+          s2j(n);
         }
         if (tid < VB) sV[((n + 2) % 3) * VB + tid] = nxt;
         if (tr) tp[3] = clock64();

@@ -23,6 +23,6 @@ for row in (4, 5):
     for w in range(16):
         grp = "B" if (w >> 2) & 1 else "A"
         e = t[row, w, :5] - base
-        print(f"  warp {w:2d} grp {grp} start {e[0]:7d}  phase1 +{e[1]-e[0]:6d}  build +{e[2]-e[1]:6d}  phase2 +{e[3]-e[2]:5d}  bar-issue +{e[4]-e[3]:6d}  end {e[3]:7d}")
+        print(f"  warp {w:2d} grp {grp} start {e[0]:7d}  p1 +{e[1]-e[0]:6d}  p2 +{e[2]-e[1]:6d}  p3 +{e[3]-e[2]:5d}  bar-issue +{e[4]-e[3]:6d}  end {e[3]:7d}")
 it = t[1:, 0, 0] - t[:-1, 0, 0]
 print("iteration lengths (warp 0):", it.tolist())
