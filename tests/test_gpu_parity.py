@@ -337,3 +337,20 @@ def test_options_are_validated():
         with pytest.raises(PsiError):
             h.set_option(key, val)
         assert key not in h._options
+
+
+def test_random_small_shapes_match_oracle(plugins):
+    """Twenty random ragged shapes (every tile / padding / block-group path of the fast kernels)."""
+    rng = np.random.default_rng(2024)
+    for trial in range(20):
+        N = int(rng.integers(1, 400))
+        M = int(rng.integers(1, 150))
+        Q = int(rng.integers(1, 90))
+        nc = int(rng.integers(0, Q // 2 + 1))
+        var, ell, Z, mu, S = make_inputs(N, M, Q, seed=1000 + trial, n_control=nc)
+        dL0, dL1, dL2 = make_upstream(N, M, seed=trial)
+        fwd, bwd = _run(plugins["fast"], var, ell, Z, mu, S, dL0, dL1, dL2)
+        try:
+            _compare(fwd, bwd, psi_forward(var, ell, Z, mu, S), psi_backward(dL0, dL1, dL2, var, ell, Z, mu, S), TIGHT)
+        except AssertionError as e:
+            raise AssertionError("shape N=%d M=%d Q=%d: %s" % (N, M, Q, e))
