@@ -65,8 +65,11 @@ const char* rgp_psi_last_error(void);
 int rgp_psi_create(int device, rgp_psi_handle_t* out);
 int rgp_psi_destroy(rgp_psi_handle_t h);
 
-/* Options: "impl" (rgp_psi_impl), "row_chunk" (rows per internal pass, 0 = auto),
- * "profile" (1 = record a CUDA-event pair around every kernel launch). */
+/* Options: "impl" (rgp_psi_impl), "row_chunk" (rows per internal device pass, 0 = 2^20),
+ * "host_chunk" (rows per pipelined host<->device chunk of the *_host calls, 0 = 262144),
+ * "bwd_warps" (8 or 16 warps per CTA in the Psi2 backward kernel), "profile" (1 = record a
+ * CUDA-event pair around every kernel launch).  Tuning / experiment knobs, not for production:
+ * "fwd_smem_pad", "debug_skip", "trace_ptr". */
 int rgp_psi_set_option(rgp_psi_handle_t h, const char* key, int64_t value);
 
 /* ---- forward: Psi0 (optional N-vector), Psi1 (optional), Psi2 -------------------
@@ -91,7 +94,10 @@ int rgp_psi_backward_dev(rgp_psi_handle_t h, void* stream, int64_t N, int M, int
                          double* dmu_out, double* dS_out, double* dZ_out,
                          double* dell_out, double* dvar_out);
 
-/* ---- host-buffer convenience wrappers (the numpy-in / numpy-out plugin path) ---- */
+/* ---- host-buffer wrappers (the numpy-in / numpy-out plugin path) -------------------
+ * Rows are streamed through double-buffered device mirrors on three streams (copy-in, compute,
+ * copy-out); copies overlap the kernels when the host buffers are pinned.  Device memory is
+ * bounded by "host_chunk", not by N.  Synchronises before returning. */
 int rgp_psi_forward_host(rgp_psi_handle_t h, int64_t N, int M, int Q,
                          const double* mu, const double* S, const double* Z,
                          const double* ell, double variance,

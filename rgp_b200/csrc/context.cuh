@@ -35,6 +35,10 @@ struct rgp_psi_ctx {
   int impl = RGP_PSI_IMPL_AUTO;
   int64_t row_chunk = 0;
   int profile = 0;
+  int accumulate = 0;      // internal: Psi2 / dZ / dell / dvar outputs are added to, not overwritten
+  int64_t host_chunk = 0;  // rows per pipelined chunk of the *_host entry points (0 = 262144)
+  cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;   // *_host pipeline streams
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_cmp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
   int bwd_warps = 16;     // 8 or 16 warps per CTA in the Psi2 backward kernel (QC >= 32)
   long long* trace = nullptr;   // optional device buffer for the bwd16 timeline trace (16*16*8 int64)
   int debug_skip = 0;     // timing experiments only (see psi2_bwd16.cuh); 0 in production

@@ -179,7 +179,7 @@ static int forward(rgp_psi_ctx* h, cudaStream_t st, int64_t N, int M, int Q, con
     else if (QC == 64) RGP_TRY(launch_fwd<64>(h, st, s, rows, Rc, Gc, Zt, w, HP, P2p));
     else RGP_TRY(launch_fwd<128>(h, st, s, rows, Rc, Gc, Zt, w, HP, P2p));
     RGP_LAUNCH(h, st, "psi2_reduce", k_psi2_reduce, s.nblocks, 256, 0, M, s.nt, Rc, variance * variance,
-               P2p, chunk > 0 ? 1 : 0, psi2);
+               P2p, (chunk > 0 || h->accumulate) ? 1 : 0, psi2);
   }
   return 0;
 }
@@ -225,9 +225,11 @@ static int backward(rgp_psi_ctx* h, cudaStream_t st, int64_t N, int M, int Q, co
   double* GL = b.take<double>((size_t)splits * Mp * 2 * QC);
   double* part = b.take<double>((size_t)nfin * (QC + 1));
 
-  RGP_CUDA(cudaMemsetAsync(dZ, 0, sizeof(double) * M * Q, st));
-  RGP_CUDA(cudaMemsetAsync(dell, 0, sizeof(double) * Q, st));
-  RGP_CUDA(cudaMemsetAsync(dvar, 0, sizeof(double), st));
+  if (!h->accumulate) {
+    RGP_CUDA(cudaMemsetAsync(dZ, 0, sizeof(double) * M * Q, st));
+    RGP_CUDA(cudaMemsetAsync(dell, 0, sizeof(double) * Q, st));
+    RGP_CUDA(cudaMemsetAsync(dvar, 0, sizeof(double), st));
+  }
   RGP_TRY(static_prep(h, st, s, Z, o, Zt, ZB));
   RGP_LAUNCH(h, st, "build_C", k_build_C, s.nblocks, 256, 0, M, s.nt, dL2, variance * variance, Ct);
 

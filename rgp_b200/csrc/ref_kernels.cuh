@@ -209,6 +209,10 @@ __global__ void psi2_bwd_tails(int M, int Q, const double* __restrict__ Z,
   atomicAdd(&dell[q], (rs * z * z - z * lnz) / (l * l * l));
 }
 
+__global__ void add_scalar(double v, double* __restrict__ out) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) out[0] += v;
+}
+
 __global__ void fill(int64_t n, double v, double* __restrict__ out) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = v;

@@ -72,7 +72,7 @@ static int forward(rgp_psi_ctx* h, cudaStream_t st, int64_t N, int M, int Q, con
   double* zz = b.take<double>((size_t)M * M);
   RGP_LAUNCH(h, st, "ref_pair_terms", ref::pair_terms, ceil_div((int64_t)M * M, 256), 256, 0, M, Q,
              Z, ell, (const double*)nullptr, zz, (double*)nullptr);
-  RGP_CUDA(cudaMemsetAsync(psi2, 0, sizeof(double) * M * M, st));
+  if (!h->accumulate) RGP_CUDA(cudaMemsetAsync(psi2, 0, sizeof(double) * M * M, st));
   if (psi0) RGP_LAUNCH(h, st, "ref_fill", ref::fill, ceil_div(N, 256), 256, 0, N, variance, psi0);
   for (int64_t s = 0; s < N; s += rc) {
     int64_t r = std::min(rc, N - s);
@@ -111,15 +111,17 @@ static int backward(rgp_psi_ctx* h, cudaStream_t st, int64_t N, int M, int Q, co
 
   RGP_CUDA(cudaMemsetAsync(dmu, 0, sizeof(double) * N * Q, st));
   RGP_CUDA(cudaMemsetAsync(dS, 0, sizeof(double) * N * Q, st));
-  RGP_CUDA(cudaMemsetAsync(dZ, 0, sizeof(double) * M * Q, st));
-  RGP_CUDA(cudaMemsetAsync(dell, 0, sizeof(double) * Q, st));
+  if (!h->accumulate) {
+    RGP_CUDA(cudaMemsetAsync(dZ, 0, sizeof(double) * M * Q, st));
+    RGP_CUDA(cudaMemsetAsync(dell, 0, sizeof(double) * Q, st));
+    RGP_CUDA(cudaMemsetAsync(dvar, 0, sizeof(double), st));
+  }
   RGP_CUDA(cudaMemsetAsync(p2, 0, sizeof(double) * M * M, st));
   if (dL0) {
-    RGP_CUDA(cudaMemsetAsync(dvar, 0, sizeof(double), st));
     RGP_LAUNCH(h, st, "ref_sum_dL0", ref::sum_to, std::min(1024, ceil_div(N, 256)), 256, 0, N, dL0,
                dvar);
   } else {
-    RGP_LAUNCH(h, st, "ref_fill", ref::fill, 1, 32, 0, (int64_t)1, dL0c * (double)N, dvar);
+    RGP_LAUNCH(h, st, "ref_add", ref::add_scalar, 1, 32, 0, dL0c * (double)N, dvar);
   }
   RGP_LAUNCH(h, st, "ref_pair_terms", ref::pair_terms, ceil_div((int64_t)M * M, 256), 256, 0, M, Q,
              Z, ell, dL2, zz, dLs);
@@ -204,6 +206,14 @@ int rgp_psi_destroy(rgp_psi_handle_t h) {
     cudaEventDestroy(p.stop);
   }
   for (auto e : h->event_pool) cudaEventDestroy(e);
+  for (int i = 0; i < 2; ++i) {
+    if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
+    if (h->ev_cmp[i]) cudaEventDestroy(h->ev_cmp[i]);
+    if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
+  }
+  if (h->s_in) cudaStreamDestroy(h->s_in);
+  if (h->s_cmp) cudaStreamDestroy(h->s_cmp);
+  if (h->s_out) cudaStreamDestroy(h->s_out);
   if (h->ws) cudaFree(h->ws);
   if (h->io) cudaFree(h->io);
   delete h;
@@ -218,6 +228,9 @@ int rgp_psi_set_option(rgp_psi_handle_t h, const char* key, int64_t value) {
   } else if (!strcmp(key, "row_chunk")) {
     if (value < 0) return set_error(RGP_PSI_ERR_INVALID, "row_chunk must be >= 0");
     h->row_chunk = value;
+  } else if (!strcmp(key, "host_chunk")) {
+    if (value < 0) return set_error(RGP_PSI_ERR_INVALID, "host_chunk must be >= 0");
+    h->host_chunk = value;
   } else if (!strcmp(key, "profile")) {
     h->profile = value != 0;
   } else if (!strcmp(key, "bwd_warps")) {
@@ -269,34 +282,89 @@ int rgp_psi_backward_dev(rgp_psi_handle_t h, void* stream, int64_t N, int M, int
 }
 
 // ------------------------------------------------------------- host-buffer wrappers
+// Rows are streamed in chunks through double-buffered device mirrors on three streams (copy-in,
+// compute, copy-out), so host<->device traffic overlaps the kernels (only truly asynchronous when
+// the caller's buffers are pinned) and device memory is bounded by the chunk size, not by N.
+} // extern "C"
+
+namespace rgp {
+static int host_pipeline_init(rgp_psi_ctx* h) {
+  if (h->s_in) return 0;
+  RGP_CUDA(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+  RGP_CUDA(cudaStreamCreateWithFlags(&h->s_cmp, cudaStreamNonBlocking));
+  RGP_CUDA(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    RGP_CUDA(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+    RGP_CUDA(cudaEventCreateWithFlags(&h->ev_cmp[i], cudaEventDisableTiming));
+    RGP_CUDA(cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
+  }
+  return 0;
+}
+static int64_t host_chunk_rows(const rgp_psi_ctx* h, int64_t N) {
+  int64_t c = h->host_chunk > 0 ? h->host_chunk : 262144;
+  return std::min<int64_t>(N, c);
+}
+struct AccumulateGuard {       // restores the handle's accumulate flag on every exit path
+  rgp_psi_ctx* h;
+  int saved;
+  explicit AccumulateGuard(rgp_psi_ctx* c) : h(c), saved(c->accumulate) {}
+  ~AccumulateGuard() { h->accumulate = saved; }
+};
+}  // namespace rgp
+
+extern "C" {
+
 int rgp_psi_forward_host(rgp_psi_handle_t h, int64_t N, int M, int Q, const double* mu,
                          const double* S, const double* Z, const double* ell, double variance,
                          double* psi0_out, double* psi1_out, double* psi2_out) {
   RGP_TRY(check_common(h, N, M, Q, mu, S, Z, ell, variance));
   if (!psi2_out) return set_error(RGP_PSI_ERR_INVALID, "psi2_out must not be null");
   RGP_CUDA(cudaSetDevice(h->device));
-  size_t nq = (size_t)N * Q, nm = (size_t)N * M, mq = (size_t)M * Q, mm = (size_t)M * M;
-  size_t need = bump_size(nq, 8) * 2 + bump_size(mq, 8) + bump_size(Q, 8) + bump_size(mm, 8) +
-                (psi0_out ? bump_size(N, 8) : 0) + (psi1_out ? bump_size(nm, 8) : 0);
+  RGP_TRY(host_pipeline_init(h));
+  const int64_t R = host_chunk_rows(h, N);
+  size_t rq = (size_t)R * Q, rm = (size_t)R * M, mq = (size_t)M * Q, mm = (size_t)M * M;
+  size_t need = bump_size(mq, 8) + bump_size(Q, 8) + bump_size(mm, 8) +
+                2 * (bump_size(rq, 8) * 2 + (psi1_out ? bump_size(rm, 8) : 0));
   RGP_TRY(arena_reserve(&h->io, &h->io_bytes, need));
   Bump b(h->io, h->io_bytes);
-  double* d_mu = b.take<double>(nq);
-  double* d_S = b.take<double>(nq);
   double* d_Z = b.take<double>(mq);
   double* d_ell = b.take<double>(Q);
   double* d_p2 = b.take<double>(mm);
-  double* d_p0 = psi0_out ? b.take<double>(N) : nullptr;
-  double* d_p1 = psi1_out ? b.take<double>(nm) : nullptr;
-  cudaStream_t st = 0;
-  RGP_CUDA(cudaMemcpyAsync(d_mu, mu, nq * 8, cudaMemcpyHostToDevice, st));
-  RGP_CUDA(cudaMemcpyAsync(d_S, S, nq * 8, cudaMemcpyHostToDevice, st));
-  RGP_CUDA(cudaMemcpyAsync(d_Z, Z, mq * 8, cudaMemcpyHostToDevice, st));
-  RGP_CUDA(cudaMemcpyAsync(d_ell, ell, (size_t)Q * 8, cudaMemcpyHostToDevice, st));
-  RGP_TRY(rgp_psi_forward_dev(h, st, N, M, Q, d_mu, d_S, d_Z, d_ell, variance, d_p0, d_p1, d_p2));
-  if (psi0_out) RGP_CUDA(cudaMemcpyAsync(psi0_out, d_p0, (size_t)N * 8, cudaMemcpyDeviceToHost, st));
-  if (psi1_out) RGP_CUDA(cudaMemcpyAsync(psi1_out, d_p1, nm * 8, cudaMemcpyDeviceToHost, st));
-  RGP_CUDA(cudaMemcpyAsync(psi2_out, d_p2, mm * 8, cudaMemcpyDeviceToHost, st));
-  RGP_CUDA(cudaStreamSynchronize(st));
+  double *d_mu[2], *d_S[2], *d_p1[2];
+  for (int i = 0; i < 2; ++i) {
+    d_mu[i] = b.take<double>(rq);
+    d_S[i] = b.take<double>(rq);
+    d_p1[i] = psi1_out ? b.take<double>(rm) : nullptr;
+  }
+  AccumulateGuard guard(h);
+  RGP_CUDA(cudaMemcpyAsync(d_Z, Z, mq * 8, cudaMemcpyHostToDevice, h->s_cmp));
+  RGP_CUDA(cudaMemcpyAsync(d_ell, ell, (size_t)Q * 8, cudaMemcpyHostToDevice, h->s_cmp));
+  int c = 0;
+  for (int64_t r0 = 0; r0 < N; r0 += R, ++c) {
+    const int64_t rows = std::min(R, N - r0);
+    const int k = c & 1;
+    if (c >= 2) RGP_CUDA(cudaStreamWaitEvent(h->s_in, h->ev_cmp[k], 0));     // inputs of chunk c-2 consumed
+    RGP_CUDA(cudaMemcpyAsync(d_mu[k], mu + r0 * Q, (size_t)rows * Q * 8, cudaMemcpyHostToDevice, h->s_in));
+    RGP_CUDA(cudaMemcpyAsync(d_S[k], S + r0 * Q, (size_t)rows * Q * 8, cudaMemcpyHostToDevice, h->s_in));
+    RGP_CUDA(cudaEventRecord(h->ev_in[k], h->s_in));
+    RGP_CUDA(cudaStreamWaitEvent(h->s_cmp, h->ev_in[k], 0));
+    if (c >= 2) RGP_CUDA(cudaStreamWaitEvent(h->s_cmp, h->ev_out[k], 0));    // psi1 of chunk c-2 drained
+    h->accumulate = c > 0;
+    RGP_TRY(rgp_psi_forward_dev(h, h->s_cmp, rows, M, Q, d_mu[k], d_S[k], d_Z, d_ell, variance, nullptr,
+                                d_p1[k], d_p2));
+    RGP_CUDA(cudaEventRecord(h->ev_cmp[k], h->s_cmp));
+    if (psi1_out) {
+      RGP_CUDA(cudaStreamWaitEvent(h->s_out, h->ev_cmp[k], 0));
+      RGP_CUDA(cudaMemcpyAsync(psi1_out + r0 * M, d_p1[k], (size_t)rows * M * 8, cudaMemcpyDeviceToHost, h->s_out));
+      RGP_CUDA(cudaEventRecord(h->ev_out[k], h->s_out));
+    }
+  }
+  RGP_CUDA(cudaMemcpyAsync(psi2_out, d_p2, mm * 8, cudaMemcpyDeviceToHost, h->s_cmp));
+  if (psi0_out)
+    for (int64_t i = 0; i < N; ++i) psi0_out[i] = variance;                 // Psi0[n] = variance
+  RGP_CUDA(cudaStreamSynchronize(h->s_in));
+  RGP_CUDA(cudaStreamSynchronize(h->s_cmp));
+  RGP_CUDA(cudaStreamSynchronize(h->s_out));
   return 0;
 }
 
@@ -309,39 +377,61 @@ int rgp_psi_backward_host(rgp_psi_handle_t h, int64_t N, int M, int Q, const dou
   if (!dL_dpsi2 || !dmu_out || !dS_out || !dZ_out || !dell_out || !dvar_out)
     return set_error(RGP_PSI_ERR_INVALID, "null dL_dpsi2 or output pointer");
   RGP_CUDA(cudaSetDevice(h->device));
-  size_t nq = (size_t)N * Q, nm = (size_t)N * M, mq = (size_t)M * Q, mm = (size_t)M * M;
-  size_t need = bump_size(nq, 8) * 4 + bump_size(mq, 8) * 2 + bump_size(Q, 8) * 2 + bump_size(mm, 8) +
-                bump_size(1, 8) + (dL_dpsi0 ? bump_size(N, 8) : 0) + (dL_dpsi1 ? bump_size(nm, 8) : 0);
+  RGP_TRY(host_pipeline_init(h));
+  const int64_t R = host_chunk_rows(h, N);
+  size_t rq = (size_t)R * Q, rm = (size_t)R * M, mq = (size_t)M * Q, mm = (size_t)M * M;
+  size_t need = bump_size(mq, 8) * 2 + bump_size(Q, 8) * 2 + bump_size(mm, 8) + bump_size(1, 8) +
+                2 * (bump_size(rq, 8) * 4 + (dL_dpsi0 ? bump_size(R, 8) : 0) + (dL_dpsi1 ? bump_size(rm, 8) : 0));
   RGP_TRY(arena_reserve(&h->io, &h->io_bytes, need));
   Bump b(h->io, h->io_bytes);
-  double* d_mu = b.take<double>(nq);
-  double* d_S = b.take<double>(nq);
-  double* d_dmu = b.take<double>(nq);
-  double* d_dS = b.take<double>(nq);
   double* d_Z = b.take<double>(mq);
   double* d_dZ = b.take<double>(mq);
   double* d_ell = b.take<double>(Q);
   double* d_dell = b.take<double>(Q);
   double* d_dL2 = b.take<double>(mm);
   double* d_dvar = b.take<double>(1);
-  double* d_dL0 = dL_dpsi0 ? b.take<double>(N) : nullptr;
-  double* d_dL1 = dL_dpsi1 ? b.take<double>(nm) : nullptr;
-  cudaStream_t st = 0;
-  RGP_CUDA(cudaMemcpyAsync(d_mu, mu, nq * 8, cudaMemcpyHostToDevice, st));
-  RGP_CUDA(cudaMemcpyAsync(d_S, S, nq * 8, cudaMemcpyHostToDevice, st));
-  RGP_CUDA(cudaMemcpyAsync(d_Z, Z, mq * 8, cudaMemcpyHostToDevice, st));
-  RGP_CUDA(cudaMemcpyAsync(d_ell, ell, (size_t)Q * 8, cudaMemcpyHostToDevice, st));
-  RGP_CUDA(cudaMemcpyAsync(d_dL2, dL_dpsi2, mm * 8, cudaMemcpyHostToDevice, st));
-  if (dL_dpsi0) RGP_CUDA(cudaMemcpyAsync(d_dL0, dL_dpsi0, (size_t)N * 8, cudaMemcpyHostToDevice, st));
-  if (dL_dpsi1) RGP_CUDA(cudaMemcpyAsync(d_dL1, dL_dpsi1, nm * 8, cudaMemcpyHostToDevice, st));
-  RGP_TRY(rgp_psi_backward_dev(h, st, N, M, Q, d_mu, d_S, d_Z, d_ell, variance, d_dL0,
-                               dL_dpsi0_const, d_dL1, d_dL2, d_dmu, d_dS, d_dZ, d_dell, d_dvar));
-  RGP_CUDA(cudaMemcpyAsync(dmu_out, d_dmu, nq * 8, cudaMemcpyDeviceToHost, st));
-  RGP_CUDA(cudaMemcpyAsync(dS_out, d_dS, nq * 8, cudaMemcpyDeviceToHost, st));
-  RGP_CUDA(cudaMemcpyAsync(dZ_out, d_dZ, mq * 8, cudaMemcpyDeviceToHost, st));
-  RGP_CUDA(cudaMemcpyAsync(dell_out, d_dell, (size_t)Q * 8, cudaMemcpyDeviceToHost, st));
-  RGP_CUDA(cudaMemcpyAsync(dvar_out, d_dvar, 8, cudaMemcpyDeviceToHost, st));
-  RGP_CUDA(cudaStreamSynchronize(st));
+  double *d_mu[2], *d_S[2], *d_dmu[2], *d_dS[2], *d_dL0[2], *d_dL1[2];
+  for (int i = 0; i < 2; ++i) {
+    d_mu[i] = b.take<double>(rq);
+    d_S[i] = b.take<double>(rq);
+    d_dmu[i] = b.take<double>(rq);
+    d_dS[i] = b.take<double>(rq);
+    d_dL0[i] = dL_dpsi0 ? b.take<double>(R) : nullptr;
+    d_dL1[i] = dL_dpsi1 ? b.take<double>(rm) : nullptr;
+  }
+  AccumulateGuard guard(h);
+  RGP_CUDA(cudaMemcpyAsync(d_Z, Z, mq * 8, cudaMemcpyHostToDevice, h->s_cmp));
+  RGP_CUDA(cudaMemcpyAsync(d_ell, ell, (size_t)Q * 8, cudaMemcpyHostToDevice, h->s_cmp));
+  RGP_CUDA(cudaMemcpyAsync(d_dL2, dL_dpsi2, mm * 8, cudaMemcpyHostToDevice, h->s_cmp));
+  int c = 0;
+  for (int64_t r0 = 0; r0 < N; r0 += R, ++c) {
+    const int64_t rows = std::min(R, N - r0);
+    const int k = c & 1;
+    if (c >= 2) RGP_CUDA(cudaStreamWaitEvent(h->s_in, h->ev_cmp[k], 0));
+    RGP_CUDA(cudaMemcpyAsync(d_mu[k], mu + r0 * Q, (size_t)rows * Q * 8, cudaMemcpyHostToDevice, h->s_in));
+    RGP_CUDA(cudaMemcpyAsync(d_S[k], S + r0 * Q, (size_t)rows * Q * 8, cudaMemcpyHostToDevice, h->s_in));
+    if (dL_dpsi0)
+      RGP_CUDA(cudaMemcpyAsync(d_dL0[k], dL_dpsi0 + r0, (size_t)rows * 8, cudaMemcpyHostToDevice, h->s_in));
+    if (dL_dpsi1)
+      RGP_CUDA(cudaMemcpyAsync(d_dL1[k], dL_dpsi1 + r0 * M, (size_t)rows * M * 8, cudaMemcpyHostToDevice, h->s_in));
+    RGP_CUDA(cudaEventRecord(h->ev_in[k], h->s_in));
+    RGP_CUDA(cudaStreamWaitEvent(h->s_cmp, h->ev_in[k], 0));
+    if (c >= 2) RGP_CUDA(cudaStreamWaitEvent(h->s_cmp, h->ev_out[k], 0));    // dmu/dS of chunk c-2 drained
+    h->accumulate = c > 0;
+    RGP_TRY(rgp_psi_backward_dev(h, h->s_cmp, rows, M, Q, d_mu[k], d_S[k], d_Z, d_ell, variance, d_dL0[k],
+                                 dL_dpsi0_const, d_dL1[k], d_dL2, d_dmu[k], d_dS[k], d_dZ, d_dell, d_dvar));
+    RGP_CUDA(cudaEventRecord(h->ev_cmp[k], h->s_cmp));
+    RGP_CUDA(cudaStreamWaitEvent(h->s_out, h->ev_cmp[k], 0));
+    RGP_CUDA(cudaMemcpyAsync(dmu_out + r0 * Q, d_dmu[k], (size_t)rows * Q * 8, cudaMemcpyDeviceToHost, h->s_out));
+    RGP_CUDA(cudaMemcpyAsync(dS_out + r0 * Q, d_dS[k], (size_t)rows * Q * 8, cudaMemcpyDeviceToHost, h->s_out));
+    RGP_CUDA(cudaEventRecord(h->ev_out[k], h->s_out));
+  }
+  RGP_CUDA(cudaMemcpyAsync(dZ_out, d_dZ, mq * 8, cudaMemcpyDeviceToHost, h->s_cmp));
+  RGP_CUDA(cudaMemcpyAsync(dell_out, d_dell, (size_t)Q * 8, cudaMemcpyDeviceToHost, h->s_cmp));
+  RGP_CUDA(cudaMemcpyAsync(dvar_out, d_dvar, 8, cudaMemcpyDeviceToHost, h->s_cmp));
+  RGP_CUDA(cudaStreamSynchronize(h->s_in));
+  RGP_CUDA(cudaStreamSynchronize(h->s_cmp));
+  RGP_CUDA(cudaStreamSynchronize(h->s_out));
   return 0;
 }
 

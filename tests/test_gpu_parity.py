@@ -312,6 +312,21 @@ def test_sharded_nccl_matches_single_gpu():
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
 
 
+@pytest.mark.parametrize("impl", ["reference", "auto"])
+def test_host_pipeline_many_chunks(impl):
+    """The *_host entry points stream rows through double-buffered device mirrors; force ~12 chunks
+    (buffer reuse, event waits, accumulation of Psi2 / dZ / dell / dvar across chunks)."""
+    from rgp_b200.psicomp import PSICOMP_RBF_B200
+    N, M, Q = 1203, 40, 9
+    var, ell, Z, mu, S = make_inputs(N, M, Q, seed=91, n_control=2)
+    _, dL1, dL2 = make_upstream(N, M, seed=92)
+    dL0 = np.random.default_rng(3).normal(size=N)
+    pc = PSICOMP_RBF_B200(impl=impl, cache=False)
+    pc.handle.set_option("host_chunk", 101)
+    fwd, bwd = _run(pc, var, ell, Z, mu, S, dL0, dL1, dL2)
+    _compare(fwd, bwd, psi_forward(var, ell, Z, mu, S), psi_backward(dL0, dL1, dL2, var, ell, Z, mu, S), TIGHT)
+
+
 @pytest.mark.parametrize("chunk", [1000, 4096])
 def test_row_chunking_accumulates_exactly_like_one_pass(chunk):
     """The library streams rows in chunks (<= 2^20 by default; the headline run uses four).
@@ -323,7 +338,8 @@ def test_row_chunking_accumulates_exactly_like_one_pass(chunk):
     dL0, dL1, dL2 = make_upstream(N, M, seed=78)
     dL0 = np.random.default_rng(1).normal(size=N)                 # non-constant dL_dpsi0 across chunks
     pc = PSICOMP_RBF_B200(cache=False)
-    pc.handle.set_option("row_chunk", chunk)
+    pc.handle.set_option("row_chunk", chunk)          # device-side row chunks
+    pc.handle.set_option("host_chunk", 2 * chunk + 37)  # pipelined host<->device chunks (ragged, 2 then 1 inner chunks)
     fwd, bwd = _run(pc, var, ell, Z, mu, S, dL0, dL1, dL2)
     _compare(fwd, bwd, psi_forward(var, ell, Z, mu, S), psi_backward(dL0, dL1, dL2, var, ell, Z, mu, S), TIGHT)
 
