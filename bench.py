@@ -284,9 +284,19 @@ def ours(args):
                                    "MEASURED_PEAKS.json has no fp64 entry",
                     "launch_ms": per_launch_ms, "launches": cnt,
                     "flops_per_row": fl, "rows_per_launch": rows_per_launch}
+    hbm_peak = None
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            hbm_peak = json.load(f).get("hbm_gbs")
+    except Exception:
+        pass
+    hbm_ach = value / world * bytes_row(M, Q) / 1e9
     whole = {"achieved_tflops": value / world * flops_row_total(M, Q) / 1e12, "peak_tflops": peak_tf,
              "frac": value / world * flops_row_total(M, Q) / 1e12 / peak_tf if peak_tf else None,
-             "flops_per_row": flops_row_total(M, Q), "bytes_per_row": bytes_row(M, Q)}
+             "flops_per_row": flops_row_total(M, Q), "bytes_per_row": bytes_row(M, Q),
+             "hbm_gbs_algorithmic": hbm_ach, "hbm_peak_gbs": hbm_peak if hbm_peak else 6650.0,
+             "hbm_peak_source": "MEASURED_PEAKS.json" if hbm_peak else "fallback (B200_PROFILING.md)",
+             "hbm_frac": hbm_ach / (hbm_peak if hbm_peak else 6650.0)}
     kshare = {k: {"ms": round(v[0], 3), "launches": v[1]} for k, v in
               sorted(ktimes.items(), key=lambda kv: -kv[1][0])}
 
