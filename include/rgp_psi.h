@@ -126,6 +126,19 @@ int rgp_lag_scatter_dev(rgp_psi_handle_t h, void* stream, int nseq, const int64_
                         int64_t N, int Xwin, int Dx, int Uwin, int Du, const double* dX,
                         int64_t lat_total, double* lat_grad, int64_t ctl_total, double* ctl_grad);
 
+/* Latent-state terms of a hidden layer: Layer_new._prepare_gradients (autoreg/layers.py:582-615)
+ * with NormalPrior / NormalEntropy (autoreg/variational.py:4-24).  For the stacked latent
+ * series lat_mean / lat_var [lat_total, D] it WRITES lat_gmean / lat_gvar (the reference zeroes
+ * them first) = the output-side gradients dL_dYmean [N, D] / dL_dYvar on the steps t >= Xwin
+ * plus the entropy gradient there and the prior gradient on the first Xwin steps, and stores
+ * the value the layer adds to its bound (-prior - entropy, "delta" at :594-615) in value_out
+ * (one device double).  dyvar_cols = 1 when dL_dYvar is [N] (VarDTC), D when it is [N, D]
+ * (SVI).  rgp_lag_scatter_dev then adds the input-side row gradients on top. */
+int rgp_latent_terms_dev(rgp_psi_handle_t h, void* stream, int nseq, const int64_t* seq_desc,
+                         int Xwin, int D, const double* lat_mean, const double* lat_var,
+                         int64_t lat_total, const double* dL_dYmean, const double* dL_dYvar,
+                         int dyvar_cols, double* lat_gmean, double* lat_gvar, double* value_out);
+
 /* ---- measurement support ------------------------------------------------------- */
 /* Kernel launches issued through this handle since creation (or the last reset). */
 int64_t rgp_psi_launch_count(rgp_psi_handle_t h);

@@ -32,20 +32,26 @@ def build_rows(Xs, Us, X_win, U_win):
     return np.vstack(rows)
 
 
-def scatter_rows(dX, Xs_shapes, Us_shapes, X_win, U_win, X_dim, U_dim):
-    """layers.py:552-571: add X-row gradients back onto latent / control steps."""
-    gX = [np.zeros(s) for s in Xs_shapes]
-    gU = [np.zeros(s) for s in Us_shapes] if Us_shapes is not None else None
+def scatter_rows_into(dX, gX, gU, X_win, U_win, X_dim, U_dim):
+    """layers.py:552-571 verbatim in effect: ``+=`` of every X-row gradient onto the latent /
+    control gradient arrays it was built from, in place, rows in increasing n."""
     X_offset = 0
-    for i, shp in enumerate(Xs_shapes):
-        N = shp[0] - X_win
-        Qx = X_win * X_dim
+    Qx = X_win * X_dim
+    for i in range(len(gX)):
+        N = gX[i].shape[0] - X_win
         if gU is not None:
-            U_offset = -N - U_win + 1 + Us_shapes[i][0]
+            U_offset = -N - U_win + 1 + gU[i].shape[0]
         for n in range(N):
             if X_win > 0:
                 gX[i][n:n + X_win] += dX[X_offset + n, :Qx].reshape(-1, X_dim)
             if gU is not None:
                 gU[i][U_offset + n:U_offset + n + U_win] += dX[X_offset + n, Qx:].reshape(-1, U_dim)
         X_offset += N
+
+
+def scatter_rows(dX, Xs_shapes, Us_shapes, X_win, U_win, X_dim, U_dim):
+    """``scatter_rows_into`` onto zero-initialised gradients."""
+    gX = [np.zeros(s) for s in Xs_shapes]
+    gU = [np.zeros(s) for s in Us_shapes] if Us_shapes is not None else None
+    scatter_rows_into(dX, gX, gU, X_win, U_win, X_dim, U_dim)
     return gX, gU

@@ -40,6 +40,9 @@ SIGNATURES = {
     "rgp_lag_scatter_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int,
                                       C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                       C.c_void_p]),
+    "rgp_latent_terms_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                       C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                       C.c_void_p, C.c_void_p]),
     "rgp_psi_launch_count": (C.c_int64, [C.c_void_p]),
     "rgp_psi_reset_counters": (C.c_int, [C.c_void_p]),
     "rgp_psi_kernel_times": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), c_double_p,
@@ -182,6 +185,11 @@ class Handle:
                     ctl_total, ctl_grad) -> None:
         check(load().rgp_lag_scatter_dev(self._ensure(), C.c_void_p(stream), nseq, seq_desc, N, Xwin, Dx, Uwin, Du,
                                          dX, lat_total, lat_grad, ctl_total, ctl_grad))
+
+    def latent_terms(self, stream, nseq, seq_desc, Xwin, D, lat_mean, lat_var, lat_total, dYmean, dYvar,
+                     dyvar_cols, gmean, gvar, value_out) -> None:
+        check(load().rgp_latent_terms_dev(self._ensure(), C.c_void_p(stream), nseq, seq_desc, Xwin, D, lat_mean,
+                                          lat_var, lat_total, dYmean, dYvar, dyvar_cols, gmean, gvar, value_out))
 
     def forward_host(self, N, M, Q, mu, S, Z, ell, variance, psi0, psi1, psi2) -> None:
         check(load().rgp_psi_forward_host(self._ensure(), N, M, Q, mu, S, Z, ell, float(variance),

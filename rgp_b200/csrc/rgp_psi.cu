@@ -470,6 +470,27 @@ int rgp_lag_scatter_dev(rgp_psi_handle_t h, void* stream, int nseq, const int64_
   return 0;
 }
 
+int rgp_latent_terms_dev(rgp_psi_handle_t h, void* stream, int nseq, const int64_t* seq_desc, int Xwin, int D,
+                         const double* lat_mean, const double* lat_var, int64_t lat_total,
+                         const double* dL_dYmean, const double* dL_dYvar, int dyvar_cols, double* lat_gmean,
+                         double* lat_gvar, double* value_out) {
+  if (!h) return set_error(RGP_PSI_ERR_INVALID, "null handle");
+  if (nseq <= 0 || !seq_desc || Xwin < 0 || D <= 0 || lat_total <= 0 || !lat_mean || !lat_var || !dL_dYmean ||
+      !dL_dYvar || !lat_gmean || !lat_gvar || !value_out)
+    return set_error(RGP_PSI_ERR_INVALID, "bad latent-terms arguments");
+  if (dyvar_cols != 1 && dyvar_cols != D)
+    return set_error(RGP_PSI_ERR_INVALID, "dyvar_cols must be 1 or D (got %d, D = %d)", dyvar_cols, D);
+  RGP_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = (int)std::min<int64_t>(ceil_div(lat_total * D, 256), (int64_t)h->sm_count * 8);
+  RGP_TRY(arena_reserve(&h->ws, &h->ws_bytes, bump_size(blocks, sizeof(double))));
+  double* partial = (double*)h->ws;
+  RGP_LAUNCH(h, st, "latent_terms", lag::k_latent_terms, blocks, 256, 0, nseq, seq_desc, Xwin, D, lat_mean,
+             lat_var, dL_dYmean, dL_dYvar, dyvar_cols, lat_total, lat_gmean, lat_gvar, partial);
+  RGP_LAUNCH(h, st, "latent_terms_sum", lag::k_sum_partials, 1, 256, 0, blocks, partial, value_out);
+  return 0;
+}
+
 // ------------------------------------------------------------------ measurement
 int64_t rgp_psi_launch_count(rgp_psi_handle_t h) { return h ? h->launches : -1; }
 

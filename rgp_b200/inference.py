@@ -54,6 +54,16 @@ def backsub_both_sides(L: torch.Tensor, X: torch.Tensor, transpose: str = "left"
     return dtrtrs(L, tmp.mT, trans=t).mT
 
 
+def rsolve_T(L: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
+    """B L^-T  ( = dtrtrs(L, B.T).T of the reference) for tall B [N, M] without transposing it."""
+    return torch.linalg.solve_triangular(L.mT, B, upper=True, left=False)
+
+
+def rsolve(L: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
+    """B L^-1  ( = dtrtrs(L, B.T, trans=1).T )."""
+    return torch.linalg.solve_triangular(L, B, upper=False, left=False)
+
+
 def tdot(A: torch.Tensor) -> torch.Tensor:
     return A @ A.mT
 
@@ -84,9 +94,13 @@ class DeviceBound:
         self.psi = psi if psi is not None else DevicePsi(device)
 
     # ------------------------------------------------------------------ VarDTC
-    def vardtc(self, variance: float, ell, Z, mu, S, Y, noise_variance: float
+    def vardtc(self, variance: float, ell, Z, mu, S, Y, noise_variance: float, Y_var=None
                ) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
-        """autoreg/inference/vardtc.py:88-208 (uncertain inputs, certain outputs)."""
+        """autoreg/inference/vardtc.py:88-208, uncertain inputs.  ``Y_var`` [N, D] switches on
+        the uncertain-output branch (hidden layers: :70-77, :136-140, :179, :201-206), whose
+        N x M triangular solves run as cuBLAS TRSMs on the rows resident in HBM; the two
+        solves of the reference against the same factor (:137, :203) differ by a row scaling
+        and are done once."""
         N, D = Y.shape
         M = Z.shape[0]
         beta = 1.0 / max(float(noise_variance), 1e-6)                         # :102
@@ -95,6 +109,8 @@ class DeviceBound:
         psi2b = psi2 * beta
         psi1Y = (Y.mT @ psi1) * beta                                          # :79  D x M
         YRY = Y.square().sum() * beta                                         # :81-82
+        if Y_var is not None:
+            YRY = YRY + Y_var.sum() * beta                                    # :77
         eye = torch.eye(M, dtype=Z.dtype, device=Z.device)
         Kmm = rbf_K(variance, ell, Z) + eye * CONST_JITTER                    # :110-114
         Lm = jitchol(Kmm)
@@ -106,6 +122,13 @@ class DeviceBound:
         bbt = b.square().sum()
         v = dtrtrs(LmLL, b.mT, trans=1).mT                                    # :133
         C = tdot(b.mT)
+        if Y_var is not None:
+            Shalf = Y_var.sum(dim=1).sqrt()                                   # :74
+            psi1LmiLLi = rsolve_T(LmLL, psi1) * beta                          # :203  N x M
+            psi1SLLinv = Shalf[:, None] * psi1LmiLLi                          # :137
+            bbt = bbt + psi1SLLinv.square().sum()
+            C = C + psi1SLLinv.mT @ psi1SLLinv                                # :139
+            psi1SP = rsolve(LmLL, psi1SLLinv)                                 # :140
         tmp = -backsub_both_sides(LL, C + D * eye)                            # :141
         dL_dpsi2R = backsub_both_sides(Lm, tmp + D * eye) / 2.0               # :142
         logL_R = -N * math.log(beta)
@@ -116,14 +139,20 @@ class DeviceBound:
             - beta * (dL_dpsi2R * psi2b).sum() - beta * torch.trace(C)        # :169
         dL_dpsi0 = -D * beta / 2.0                                            # :175 (constant over rows)
         dL_dpsi1 = (Y @ v) * beta                                             # :181
+        extra = {"dL_dthetaL": dL_dthetaL, "woodbury_vector": v.mT}
+        if Y_var is not None:
+            dL_dpsi1 = dL_dpsi1 + (Shalf[:, None] * psi1SP) * beta            # :179
+            extra["dL_dYmean"] = psi1LmiLLi @ b.mT - Y * beta                 # :205
+            extra["dL_dYvar"] = psi1LmiLLi.square().sum(dim=1) / 2.0 - beta / 2.0   # :206  [N]
+            del psi1SP, psi1SLLinv, psi1LmiLLi
         dL_dpsi2 = dL_dpsi2R * beta                                           # :184
-        return logL, self._finish(variance, ell, Z, mu, S, dL_dpsi0, dL_dpsi1, dL_dpsi2, dL_dKmm,
-                                  {"dL_dthetaL": dL_dthetaL, "woodbury_vector": v.mT})
+        return logL, self._finish(variance, ell, Z, mu, S, dL_dpsi0, dL_dpsi1, dL_dpsi2, dL_dKmm, extra)
 
     # -------------------------------------------------------------------- SVI
     def svi(self, variance: float, ell, Z, mu, S, Y, noise_variance: float, qU_mean, qU_var,
-            qU_ratio: float = 1.0) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
-        """autoreg/inference/svi_vardtc.py:70-215 plus the KL scaling of layers.py:75-79."""
+            qU_ratio: float = 1.0, Y_var=None) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
+        """autoreg/inference/svi_vardtc.py:70-215 plus the KL scaling of layers.py:75-79.
+        ``Y_var`` [N, D]: uncertain outputs (:56-59, :190-193)."""
         N, D = Y.shape
         M = Z.shape[0]
         beta = 1.0 / float(noise_variance)                                    # :80
@@ -132,6 +161,8 @@ class DeviceBound:
         psi2b = psi2 * beta
         psi1Y = (Y.mT @ psi1) * beta
         YRY = Y.square().sum() * beta
+        if Y_var is not None:
+            YRY = YRY + Y_var.sum() * beta                                    # :59
         eye = torch.eye(M, dtype=Z.dtype, device=Z.device)
         Lm = jitchol(rbf_K(variance, ell, Z) + eye * CONST_JITTER)            # :88-93
         Ls = jitchol(qU_var)                                                  # :96
@@ -169,6 +200,10 @@ class DeviceBound:
         extra = {"dL_dthetaL": dL_dthetaL,
                  "dL_dqU_mean": dL_dqU_mean - dKL_dqU_mean * qU_ratio,
                  "dL_dqU_var": dL_dqU_var - dKL_dqU_var * qU_ratio}
+        if Y_var is not None:
+            # :192  dtrtrs(Lm, psi1^T)^T . dtrtrs(Lm, mu) = psi1 . Kuu^-1 mu, without the N x M solve
+            extra["dL_dYmean"] = (psi1 @ KuuInvmu) * beta - Y * beta
+            extra["dL_dYvar"] = torch.full_like(Y, beta / -2.0)               # :193  [N, D]
         return logL, self._finish(variance, ell, Z, mu, S, dL_dpsi0, dL_dpsi1, dL_dpsi2,
                                   dL_dKmm - dKL_dKuu * qU_ratio, extra)
 

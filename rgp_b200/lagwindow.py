@@ -60,14 +60,35 @@ class LagWindow:
         return out
 
     def scatter_add(self, dX: torch.Tensor, lat_grad: Optional[torch.Tensor] = None,
-                    ctl_grad: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
-        """Adds dX [N, Q] onto lat_grad [lat_total, X_dim] / ctl_grad [ctl_total, U_dim]
-        (allocated as zeros when omitted)."""
-        if lat_grad is None:
-            lat_grad = torch.zeros((self.lat_total, max(self.X_dim, 1)), dtype=torch.float64, device=self.device)
-        if ctl_grad is None and self.U_win:
+                    ctl_grad: Optional[torch.Tensor] = None, allocate: bool = True
+                    ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+        """Adds dX [N, Q] onto lat_grad [lat_total, X_dim] / ctl_grad [ctl_total, U_dim], every
+        element in the reference's order of ``+=`` (layers.py:552-571).  Omitted targets are
+        allocated as zeros (``allocate=True``) or skipped."""
+        if lat_grad is None and allocate and self.X_win:
+            lat_grad = torch.zeros((self.lat_total, self.X_dim), dtype=torch.float64, device=self.device)
+        if ctl_grad is None and allocate and self.U_win:
             ctl_grad = torch.zeros((self.ctl_total, self.U_dim), dtype=torch.float64, device=self.device)
         self.handle.lag_scatter(self._stream(), self.nseq, self.desc.data_ptr(), self.N, self.X_win, self.X_dim,
-                                self.U_win, self.U_dim, dX.data_ptr(), self.lat_total, lat_grad.data_ptr(),
+                                self.U_win, self.U_dim, dX.data_ptr(), self.lat_total,
+                                lat_grad.data_ptr() if lat_grad is not None else None,
                                 self.ctl_total, ctl_grad.data_ptr() if ctl_grad is not None else None)
         return lat_grad, ctl_grad
+
+    def latent_terms(self, lat_mean: torch.Tensor, lat_var: torch.Tensor, dL_dYmean: torch.Tensor,
+                     dL_dYvar: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """``_prepare_gradients`` of a hidden layer (layers.py:582-615): returns the freshly
+        written latent gradients (gmean, gvar) [lat_total, X_dim] - output-side gradients on the
+        steps t >= X_win plus the entropy / prior gradients (variational.py:4-24) - and the
+        value the layer adds to its bound (0-d tensor)."""
+        D = self.X_dim
+        cols = 1 if dL_dYvar.dim() == 1 else int(dL_dYvar.shape[1])
+        if tuple(dL_dYmean.shape) != (self.N, D) or dL_dYvar.shape[0] != self.N or cols not in (1, D):
+            raise ValueError("dL_dYmean must be [N, D] and dL_dYvar [N] or [N, D]")
+        gm, gv = torch.empty_like(lat_mean), torch.empty_like(lat_var)
+        val = torch.empty((), dtype=torch.float64, device=self.device)
+        dym, dyv = dL_dYmean.contiguous(), dL_dYvar.contiguous()
+        self.handle.latent_terms(self._stream(), self.nseq, self.desc.data_ptr(), self.X_win, D,
+                                 lat_mean.data_ptr(), lat_var.data_ptr(), self.lat_total,
+                                 dym.data_ptr(), dyv.data_ptr(), cols, gm.data_ptr(), gv.data_ptr(), val.data_ptr())
+        return gm, gv, val

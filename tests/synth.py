@@ -29,3 +29,33 @@ def relerr(a, b):
     b = np.asarray(b, dtype=np.float64)
     denom = np.abs(b).max()
     return float(np.abs(a - b).max() / (denom if denom > 0 else 1.0))
+
+
+def make_deep_model(seed=3, wins=(0, 2, 3), nDims=(2, 1, 2), seq_lens=(9, 7), U_win=2, U_dim=1,
+                    M=5, control=True, svi=False):
+    """A small DeepAutoreg_new instance (autoreg/model.py:95-156): observations, hidden
+    latents per level (wins[i] + T_s steps), optional controls with variance 1e-10, and one
+    parameter dict per layer.  Level 0 is the observed layer (window 0)."""
+    rng = np.random.default_rng(seed)
+    L = len(wins)
+    Ys = [rng.normal(size=(T, nDims[0])) for T in seq_lens]
+    Us = None
+    if control:        # model.py:57-66: the control series is U_win-1 steps longer than Y
+        Us = [(rng.normal(size=(T + U_win - 1, U_dim)), np.full((T + U_win - 1, U_dim), 1e-10)) for T in seq_lens]
+    latents = []
+    for i in range(1, L):
+        latents.append([(rng.normal(size=(wins[i] + T, nDims[i])) * 0.7,
+                         rng.uniform(0.02, 0.3, size=(wins[i] + T, nDims[i]))) for T in seq_lens])
+    params = []
+    for i in range(L):
+        top = i == L - 1
+        Q = wins[i] * nDims[i] if i > 0 else 0
+        Q += (U_win * U_dim if control else 0) if top else wins[i + 1] * nDims[i + 1]
+        D = nDims[i]
+        p = dict(variance=float(rng.uniform(0.8, 1.6)), lengthscale=np.sqrt(Q) * rng.uniform(0.7, 1.4, size=Q),
+                 Z=rng.normal(size=(M, Q)), noise_variance=float(rng.uniform(0.05, 0.3)))
+        if svi:
+            p.update(qU_mean=rng.normal(size=(M, D)), qU_W=rng.normal(size=(M, M)) * 0.3,
+                     qU_a=float(rng.uniform(0.2, 0.6)), qU_ratio=1.0)
+        params.append(p)
+    return dict(wins=list(wins), Ys=Ys, Us=Us, U_win=U_win, latents=latents, params=params, svi=svi)

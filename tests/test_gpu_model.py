@@ -1,0 +1,97 @@
+"""GPU parity of the composed objective (SURVEY.md 8 f1 + f2): the latent-terms kernel, the
+in-order scatter onto non-zero gradients, and a whole DeepAutoreg evaluation on the device
+against oracle/model_oracle.py (itself pinned by finite differences, test_model_oracle.py)."""
+import numpy as np
+import pytest
+import torch
+
+from model_standins import compare_with_oracle, stack_model
+from oracle import bound_oracle as bo
+from oracle.lag_oracle import scatter_rows_into
+from synth import make_deep_model, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def _cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("lens,X_win,D,cols", [((9, 6, 12), 3, 2, 1), ((512,), 10, 1, 1), ((40, 33), 0, 3, 3),
+                                              ((100000, 77), 20, 2, 2)])
+def test_latent_terms_kernel(lens, X_win, D, cols):
+    from rgp_b200._lib import Handle
+    from rgp_b200.lagwindow import LagWindow
+    rng = np.random.default_rng(5)
+    ms = [rng.normal(size=(T, D)) for T in lens]
+    vs = [rng.uniform(0.01, 2.0, size=(T, D)) for T in lens]
+    N = sum(T - X_win for T in lens)
+    dYm = rng.normal(size=(N, D))
+    dYv = rng.normal(size=(N,) if cols == 1 else (N, D))
+    lw = LagWindow(Handle(0), lens, X_win, D, [T - X_win + 1 for T in lens], 2, 1)
+    gm, gv, val = lw.latent_terms(_cuda(np.vstack(ms)), _cuda(np.vstack(vs)), _cuda(dYm), _cuda(dYv))
+    ogm, ogv, delta, off, yoff = [], [], 0.0, 0, 0
+    for m, v in zip(ms, vs):
+        n = m.shape[0] - X_win
+        a, b = np.zeros_like(m), np.zeros_like(v)
+        a[X_win:] += dYm[yoff:yoff + n]
+        b[X_win:] += dYv[yoff:yoff + n] if cols != 1 else dYv[yoff:yoff + n, None]
+        if X_win:
+            val_, da, db = bo.normal_prior_term(m[:X_win], v[:X_win])
+            delta += val_; a[:X_win] += da; b[:X_win] += db
+        val_, db = bo.normal_entropy_term(v[X_win:])
+        delta += val_; b[X_win:] += db
+        ogm.append(a); ogv.append(b); yoff += n
+    np.testing.assert_array_equal(gm.cpu().numpy(), np.vstack(ogm))          # bit for bit
+    np.testing.assert_array_equal(gv.cpu().numpy(), np.vstack(ogv))
+    assert abs(float(val) - delta) <= 1e-13 * abs(delta)
+
+
+def test_scatter_adds_in_reference_order_onto_nonzero_gradients():
+    from rgp_b200._lib import Handle
+    from rgp_b200.lagwindow import LagWindow
+    rng = np.random.default_rng(6)
+    lens, X_win, X_dim, U_win, U_dim = (50, 31), 4, 2, 3, 2
+    ctl_lens = [T - X_win + U_win - 1 + 2 for T in lens]
+    lw = LagWindow(Handle(0), lens, X_win, X_dim, ctl_lens, U_win, U_dim)
+    g = rng.normal(size=(lw.N, lw.Q))
+    gX = [rng.normal(size=(T, X_dim)) for T in lens]
+    gU = [rng.normal(size=(T, U_dim)) for T in ctl_lens]
+    dlat, dctl = _cuda(np.vstack(gX)), _cuda(np.vstack(gU))
+    lw.scatter_add(_cuda(g), dlat, dctl, allocate=False)
+    scatter_rows_into(g, gX, gU, X_win, U_win, X_dim, U_dim)
+    np.testing.assert_array_equal(dlat.cpu().numpy(), np.vstack(gX))
+    np.testing.assert_array_equal(dctl.cpu().numpy(), np.vstack(gU))
+
+
+@pytest.mark.parametrize("svi,control,wins,nDims,seq_lens,M", [
+    (False, True, (0, 2, 3), (2, 1, 2), (9, 7), 5),
+    (False, False, (0, 2, 3), (2, 1, 2), (9, 7), 5),
+    (True, True, (0, 2, 3), (2, 1, 2), (9, 7), 5),
+    (True, False, (0, 1, 1, 2), (3, 2, 1, 1), (12, 5, 8), 7),
+    (False, True, (0, 10), (1, 1), (300,), 40),              # Actuator-like wiring, smaller
+    (False, False, (0, 20, 20), (6, 2, 2), (60, 45, 51), 30),  # MoCap-like wiring, smaller
+])
+def test_deep_model_on_device_matches_oracle(svi, control, wins, nDims, seq_lens, M):
+    from rgp_b200.layer import DeviceDeepAutoreg
+    m = make_deep_model(svi=svi, control=control, wins=wins, nDims=nDims, seq_lens=seq_lens, M=M,
+                        U_win=wins[-1] if control else 2)
+    Y, latents, controls, params = stack_model(m, to=_cuda)
+    model = DeviceDeepAutoreg(m["wins"], nDims, list(seq_lens), U_win=m["U_win"], ctl_dim=1 if control else 0,
+                              svi=svi, device=0)
+    out = model.evaluate(params, Y, latents, controls)
+    worst = compare_with_oracle(m, out, relerr, tol=1e-9, to_np=lambda a: a.detach().cpu().numpy())
+    print("worst relative error", worst)
+
+
+def test_deep_model_is_reproducible_run_to_run():
+    from rgp_b200.layer import DeviceDeepAutoreg
+    m = make_deep_model(wins=(0, 5, 5), nDims=(3, 2, 2), seq_lens=(700, 650), M=64, control=False)
+    Y, latents, controls, params = stack_model(m, to=_cuda)
+    model = DeviceDeepAutoreg(m["wins"], (3, 2, 2), [700, 650], U_win=m["U_win"], device=0)
+    a = model.evaluate(params, Y, latents, controls)
+    b = model.evaluate(params, Y, latents, controls)
+    assert float(a[0]) == float(b[0])            # the forward path reduces in a fixed order
+    for ga, gb in zip(a[2], b[2]):              # backward: red.global.add across block groups
+        torch.testing.assert_close(ga[0], gb[0], rtol=1e-12, atol=1e-14)
+        torch.testing.assert_close(ga[1], gb[1], rtol=1e-12, atol=1e-14)

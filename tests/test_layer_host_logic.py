@@ -1,0 +1,30 @@
+"""CPU test of the host logic in rgp_b200/layer.py (layer wiring, update order, uncertain-
+output branches of rgp_b200/inference.py) with oracle-backed stand-ins for the CUDA pieces."""
+import pytest
+
+from model_standins import OracleLag, OraclePsi, compare_with_oracle, stack_model
+from rgp_b200.inference import DeviceBound
+from rgp_b200.layer import DeviceDeepAutoreg
+from synth import make_deep_model, relerr
+
+
+@pytest.mark.parametrize("svi,control,wins,nDims", [
+    (False, True, (0, 2, 3), (2, 1, 2)),
+    (False, False, (0, 2, 3), (2, 1, 2)),
+    (True, True, (0, 2, 3), (2, 1, 2)),
+    (False, True, (0, 3), (1, 2)),
+    (True, False, (0, 1, 1, 2), (3, 2, 1, 1)),
+])
+def test_deep_model_matches_oracle(svi, control, wins, nDims):
+    m = make_deep_model(svi=svi, control=control, wins=wins, nDims=nDims)
+    Y, latents, controls, params = stack_model(m)
+    model = DeviceDeepAutoreg(m["wins"], nDims, [y.shape[0] for y in m["Ys"]], U_win=m["U_win"],
+                              ctl_dim=1 if control else 0, svi=svi, bound=DeviceBound(psi=OraclePsi()),
+                              lag_factory=OracleLag)
+    out = model.evaluate(params, Y, latents, controls)
+    compare_with_oracle(m, out, relerr, tol=1e-10)
+
+
+def test_rejects_windowed_observed_layer():
+    with pytest.raises(ValueError):
+        DeviceDeepAutoreg((1, 2), (1, 1), [5], bound=DeviceBound(psi=OraclePsi()), lag_factory=OracleLag)
