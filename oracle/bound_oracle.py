@@ -16,9 +16,13 @@ GPy helpers restated (GPy.util.linalg, not in /root/reference):
   backsub_both_sides(L, X, 'left')  = L^-T X L^-1 ;  'right' = L^-1 X L^-T
   tdot(A) = A A^T ; dpotri(L) = (L L^T)^-1 ; dtrtri(L) = L^-1
 
-PARITY UNPINNED against GPy binaries (GPy is absent); pinned relationally the way the
-reference's own tests pin it (``model.checkgrad`` -> finite differences here, and row
-additivity, testing/minibatch_tests.py:98-100, :288-296).
+PARITY PINNED against the reference's own code: tests/golden/ref_bounds.npz and
+ref_variational.npz hold outputs of autoreg/inference/vardtc.py, svi_vardtc.py and
+variational.py EXECUTED in the build container (tests/golden/make_reference_golden.py; only the
+GPy.util.linalg LAPACK wrappers and container classes they import are stubbed, GPy itself is
+absent), and tests/test_reference_golden.py holds this file to them at <= 1e-12.  Also pinned
+relationally the way the reference's tests pin themselves (``model.checkgrad`` -> finite
+differences, row additivity, testing/minibatch_tests.py:98-100, :288-296).
 """
 from __future__ import annotations
 

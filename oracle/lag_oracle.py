@@ -3,8 +3,9 @@ TEST INFRASTRUCTURE ONLY (see oracle/psi_oracle.py).
 
 Restates autoreg/util.py:6-12 (get_conv_1D), autoreg/layers.py:510-526 (_update_conv),
 :475-489 (_init_XY stacking) and :552-571 (update_latent_gradients) for one layer, with
-plain numpy and the same loops.  The reference has no fixture for this; it is pinned by the
-adjoint identity <gather(x), g> == <x, scatter(g)> (tests/test_lagwindow.py).
+plain numpy and the same loops.  ``get_conv_1D`` is pinned bit for bit against the reference's own function executed in
+the build container (tests/golden/ref_conv.npz, tests/test_reference_golden.py); the stacking and
+the scatter loops by the adjoint identity <gather(x), g> == <x, scatter(g)> (tests/test_lagwindow.py).
 """
 import numpy as np
 

@@ -25,8 +25,15 @@ LOG_2_PI = math.log(2.0 * math.pi)
 CONST_JITTER = 1e-6            # vardtc.py:28, svi_vardtc.py:28
 
 
-def jitchol(A: torch.Tensor, maxtries: int = 5) -> torch.Tensor:
+def jitchol(A: torch.Tensor, maxtries: int = 5, pending: Optional[list] = None) -> torch.Tensor:
+    """GPy ``jitchol``: plain Cholesky, and only if that fails growing diagonal jitter.
+    With ``pending`` (a list) the success flag of the plain factorisation is appended to it
+    instead of being read back - no host synchronisation; the caller checks all flags once
+    (``DeviceBound.verify``) and re-runs in the careful mode if any is non-zero."""
     L, info = torch.linalg.cholesky_ex(A)
+    if pending is not None:
+        pending.append(info)
+        return L
     if int(info) == 0:
         return L
     diag = torch.diagonal(A)
@@ -92,6 +99,23 @@ class DeviceBound:
 
     def __init__(self, device: Optional[int] = None, psi: Optional[DevicePsi] = None):
         self.psi = psi if psi is not None else DevicePsi(device)
+        self._pending: Optional[list] = None     # deferred Cholesky success flags (see jitchol)
+
+    # The M x M factorisations almost never need jitter.  A caller that evaluates several
+    # layers (rgp_b200.layer) opens a deferred section so that no factorisation reads its
+    # status back to the host; verify() reads all of them with one synchronisation.
+    def defer_checks(self) -> None:
+        self._pending = []
+
+    def verify(self) -> bool:
+        """True if every factorisation since defer_checks() succeeded; ends the section."""
+        pending, self._pending = self._pending, None
+        if not pending:
+            return True
+        return int(torch.stack([p.reshape(()) for p in pending]).abs().sum()) == 0
+
+    def _chol(self, A: torch.Tensor) -> torch.Tensor:
+        return jitchol(A, pending=self._pending)
 
     # ------------------------------------------------------------------ VarDTC
     def vardtc(self, variance: float, ell, Z, mu, S, Y, noise_variance: float, Y_var=None
@@ -113,9 +137,9 @@ class DeviceBound:
             YRY = YRY + Y_var.sum() * beta                                    # :77
         eye = torch.eye(M, dtype=Z.dtype, device=Z.device)
         Kmm = rbf_K(variance, ell, Z) + eye * CONST_JITTER                    # :110-114
-        Lm = jitchol(Kmm)
+        Lm = self._chol(Kmm)
         A = backsub_both_sides(Lm, psi2b, "right")                            # :120
-        LL = jitchol(eye + A)                                                 # :124-125
+        LL = self._chol(eye + A)                                                 # :124-125
         LmLL = Lm @ LL
         logdet_L = 2.0 * torch.log(torch.diagonal(LL)).sum()
         b = dtrtrs(LmLL, psi1Y.mT).mT                                         # :131
@@ -164,8 +188,8 @@ class DeviceBound:
         if Y_var is not None:
             YRY = YRY + Y_var.sum() * beta                                    # :59
         eye = torch.eye(M, dtype=Z.dtype, device=Z.device)
-        Lm = jitchol(rbf_K(variance, ell, Z) + eye * CONST_JITTER)            # :88-93
-        Ls = jitchol(qU_var)                                                  # :96
+        Lm = self._chol(rbf_K(variance, ell, Z) + eye * CONST_JITTER)            # :88-93
+        Ls = self._chol(qU_var)                                                  # :96
         LinvLs = dtrtrs(Lm, Ls)
         Linvmu = dtrtrs(Lm, qU_mean)
         psi1YLinvT = dtrtrs(Lm, psi1Y.mT).mT                                  # :99

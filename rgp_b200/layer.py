@@ -138,6 +138,13 @@ class DeviceDeepAutoreg:
         """params[i]: parameters of the level-i layer; Y [sum T_s, nDims[0]]; latents[i-1]:
         (mean, var) of level i, stacked over sequences; controls: (mean, var) stacked.
         Returns (logL, layer_results, latent_grads, control_grads) like the model oracle."""
+        self.bound.defer_checks()            # no per-factorisation read-back; checked once below
+        out = self._evaluate(params, Y, latents, controls)
+        if not self.bound.verify():          # some K(Z,Z) / Lambda needed jitter: careful re-run
+            out = self._evaluate(params, Y, latents, controls)
+        return out
+
+    def _evaluate(self, params, Y, latents, controls):
         L = len(self.wins)
         res: List[Optional[Dict]] = [None] * L
         for i in range(L - 1, -1, -1):                                   # model.py:176, top first

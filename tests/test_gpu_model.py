@@ -95,3 +95,47 @@ def test_deep_model_is_reproducible_run_to_run():
     for ga, gb in zip(a[2], b[2]):              # backward: red.global.add across block groups
         torch.testing.assert_close(ga[0], gb[0], rtol=1e-12, atol=1e-14)
         torch.testing.assert_close(ga[1], gb[1], rtol=1e-12, atol=1e-14)
+
+
+@pytest.mark.parametrize("tag", ["rnn", "gru", "lstm_bi"])
+def test_encoder_on_device_matches_reference_module(tag):
+    from test_encoder import load_reference_case
+    r, net = load_reference_case(tag, device="cuda")
+    means, variances = net(_cuda(r[tag + "__input"]))
+    for i in range(2):
+        np.testing.assert_allclose(means[i].detach().cpu().numpy(), r["%s__mean%d" % (tag, i)], rtol=0, atol=1e-13)
+        np.testing.assert_allclose(variances[i].detach().cpu().numpy(), r["%s__var%d" % (tag, i)], rtol=0, atol=1e-13)
+    torch.autograd.backward(means + variances, [_cuda(r["%s__gmean%d" % (tag, i)]) for i in range(2)] +
+                            [_cuda(r["%s__gvar%d" % (tag, i)]) for i in range(2)])
+    for name, p in net.named_parameters():
+        np.testing.assert_allclose(p.grad.cpu().numpy(), r["%s__grad__%s" % (tag, name)], rtol=1e-11, atol=1e-13)
+
+
+def test_encoder_to_objective_end_to_end_on_device():
+    """Recognition model -> latents -> device objective -> backward, all on the GPU, against
+    the CPU chain: reference-identical encoder (CPU) + oracle model gradients."""
+    import copy
+    from oracle.model_oracle import deep_autoreg_oracle
+    from rgp_b200.autograd import deep_autoreg_objective
+    from rgp_b200.encoder import RecognitionEncoder
+    from rgp_b200.layer import DeviceDeepAutoreg
+    T, w, B = 40, 3, 4
+    m = make_deep_model(seed=8, wins=(0, w, w), nDims=(2, 1, 2), seq_lens=(T,) * B, U_win=w, control=False, M=12)
+    torch.manual_seed(8)
+    enc_cpu = RecognitionEncoder([2, 1], [1, 2], 6, rnn_type="lstm")
+    enc = copy.deepcopy(enc_cpu).cuda()
+    x = np.random.default_rng(8).normal(size=(T + w, B, 2))
+    Y, _, _, params = stack_model(m, to=_cuda)
+    model = DeviceDeepAutoreg(m["wins"], (2, 1, 2), [T] * B, U_win=w, device=0)
+    L = deep_autoreg_objective(model, params, Y, enc.latents(_cuda(x)))
+    L.backward()
+    # CPU chain
+    lat = enc_cpu.latents(torch.from_numpy(x))
+    m["latents"] = [[(a.detach().numpy()[s * (T + w):(s + 1) * (T + w)], b.detach().numpy()[s * (T + w):(s + 1) * (T + w)])
+                     for s in range(B)] for a, b in lat]
+    oL, _, olat, _ = deep_autoreg_oracle(m["wins"], m["Ys"], m["latents"], m["params"], U_win=w)
+    assert abs(float(L) - oL) <= 1e-10 * abs(oL)
+    torch.autograd.backward([t for pair in lat for t in pair],
+                            [torch.from_numpy(np.vstack([s[k] for s in lvl])) for lvl in olat for k in (0, 1)])
+    for (n, p), (_, q) in zip(enc.named_parameters(), enc_cpu.named_parameters()):
+        assert relerr(p.grad.cpu().numpy(), q.grad.numpy()) <= 1e-8, n

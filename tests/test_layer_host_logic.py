@@ -28,3 +28,25 @@ def test_deep_model_matches_oracle(svi, control, wins, nDims):
 def test_rejects_windowed_observed_layer():
     with pytest.raises(ValueError):
         DeviceDeepAutoreg((1, 2), (1, 1), [5], bound=DeviceBound(psi=OraclePsi()), lag_factory=OracleLag)
+
+
+def test_deferred_cholesky_checks_fall_back_to_the_jitter_path():
+    """qU_var = W W^T with rank-1 W: the plain factorisation fails, GPy's jitchol adds jitter.
+    The deferred (no read-back) pass must notice and re-run in the careful mode."""
+    import numpy as np
+    import torch
+    m = make_deep_model(svi=True, control=False)
+    for p in m["params"]:
+        p["qU_W"] = np.ones_like(p["qU_W"])
+        p["qU_a"] = 0.0
+    Y, latents, controls, params = stack_model(m)
+    bound = DeviceBound(psi=OraclePsi())
+    model = DeviceDeepAutoreg(m["wins"], (2, 1, 2), [y.shape[0] for y in m["Ys"]], U_win=m["U_win"], svi=True,
+                              bound=bound, lag_factory=OracleLag)
+    calls = []
+    inner = model._evaluate
+    model._evaluate = lambda *a: (calls.append(bound._pending is None), inner(*a))[1]
+    logL, res, lat_grads, _ = model.evaluate(params, Y, latents, controls)
+    assert calls == [False, True]                      # deferred pass, then careful pass
+    assert np.isfinite(float(logL))
+    assert all(torch.isfinite(g[0]).all() and torch.isfinite(g[1]).all() for g in lat_grads)
