@@ -13,9 +13,12 @@ for models without back-constraints (no encoder).  The observed layer must have
 ``wins[0] == 0`` - the reference's ``_update_conv`` reads ``Xs_flat[i].mean`` and so cannot
 window plain observed arrays either.
 
-PARITY UNPINNED against GPy binaries; pinned relationally by finite differences of the
-whole objective with respect to every parameter block (tests/test_model_oracle.py), the way
-the reference pins itself with ``model.checkgrad`` (testing/*_tests.py).
+Pinning: the pieces this file composes (bounds, latent terms, lag windows) are held to outputs
+of the reference's own code (tests/golden/ref_*.npz, tests/test_reference_golden.py); the
+composition itself (layers.py / model.py need all of GPy to run and cannot be executed here) is
+pinned relationally by finite differences of the whole objective with respect to every
+parameter block (tests/test_model_oracle.py), the way the reference pins itself with
+``model.checkgrad`` (testing/*_tests.py).
 """
 from __future__ import annotations
 
