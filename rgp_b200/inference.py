@@ -97,8 +97,17 @@ class DeviceBound:
     psi forward -> bound algebra -> psi backward (+ the K(Z,Z) terms the layer adds,
     layers.py:98-134, 574-580)."""
 
-    def __init__(self, device: Optional[int] = None, psi: Optional[DevicePsi] = None):
+    def __init__(self, device: Optional[int] = None, psi: Optional[DevicePsi] = None, group=None,
+                 sharded: bool = False):
+        """``sharded=True`` (or a ``group``): the rows handed to vardtc / svi are THIS rank's
+        rows of a data set split across the ranks of ``group`` (default: the world).  The
+        sums over rows - Psi2, Psi1^T Y, YRY, N, the uncertain-output M x M terms, and after the
+        backward dvariance / dlengthscale / dZ - are all-reduced (exchanges C1 and
+        C2; the reference's dead MPI path did the first, svi_vardtc.py:65-67); the M x M
+        algebra then runs redundantly on every rank.  Returned bound and parameter gradients
+        are global and identical on every rank; Psi1, dL_dpsi1 and the row gradients stay local."""
         self.psi = psi if psi is not None else DevicePsi(device)
+        self.group, self.sharded = group, bool(sharded or group is not None)
         self._pending: Optional[list] = None     # deferred Cholesky success flags (see jitchol)
 
     # The M x M factorisations almost never need jitter.  A caller that evaluates several
@@ -117,6 +126,22 @@ class DeviceBound:
     def _chol(self, A: torch.Tensor) -> torch.Tensor:
         return jitchol(A, pending=self._pending)
 
+    def allsum(self, tensors):
+        """SUM over the ranks of the group of a list of tensors (one packed all-reduce);
+        identity when not sharded."""
+        if not self.sharded:
+            return list(tensors)
+        from .sharded import allreduce_packed
+        return allreduce_packed(list(tensors), self.group)
+
+    def _gather_stats(self, N, psi2, psi1Y, YRY):
+        """Exchange C1: the row sums every rank needs before the M x M algebra."""
+        if not self.sharded:
+            return N, psi2, psi1Y, YRY
+        n = torch.tensor([float(N)], dtype=psi2.dtype, device=psi2.device)
+        n, psi2, psi1Y, YRY = self.allsum([n, psi2, psi1Y, YRY.reshape(1)])
+        return int(round(float(n))), psi2, psi1Y, YRY.reshape(())
+
     # ------------------------------------------------------------------ VarDTC
     def vardtc(self, variance: float, ell, Z, mu, S, Y, noise_variance: float, Y_var=None
                ) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
@@ -129,12 +154,13 @@ class DeviceBound:
         M = Z.shape[0]
         beta = 1.0 / max(float(noise_variance), 1e-6)                         # :102
         _, psi1, psi2 = self.psi.forward(mu, S, Z, ell, variance)
-        psi0b = variance * N * beta                                           # :68
-        psi2b = psi2 * beta
         psi1Y = (Y.mT @ psi1) * beta                                          # :79  D x M
         YRY = Y.square().sum() * beta                                         # :81-82
         if Y_var is not None:
             YRY = YRY + Y_var.sum() * beta                                    # :77
+        N, psi2, psi1Y, YRY = self._gather_stats(N, psi2, psi1Y, YRY)         # N is global from here on
+        psi0b = variance * N * beta                                           # :68
+        psi2b = psi2 * beta
         eye = torch.eye(M, dtype=Z.dtype, device=Z.device)
         Kmm = rbf_K(variance, ell, Z) + eye * CONST_JITTER                    # :110-114
         Lm = self._chol(Kmm)
@@ -150,8 +176,9 @@ class DeviceBound:
             Shalf = Y_var.sum(dim=1).sqrt()                                   # :74
             psi1LmiLLi = rsolve_T(LmLL, psi1) * beta                          # :203  N x M
             psi1SLLinv = Shalf[:, None] * psi1LmiLLi                          # :137
-            bbt = bbt + psi1SLLinv.square().sum()
-            C = C + psi1SLLinv.mT @ psi1SLLinv                                # :139
+            C_S, bbt_S = self.allsum([psi1SLLinv.mT @ psi1SLLinv, psi1SLLinv.square().sum().reshape(1)])
+            bbt = bbt + bbt_S.reshape(())
+            C = C + C_S                                                       # :139
             psi1SP = rsolve(LmLL, psi1SLLinv)                                 # :140
         tmp = -backsub_both_sides(LL, C + D * eye)                            # :141
         dL_dpsi2R = backsub_both_sides(Lm, tmp + D * eye) / 2.0               # :142
@@ -181,12 +208,13 @@ class DeviceBound:
         M = Z.shape[0]
         beta = 1.0 / float(noise_variance)                                    # :80
         _, psi1, psi2 = self.psi.forward(mu, S, Z, ell, variance)
-        psi0b = variance * N * beta
-        psi2b = psi2 * beta
         psi1Y = (Y.mT @ psi1) * beta
         YRY = Y.square().sum() * beta
         if Y_var is not None:
             YRY = YRY + Y_var.sum() * beta                                    # :59
+        N, psi2, psi1Y, YRY = self._gather_stats(N, psi2, psi1Y, YRY)         # :65-67 (allReduceArrays)
+        psi0b = variance * N * beta
+        psi2b = psi2 * beta
         eye = torch.eye(M, dtype=Z.dtype, device=Z.device)
         Lm = self._chol(rbf_K(variance, ell, Z) + eye * CONST_JITTER)            # :88-93
         Ls = self._chol(qU_var)                                                  # :96
@@ -234,6 +262,7 @@ class DeviceBound:
     # ------------------------------------------------------------ shared tail
     def _finish(self, variance, ell, Z, mu, S, dL_dpsi0, dL_dpsi1, dL_dpsi2, dL_dKmm, extra):
         dvar, dl, dZ, dmu, dS = self.psi.backward(mu, S, Z, ell, variance, dL_dpsi0, dL_dpsi1, dL_dpsi2)
+        dvar, dl, dZ = self.allsum([dvar, dl, dZ])                            # exchange C2
         kvar, kl, kZ = rbf_K_grads(dL_dKmm, variance, ell, Z)
         out = {"variance": dvar.reshape(()) + kvar, "lengthscale": dl + kl, "Z": dZ + kZ, "mu": dmu, "S": dS,
                "dL_dKmm": dL_dKmm, "dL_dpsi1": dL_dpsi1, "dL_dpsi2": dL_dpsi2}

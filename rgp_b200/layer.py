@@ -87,7 +87,7 @@ class DeviceLayer:
                    noise_variance=g["dL_dthetaL"], dmu=g["mu"], dS=g["S"])
         if not self.observed:                                                           # :582-615
             gm, gv, delta = self.lag.latent_terms(lm, lv, g["dL_dYmean"], g["dL_dYvar"])
-            logL = logL + delta
+            logL = logL + self.bound.allsum([delta.reshape(1)])[0].reshape(())   # local latents, global bound
             out["gX"] = (gm, gv)
         out["logL"] = logL
         return out
@@ -108,6 +108,12 @@ class DeviceDeepAutoreg:
     seq_lens[s]         T_s, aligned observation steps per sequence (model.py:52-66)
     ctl_dim             dimensionality of the control series (0 = no controls); the control
                         series of sequence s has T_s + U_win - 1 steps (model.py:57-62)
+
+    Multi-GPU: build ``bound=DeviceBound(device, sharded=True)`` and give every rank ITS
+    sequences (``seq_lens``, Y, latents, controls of those sequences only).  Sequences are
+    independent given the layer parameters, so rows shard on sequence boundaries with no halo;
+    the bound and the parameter gradients come back global, latent gradients stay with the
+    rank that owns the sequence.
     """
 
     def __init__(self, wins: Sequence[int], nDims: Sequence[int], seq_lens: Sequence[int], U_win: int = 1,

@@ -139,3 +139,19 @@ def test_encoder_to_objective_end_to_end_on_device():
                             [torch.from_numpy(np.vstack([s[k] for s in lvl])) for lvl in olat for k in (0, 1)])
     for (n, p), (_, q) in zip(enc.named_parameters(), enc_cpu.named_parameters()):
         assert relerr(p.grad.cpu().numpy(), q.grad.numpy()) <= 1e-8, n
+
+
+def test_sharded_model_nccl_matches_single_gpu():
+    """>= 2 GPUs only: torchrun scripts/check_sharded_model_nccl.py (sequence-sharded objective)."""
+    import os
+    import subprocess
+    import sys
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(min(n, 4)),
+           "--master-addr", "127.0.0.1", "--master-port", "29613",
+           os.path.join(root, "scripts", "check_sharded_model_nccl.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
