@@ -1,0 +1,90 @@
+"""Trains BASELINE.json config 1 (Actuator, two layers, N = 502, M = 100, Q = 20 / 10) on the
+real data with the objective and every gradient computed on the GPU
+(rgp_b200.layer.DeviceDeepAutoreg through the autograd bridge) and scipy's L-BFGS-B driving it,
+following the reference's recipe (autoreg/benchmark/methods.py:62-84: 50 iterations with the
+kernel variances and noise fixed, then everything free).  Positive parameters are optimised in
+log space.  Prints one JSON line: bound before / after, evaluations, ms per evaluation."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import scipy.optimize
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from rgp_b200.autograd import deep_autoreg_objective  # noqa: E402
+from rgp_b200.layer import DeviceDeepAutoreg  # noqa: E402
+from synth import load_actuator_config1  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--init-iters", type=int, default=50)
+    ap.add_argument("--iters", type=int, default=300)
+    a = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    m, g = load_actuator_config1()
+    cuda = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    Y = cuda(m["Ys"][0])
+    controls = (cuda(m["Us"][0][0]), cuda(m["Us"][0][1]))
+    model = DeviceDeepAutoreg([0, 10], (1, 1), [502], U_win=10, ctl_dim=1, device=0)
+    # unconstrained parameter blocks
+    blocks = {}
+    for i, p in enumerate(m["params"]):
+        blocks["log_var%d" % i] = cuda(np.log([p["variance"]]))
+        blocks["log_ell%d" % i] = cuda(np.log(p["lengthscale"]))
+        blocks["Z%d" % i] = cuda(p["Z"])
+        blocks["log_noise%d" % i] = cuda(np.log([p["noise_variance"]]))
+    blocks["lat_mean"] = cuda(m["latents"][0][0][0])
+    blocks["log_lat_var"] = cuda(np.log(m["latents"][0][0][1]))
+    names = list(blocks)
+    sizes = [blocks[n].numel() for n in names]
+    evals = [0]
+
+    def unpack(x):
+        out, off = {}, 0
+        for n, s in zip(names, sizes):
+            out[n] = torch.from_numpy(x[off:off + s]).to(dev).reshape(blocks[n].shape).requires_grad_(True)
+            off += s
+        return out
+
+    def objective(x, frozen=()):
+        t = unpack(x)
+        params = [dict(variance=t["log_var%d" % i].exp().reshape(()), lengthscale=t["log_ell%d" % i].exp(),
+                       Z=t["Z%d" % i], noise_variance=t["log_noise%d" % i].exp().reshape(())) for i in range(2)]
+        L = deep_autoreg_objective(model, params, Y, [(t["lat_mean"], t["log_lat_var"].exp())], controls)
+        (-L).backward()
+        grad = torch.cat([(torch.zeros_like(t[n]) if (t[n].grad is None or n.startswith(frozen)) else t[n].grad).reshape(-1)
+                          for n in names]).cpu().numpy() if frozen else \
+            torch.cat([t[n].grad.reshape(-1) for n in names]).cpu().numpy()
+        evals[0] += 1
+        return -float(L), grad
+
+    x0 = torch.cat([blocks[n].reshape(-1) for n in names]).cpu().numpy()
+    f0, _ = objective(x0)
+    assert abs(-f0 - float(g["logL"])) <= max(1e-9, 50 * float(g["sens_logL"])) * abs(f0), \
+        "device objective differs from the oracle fixture"
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    r1 = scipy.optimize.minimize(lambda x: objective(x, frozen=("log_var", "log_noise")), x0, jac=True,
+                                 method="L-BFGS-B", options=dict(maxiter=a.init_iters))
+    r2 = scipy.optimize.minimize(objective, r1.x, jac=True, method="L-BFGS-B", options=dict(maxiter=a.iters))
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    t = unpack(r2.x)
+    print(json.dumps({
+        "row": "train_config1_actuator", "data": "real (actuator.mat via tests/golden/actuator_config1.npz)",
+        "n_parameters": int(x0.size), "bound_initial": -f0, "bound_after_init_phase": -float(r1.fun),
+        "bound_final": -float(r2.fun), "lbfgs_iterations": int(r1.nit + r2.nit), "evaluations": evals[0] - 1,
+        "wall_s": wall, "ms_per_evaluation_incl_optimizer": wall / (evals[0] - 1) * 1e3,
+        "noise_variance_final": [float(t["log_noise%d" % i].exp()) for i in range(2)],
+        "kernel_variance_final": [float(t["log_var%d" % i].exp()) for i in range(2)]}), flush=True)
+
+
+if __name__ == "__main__":
+    main()

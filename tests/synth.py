@@ -59,3 +59,18 @@ def make_deep_model(seed=3, wins=(0, 2, 3), nDims=(2, 1, 2), seq_lens=(9, 7), U_
                      qU_a=float(rng.uniform(0.2, 0.6)), qU_ratio=1.0)
         params.append(p)
     return dict(wins=list(wins), Ys=Ys, Us=Us, U_win=U_win, latents=latents, params=params, svi=svi)
+
+
+def load_actuator_config1(path=None):
+    """BASELINE.json config 1 on the real Actuator data (tests/golden/actuator_config1.npz, made
+    by tests/golden/make_actuator_config1.py): a make_deep_model-style dict plus the oracle's
+    bound and gradients."""
+    import os
+    if path is None:
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "actuator_config1.npz")
+    g = np.load(path)
+    params = [dict(variance=float(g["p%d_variance" % i]), lengthscale=g["p%d_lengthscale" % i].copy(),
+                   Z=g["p%d_Z" % i].copy(), noise_variance=float(g["p%d_noise_variance" % i])) for i in range(2)]
+    m = dict(wins=[0, 10], Ys=[g["Y"].copy()], Us=[(g["U"].copy(), np.full(g["U"].shape, 1e-10))], U_win=10,
+             latents=[[(g["lat_mean"].copy(), g["lat_var"].copy())]], params=params, svi=False)
+    return m, g

@@ -84,6 +84,29 @@ def test_deep_model_on_device_matches_oracle(svi, control, wins, nDims, seq_lens
     print("worst relative error", worst)
 
 
+def test_config1_real_actuator_data_matches_fixture():
+    """BASELINE.json config 1 at its real shapes on the real Actuator data (N = 502, M = 100,
+    Q = 20 / 10): device objective against the committed oracle fixture.  K(Z,Z) has a condition
+    number of 1e7-1e8 at this initialisation; the fixture records how far the oracle's own outputs
+    move under a 1e-15 relative perturbation of Z (``sens_*``), and that - not 1e-9 - bounds what
+    any two correct implementations can agree to (see tests/golden/make_actuator_config1.py)."""
+    from rgp_b200.layer import DeviceDeepAutoreg
+    from synth import load_actuator_config1
+    m, g = load_actuator_config1()
+    Y, latents, controls, params = stack_model(m, to=_cuda)
+    model = DeviceDeepAutoreg([0, 10], (1, 1), [502], U_win=10, ctl_dim=1, device=0)
+    logL, res, lat_grads, ctl_grads = model.evaluate(params, Y, latents, controls)
+    tol = lambda key: max(1e-9, 50.0 * float(g["sens_" + key]))
+    assert abs(float(logL) - float(g["logL"])) <= tol("logL") * abs(float(g["logL"]))
+    cpu = lambda a: a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    for i in range(2):
+        for k in ("variance", "lengthscale", "Z", "noise_variance"):
+            assert relerr(cpu(res[i][k]), g["g%d_%s" % (i, k)]) <= tol("g%d_%s" % (i, k)), (i, k)
+    assert relerr(cpu(lat_grads[0][0]), g["g_lat_mean"]) <= tol("g_lat_mean")
+    assert relerr(cpu(lat_grads[0][1]), g["g_lat_var"]) <= tol("g_lat_var")
+    assert relerr(cpu(ctl_grads[0]), g["g_ctl_mean"]) <= tol("g_ctl_mean")
+
+
 def test_deep_model_is_reproducible_run_to_run():
     from rgp_b200.layer import DeviceDeepAutoreg
     m = make_deep_model(wins=(0, 5, 5), nDims=(3, 2, 2), seq_lens=(700, 650), M=64, control=False)

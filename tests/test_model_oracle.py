@@ -71,3 +71,18 @@ def test_control_gradients_are_scattered_from_zero():
     idx = (3, 0)
     fd = _fd(m, lambda mm: mm["Us"][1][0], idx, 1e-6)
     assert abs(fd - ctl_grads[1][0][idx]) <= 2e-6 * max(1.0, abs(fd))
+
+
+def test_config1_fixture_is_what_the_oracle_computes():
+    """tests/golden/actuator_config1.npz (real Actuator data, reference benchmark recipe) must
+    stay what the oracle computes - a change of the oracle shows up here."""
+    from synth import load_actuator_config1, relerr
+    m, g = load_actuator_config1()
+    logL, res, lat_grads, ctl_grads = _objective(m)
+    # same code, same LAPACK: reproduces to rounding; conditioning (sens_*) bounds anything else
+    assert abs(logL - float(g["logL"])) <= 1e-12 * abs(logL)
+    for i in range(2):
+        for k in ("variance", "lengthscale", "Z", "noise_variance"):
+            assert relerr(res[i][k], g["g%d_%s" % (i, k)]) <= max(1e-10, float(g["sens_g%d_%s" % (i, k)])), (i, k)
+    assert relerr(lat_grads[0][0][0], g["g_lat_mean"]) <= max(1e-10, float(g["sens_g_lat_mean"]))
+    assert relerr(lat_grads[0][0][1], g["g_lat_var"]) <= max(1e-10, float(g["sens_g_lat_var"]))
