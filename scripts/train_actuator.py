@@ -55,15 +55,15 @@ def main():
 
     def objective(x, frozen=()):
         """-bound and its gradient.  A step of the line search that leaves the region where the
-        factorisations succeed is reported as +inf with a zero gradient - what paramz does for the
-        reference (it catches LinAlgError in its objective wrapper) - so L-BFGS-B backtracks."""
+        factorisations succeed is reported as a huge value with a zero gradient - what paramz does for
+        the reference (it catches LinAlgError in its objective wrapper) - so L-BFGS-B backtracks."""
         try:
             return _objective(x, frozen)
         except RuntimeError as err:
             if "not p" not in str(err):
                 raise
             failures[0] += 1
-            return np.inf, np.zeros_like(x)
+            return 1e10, np.zeros_like(x)
 
     failures = [0]
 
@@ -96,7 +96,7 @@ def main():
         "n_parameters": int(x0.size), "bound_initial": -f0, "bound_after_init_phase": -float(r1.fun),
         "bound_final": -float(r2.fun), "lbfgs_iterations": int(r1.nit + r2.nit), "evaluations": evals[0] - 1,
         "wall_s": wall, "ms_per_evaluation_incl_optimizer": wall / (evals[0] - 1) * 1e3,
-        "rejected_line_search_points": failures[0],
+        "rejected_line_search_points": failures[0], "termination": [str(r1.message), str(r2.message)],
         "noise_variance_final": [float(t["log_noise%d" % i].exp()) for i in range(2)],
         "kernel_variance_final": [float(t["log_var%d" % i].exp()) for i in range(2)]}), flush=True)
 
