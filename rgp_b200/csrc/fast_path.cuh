@@ -6,6 +6,7 @@
 #include "fast_prep.cuh"
 #include "psi2_kernels.cuh"
 #include "psi2_bwd16.cuh"
+#include "psi2_bwds.cuh"
 
 namespace rgp {
 namespace fast {
@@ -24,6 +25,8 @@ static int init(rgp_psi_ctx*) {
   RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwd<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<128>::BWD_SMEM));
   RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwd16<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg16<32>::BWD_SMEM));
   RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwd16<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg16<64>::BWD_SMEM));
+  RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwds<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2CfgS<32>::SMEM));
+  RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwds<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2CfgS<64>::SMEM));
   return 0;
 }
 
@@ -95,6 +98,11 @@ static int launch_bwd(rgp_psi_ctx* h, cudaStream_t st, const Shape& s, int64_t r
                       const double* Zt, const double* Ct, const double* w, const double* HP,
                       double* lam, double* Wq, double* ACCp) {
   if constexpr (QC == 32 || QC == 64) {
+    if (h->bwd_strip) {
+      RGP_LAUNCH(h, st, "psi2_bwd", (k_psi2_bwds<QC>), dim3(R, G), SW * 32, P2CfgS<QC>::SMEM, rows, s.Mp, s.nt,
+                 s.nblocks, s.qk, Zt, Ct, w, HP, lam, Wq, ACCp, 0);
+      return 0;
+    }
     if (h->bwd_warps == 16) {
       RGP_LAUNCH(h, st, "psi2_bwd", (k_psi2_bwd16<QC>), dim3(R, G), P2_THREADS16, P2Cfg16<QC>::BWD_SMEM, rows,
                  s.Mp, s.nt, s.nblocks, s.qk, Zt, Ct, w, HP, lam, Wq, ACCp, h->debug_skip, h->trace);

@@ -27,8 +27,10 @@ def plugins():
     from rgp_b200.psicomp import PSICOMP_RBF_B200
     p8 = PSICOMP_RBF_B200(impl="auto", cache=False)
     p8.handle.set_option("bwd_warps", 8)             # the 8-warp backward kernel (default is 16)
+    ps = PSICOMP_RBF_B200(impl="auto", cache=False)
+    ps.handle.set_option("bwd_strip", 1)             # the strip backward kernel (split-phase tile hand-off)
     return {"reference": PSICOMP_RBF_B200(impl="reference", cache=False),
-            "fast": PSICOMP_RBF_B200(impl="auto", cache=False), "fast8": p8}
+            "fast": PSICOMP_RBF_B200(impl="auto", cache=False), "fast8": p8, "strip": ps}
 
 
 def _kern(pc, var, ell, ard=True):
@@ -72,7 +74,7 @@ SHAPES = [
 ]
 
 
-@pytest.mark.parametrize("impl", IMPLS + ["fast8"])
+@pytest.mark.parametrize("impl", IMPLS + ["fast8", "strip"])
 @pytest.mark.parametrize("N,M,Q,nc", SHAPES)
 def test_forward_and_backward_match_oracle(plugins, impl, N, M, Q, nc):
     var, ell, Z, mu, S = make_inputs(N, M, Q, seed=100 + N + M + Q, n_control=nc)
@@ -81,7 +83,7 @@ def test_forward_and_backward_match_oracle(plugins, impl, N, M, Q, nc):
     _compare(fwd, bwd, psi_forward(var, ell, Z, mu, S), psi_backward(dL0, dL1, dL2, var, ell, Z, mu, S), TIGHT)
 
 
-@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("impl", IMPLS + ["strip"])
 def test_headline_tile_shape_small_n(plugins, impl):
     # M=512, Q=64 (the headline kernel configuration) at an N the oracle finishes in seconds
     N, M, Q = 192, 512, 64
