@@ -7,6 +7,7 @@
 #include "psi2_kernels.cuh"
 #include "psi2_bwd16.cuh"
 #include "psi2_bwds.cuh"
+#include "psi2_bwdm.cuh"
 
 namespace rgp {
 namespace fast {
@@ -25,6 +26,9 @@ static int init(rgp_psi_ctx*) {
   RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwd<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<128>::BWD_SMEM));
   RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwd16<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg16<32>::BWD_SMEM));
   RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwd16<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg16<64>::BWD_SMEM));
+  RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwdm<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2CfgM<16>::SMEM));
+  RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwdm<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2CfgM<32>::SMEM));
+  RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwdm<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2CfgM<64>::SMEM));
   RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwds<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2CfgS<32>::SMEM));
   RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwds<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2CfgS<64>::SMEM));
   return 0;
@@ -97,6 +101,13 @@ template <int QC>
 static int launch_bwd(rgp_psi_ctx* h, cudaStream_t st, const Shape& s, int64_t rows, int R, int G,
                       const double* Zt, const double* Ct, const double* w, const double* HP,
                       double* lam, double* Wq, double* ACCp) {
+  if constexpr (QC <= 64) {
+    if (h->bwd_mbar) {
+      RGP_LAUNCH(h, st, "psi2_bwd", (k_psi2_bwdm<QC>), dim3(R, G), P2_THREADS, P2CfgM<QC>::SMEM, rows, s.Mp, s.nt,
+                 s.nblocks, s.qk, Zt, Ct, w, HP, lam, Wq, ACCp, 0, h->debug_skip);
+      return 0;
+    }
+  }
   if constexpr (QC == 32 || QC == 64) {
     if (h->bwd_strip) {
       RGP_LAUNCH(h, st, "psi2_bwd", (k_psi2_bwds<QC>), dim3(R, G), SW * 32, P2CfgS<QC>::SMEM, rows, s.Mp, s.nt,

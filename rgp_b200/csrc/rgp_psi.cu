@@ -236,6 +236,9 @@ int rgp_psi_set_option(rgp_psi_handle_t h, const char* key, int64_t value) {
   } else if (!strcmp(key, "bwd_warps")) {
     if (value != 8 && value != 16) return set_error(RGP_PSI_ERR_INVALID, "bwd_warps must be 8 or 16");
     h->bwd_warps = (int)value;
+  } else if (!strcmp(key, "bwd_mbar")) {
+    if (value != 0 && value != 1) return set_error(RGP_PSI_ERR_INVALID, "bwd_mbar must be 0 or 1");
+    h->bwd_mbar = (int)value;
   } else if (!strcmp(key, "bwd_strip")) {
     if (value != 0 && value != 1) return set_error(RGP_PSI_ERR_INVALID, "bwd_strip must be 0 or 1");
     h->bwd_strip = (int)value;

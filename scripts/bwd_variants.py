@@ -11,8 +11,10 @@ mu = torch.randn((N, Q), generator=g, **f64); S = torch.rand((N, Q), generator=g
 Z = torch.randn((M, Q), generator=g, **f64); ell = (torch.rand(Q, generator=g, **f64) * 0.7 + 0.7) * Q ** 0.5
 dL1 = torch.randn((N, M), generator=g, **f64) / M; dL2 = torch.randn((M, M), generator=g, **f64) / M ** 2
 ref = None
-only = os.environ.get("BWD_VARIANTS", "bwd16,bwd8,strip").split(",")
-for name, opts in (("bwd16", {"bwd_warps": 16}), ("bwd8", {"bwd_warps": 8}), ("strip", {"bwd_strip": 1})):
+only = os.environ.get("BWD_VARIANTS", "bwd16,bwd8,mbar,strip")  # also: mbar_nolam, mbar_noatom (timing only).split(",")
+for name, opts in (("bwd16", {"bwd_warps": 16}), ("bwd8", {"bwd_warps": 8}), ("mbar", {"bwd_mbar": 1}), ("mbar_nolam", {"bwd_mbar": 1, "debug_skip": 1}),
+                   ("mbar_noatom", {"bwd_mbar": 1, "debug_skip": 3}),
+                   ("strip", {"bwd_strip": 1})):
     if name not in only:
         continue
     dp = DevicePsi(0)

@@ -29,8 +29,10 @@ def plugins():
     p8.handle.set_option("bwd_warps", 8)             # the 8-warp backward kernel (default is 16)
     ps = PSICOMP_RBF_B200(impl="auto", cache=False)
     ps.handle.set_option("bwd_strip", 1)             # the strip backward kernel (split-phase tile hand-off)
+    pm = PSICOMP_RBF_B200(impl="auto", cache=False)
+    pm.handle.set_option("bwd_mbar", 1)              # 8-warp kernel, split-phase hand-off instead of a barrier per row
     return {"reference": PSICOMP_RBF_B200(impl="reference", cache=False),
-            "fast": PSICOMP_RBF_B200(impl="auto", cache=False), "fast8": p8, "strip": ps}
+            "fast": PSICOMP_RBF_B200(impl="auto", cache=False), "fast8": p8, "strip": ps, "mbar": pm}
 
 
 def _kern(pc, var, ell, ard=True):
@@ -74,7 +76,7 @@ SHAPES = [
 ]
 
 
-@pytest.mark.parametrize("impl", IMPLS + ["fast8", "strip"])
+@pytest.mark.parametrize("impl", IMPLS + ["fast8", "strip", "mbar"])
 @pytest.mark.parametrize("N,M,Q,nc", SHAPES)
 def test_forward_and_backward_match_oracle(plugins, impl, N, M, Q, nc):
     var, ell, Z, mu, S = make_inputs(N, M, Q, seed=100 + N + M + Q, n_control=nc)
@@ -83,7 +85,7 @@ def test_forward_and_backward_match_oracle(plugins, impl, N, M, Q, nc):
     _compare(fwd, bwd, psi_forward(var, ell, Z, mu, S), psi_backward(dL0, dL1, dL2, var, ell, Z, mu, S), TIGHT)
 
 
-@pytest.mark.parametrize("impl", IMPLS + ["strip"])
+@pytest.mark.parametrize("impl", IMPLS + ["strip", "mbar"])
 def test_headline_tile_shape_small_n(plugins, impl):
     # M=512, Q=64 (the headline kernel configuration) at an N the oracle finishes in seconds
     N, M, Q = 192, 512, 64
