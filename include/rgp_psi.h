@@ -112,6 +112,20 @@ int rgp_psi_backward_host(rgp_psi_handle_t h, int64_t N, int M, int Q,
                           double* dmu_out, double* dS_out, double* dZ_out,
                           double* dell_out, double* dvar_out);
 
+/* Fused evaluation: the statistics AND the gradients from one pass over the rows, for callers whose
+ * upstream gradients do not depend on the statistics of the same evaluation - the uncollapsed SVI
+ * bound, where dL_dpsi1 = beta Y (Kuu^-1 mu)^T and dL_dpsi2 = beta Lm^-T (D I - ...) Lm^-1 / 2 are
+ * functions of q(U) and Kuu only (autoreg/inference/svi_vardtc.py:162-169).  The Psi2 backward kernel
+ * has exp(E_n) in hand for every row and accumulates Psi2 on the side, so the separate forward pass
+ * (a quarter of a two-phase evaluation) disappears.  Arguments as rgp_psi_backward_dev plus
+ * psi1_out [N, M] (may be NULL) and psi2_out [M, M]. */
+int rgp_psi_fused_dev(rgp_psi_handle_t h, void* stream, int64_t N, int M, int Q,
+                      const double* mu, const double* S, const double* Z, const double* ell,
+                      double variance, const double* dL_dpsi0, double dL_dpsi0_const,
+                      const double* dL_dpsi1, const double* dL_dpsi2, double* psi1_out,
+                      double* psi2_out, double* dmu_out, double* dS_out, double* dZ_out,
+                      double* dell_out, double* dvar_out);
+
 /* ---- lag-window gather / scatter-add (the callers either side of the path) ----------
  * Builds the layer input rows from the stacked latent sequences and adds X-row gradients
  * back onto latent steps: autoreg/layers.py:510-526 (_update_conv via get_conv_1D,

@@ -35,6 +35,10 @@ SIGNATURES = {
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                         C.c_void_p, C.c_double, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rgp_psi_fused_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
+                                    C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rgp_lag_gather_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int,
                                      C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rgp_lag_scatter_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int,
@@ -176,6 +180,12 @@ class Handle:
         check(load().rgp_psi_backward_dev(self._ensure(), C.c_void_p(stream), N, M, Q, mu, S, Z, ell,
                                           float(variance), dL0, float(dL0c), dL1, dL2,
                                           dmu, dS, dZ, dell, dvar))
+
+    def fused_dev(self, stream, N, M, Q, mu, S, Z, ell, variance, dL0, dL0c, dL1, dL2, psi1, psi2,
+                  dmu, dS, dZ, dell, dvar) -> None:
+        check(load().rgp_psi_fused_dev(self._ensure(), C.c_void_p(stream), N, M, Q, mu, S, Z, ell,
+                                       float(variance), dL0, float(dL0c), dL1, dL2, psi1, psi2,
+                                       dmu, dS, dZ, dell, dvar))
 
     def lag_gather(self, stream, nseq, seq_desc, N, Xwin, Dx, Uwin, Du, lat, ctl, out) -> None:
         check(load().rgp_lag_gather_dev(self._ensure(), C.c_void_p(stream), nseq, seq_desc, N, Xwin, Dx, Uwin, Du,

@@ -22,6 +22,10 @@ static int init(rgp_psi_ctx*) {
   RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwd<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<16>::BWD_SMEM));
   RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwd<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<32>::BWD_SMEM));
   RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwd<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<64>::BWD_SMEM));
+  RGP_CUDA(cudaFuncSetAttribute((k_psi2_bwd<16, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<16>::BWD_FUSED_SMEM));
+  RGP_CUDA(cudaFuncSetAttribute((k_psi2_bwd<32, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<32>::BWD_FUSED_SMEM));
+  RGP_CUDA(cudaFuncSetAttribute((k_psi2_bwd<64, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<64>::BWD_FUSED_SMEM));
+  RGP_CUDA(cudaFuncSetAttribute((k_psi2_bwd<128, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<128>::BWD_FUSED_SMEM));
   RGP_CUDA(cudaFuncSetAttribute(k_psi2_fwd<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<128>::FWD_SMEM));
   RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwd<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<128>::BWD_SMEM));
   RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwd16<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg16<32>::BWD_SMEM));
@@ -100,7 +104,15 @@ static int launch_fwd(rgp_psi_ctx* h, cudaStream_t st, const Shape& s, int64_t r
 template <int QC>
 static int launch_bwd(rgp_psi_ctx* h, cudaStream_t st, const Shape& s, int64_t rows, int R, int G,
                       const double* Zt, const double* Ct, const double* w, const double* HP,
-                      double* lam, double* Wq, double* ACCp) {
+                      double* lam, double* Wq, double* ACCp, double* P2p) {
+  if (P2p) {   // fused forward + backward: the 8-warp kernel also accumulates the Psi2 partial tiles
+    RGP_LAUNCH(h, st, "psi2_bwd_fused", (k_psi2_bwd<QC, true>), dim3(R, G), P2_THREADS, P2Cfg<QC>::BWD_FUSED_SMEM,
+               rows, s.Mp, s.nt, s.nblocks, s.qk, Zt, Ct, w, HP, lam, Wq, ACCp, 0, P2p);
+    for (int qoff = P2Cfg<QC>::QS; qoff < QC; qoff += P2Cfg<QC>::QS)
+      RGP_LAUNCH(h, st, "psi2_bwd", (k_psi2_bwd<QC>), dim3(R, G), P2_THREADS, P2Cfg<QC>::BWD_SMEM, rows, s.Mp,
+                 s.nt, s.nblocks, s.qk, Zt, Ct, w, HP, lam, Wq, ACCp, qoff, (double*)nullptr);
+    return 0;
+  }
   if constexpr (QC <= 64) {
     if (h->bwd_mbar) {
       RGP_LAUNCH(h, st, "psi2_bwd", (k_psi2_bwdm<QC>), dim3(R, G), P2_THREADS, P2CfgM<QC>::SMEM, rows, s.Mp, s.nt,
@@ -122,7 +134,7 @@ static int launch_bwd(rgp_psi_ctx* h, cudaStream_t st, const Shape& s, int64_t r
   }
   for (int qoff = 0; qoff < QC; qoff += P2Cfg<QC>::QS)   // two passes for QC = 128
     RGP_LAUNCH(h, st, "psi2_bwd", (k_psi2_bwd<QC>), dim3(R, G), P2_THREADS, P2Cfg<QC>::BWD_SMEM, rows,
-               s.Mp, s.nt, s.nblocks, s.qk, Zt, Ct, w, HP, lam, Wq, ACCp, qoff);
+               s.Mp, s.nt, s.nblocks, s.qk, Zt, Ct, w, HP, lam, Wq, ACCp, qoff, (double*)nullptr);
   return 0;
 }
 
@@ -206,7 +218,10 @@ static int forward(rgp_psi_ctx* h, cudaStream_t st, int64_t N, int M, int Q, con
 static int backward(rgp_psi_ctx* h, cudaStream_t st, int64_t N, int M, int Q, const double* mu,
                     const double* S, const double* Z, const double* ell, double variance,
                     const double* dL0, double dL0c, const double* dL1, const double* dL2,
-                    double* dmu, double* dS, double* dZ, double* dell, double* dvar) {
+                    double* dmu, double* dS, double* dZ, double* dell, double* dvar,
+                    double* psi1_out = nullptr, double* psi2_out = nullptr) {
+  // psi1_out / psi2_out (optional): fused evaluation - the statistics come out of the same pass
+  // (Psi1 from one more small GEMM, Psi2 from the backward kernel itself, see k_psi2_bwd FUSE)
   const Shape s = make_shape(h, N, M, Q);
   int R, G;
   pick_grid(s.rc, s.nblocks, h->sm_count, &R, &G);
@@ -221,13 +236,15 @@ static int backward(rgp_psi_ctx* h, cudaStream_t st, int64_t N, int M, int Q, co
                 bump_size(s.rc * 2 * QC, 8) * 4 + bump_size(s.rc, 8) * 2 + bump_size(s.rc * Mp, 8) * 2 +
                 bump_size((size_t)G * s.rc * Mp, 8) + bump_size((size_t)G * s.rc * QC, 8) +
                 bump_size((size_t)ncta * Mp * QC, 8) + bump_size((size_t)splits * Mp * 2 * QC, 8) * 2 +
-                bump_size((size_t)nfin * (QC + 1), 8);
+                bump_size((size_t)nfin * (QC + 1), 8) +
+                (psi2_out ? bump_size((size_t)s.nblocks * R * 4096, 8) : 0);
   RGP_TRY(arena_reserve(&h->ws, &h->ws_bytes, need));
   Bump b(h->ws, h->ws_bytes);
   double* o = b.take<double>(Q);
   double* Zt = b.take<double>((size_t)Mp * s.RS);
   double* ZB = b.take<double>((size_t)Mp * 2 * QC);
   double* Ct = b.take<double>((size_t)s.nblocks * 4096);
+  double* P2p = psi2_out ? b.take<double>((size_t)s.nblocks * R * 4096) : nullptr;
   double* w = b.take<double>(s.rc * QC);
   double* A2 = b.take<double>(s.rc * 2 * QC);
   double* A1 = b.take<double>(s.rc * 2 * QC);
@@ -252,7 +269,8 @@ static int backward(rgp_psi_ctx* h, cudaStream_t st, int64_t N, int M, int Q, co
   RGP_TRY(static_prep(h, st, s, Z, o, Zt, ZB));
   RGP_LAUNCH(h, st, "build_C", k_build_C, s.nblocks, 256, 0, M, s.nt, dL2, variance * variance, Ct);
 
-  for (int64_t r0 = 0; r0 < N; r0 += s.rc) {
+  int chunk = 0;
+  for (int64_t r0 = 0; r0 < N; r0 += s.rc, ++chunk) {
     const int64_t rows = std::min(s.rc, N - r0);
     int Rc, Gc;
     pick_grid(rows, s.nblocks, h->sm_count, &Rc, &Gc);
@@ -263,19 +281,27 @@ static int backward(rgp_psi_ctx* h, cudaStream_t st, int64_t N, int M, int Q, co
     RGP_CUDA(cudaMemsetAsync(Wq, 0, sizeof(double) * (size_t)Gc * rows * QC, st));
     RGP_CUDA(cudaMemsetAsync(ACCp, 0, sizeof(double) * (size_t)nc * Mp * QC, st));
     RGP_LAUNCH(h, st, "rowprep", k_rowprep, ceil_div(rows, 4), 128, 0, rows, Q, QC, mu + r0 * Q,
-               S + r0 * Q, ell, o, w, A2, b2, dL1 ? A1 : (double*)nullptr, dL1 ? b1 : (double*)nullptr);
+               S + r0 * Q, ell, o, w, A2, b2, (dL1 || psi1_out) ? A1 : (double*)nullptr,
+               (dL1 || psi1_out) ? b1 : (double*)nullptr);
     GemmEpi e;
     e.mode = EPI_HP; e.bias = b2; e.variance = variance; e.scale = nullptr; e.scale_ld = 0; e.M = M;
     e.out = HP; e.out_ld = rows; e.split_stride = 0;
     RGP_TRY(gemm_nt(h, st, "hprime_gemm", s, rows, A2, ZB, e));
+    if (psi1_out) {
+      e.mode = EPI_PSI1; e.bias = b1; e.out = psi1_out + r0 * M; e.out_ld = M;
+      RGP_TRY(gemm_nt(h, st, "psi1_fwd", s, rows, A1, ZB, e));
+    }
     if (dL1) {
       e.mode = EPI_L1; e.bias = b1; e.scale = dL1 + r0 * M; e.scale_ld = M; e.out = L1; e.out_ld = Mp;
       RGP_TRY(gemm_nt(h, st, "psi1_L1", s, rows, A1, ZB, e));
     }
-    if (QC == 16) RGP_TRY(launch_bwd<16>(h, st, s, rows, Rc, Gc, Zt, Ct, w, HP, lam, Wq, ACCp));
-    else if (QC == 32) RGP_TRY(launch_bwd<32>(h, st, s, rows, Rc, Gc, Zt, Ct, w, HP, lam, Wq, ACCp));
-    else if (QC == 64) RGP_TRY(launch_bwd<64>(h, st, s, rows, Rc, Gc, Zt, Ct, w, HP, lam, Wq, ACCp));
-    else RGP_TRY(launch_bwd<128>(h, st, s, rows, Rc, Gc, Zt, Ct, w, HP, lam, Wq, ACCp));
+    if (QC == 16) RGP_TRY(launch_bwd<16>(h, st, s, rows, Rc, Gc, Zt, Ct, w, HP, lam, Wq, ACCp, P2p));
+    else if (QC == 32) RGP_TRY(launch_bwd<32>(h, st, s, rows, Rc, Gc, Zt, Ct, w, HP, lam, Wq, ACCp, P2p));
+    else if (QC == 64) RGP_TRY(launch_bwd<64>(h, st, s, rows, Rc, Gc, Zt, Ct, w, HP, lam, Wq, ACCp, P2p));
+    else RGP_TRY(launch_bwd<128>(h, st, s, rows, Rc, Gc, Zt, Ct, w, HP, lam, Wq, ACCp, P2p));
+    if (P2p)
+      RGP_LAUNCH(h, st, "psi2_reduce", k_psi2_reduce, s.nblocks, 256, 0, M, s.nt, Rc, variance * variance, P2p,
+                 (chunk > 0 || h->accumulate) ? 1 : 0, psi2_out);
     if (Gc > 1) {
       RGP_LAUNCH(h, st, "collapse", k_collapse, ceil_div(rows * Mp, 256), 256, 0, rows * Mp, Gc, lam);
       RGP_LAUNCH(h, st, "collapse", k_collapse, ceil_div(rows * QC, 256), 256, 0, rows * QC, Gc, Wq);

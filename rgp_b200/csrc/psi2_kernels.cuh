@@ -46,6 +46,8 @@ struct P2Cfg {
   static constexpr int FWD_SMEM = (2 * 64 * RS + 3 * VB + 256) * 8;
   static constexpr int BWD_SMEM =
       (2 * 64 * RS + 2 * 64 * RSL + 3 * VB + 2 * 4 * QS + 2 * 2 * 64 + 2 * 4 * 64 + 256) * 8;
+  // fused variant (also accumulates the Psi2 tile of the block in shared memory): + [64][RSL]
+  static constexpr int BWD_FUSED_SMEM = BWD_SMEM + 64 * RSL * 8;
 };
 
 RGP_DEVINL void dmma(double& d0, double& d1, double a, double b) {
@@ -279,13 +281,19 @@ k_psi2_fwd(int64_t rc, int nt, int nblocks, int qk, const double* __restrict__ Z
 //   lam [g][rc][Mp]  += row / column sums of L        (red.global.add, buffers pre-zeroed)
 //   Wq  [g][rc][QC]  += (1 or 2) * sum_m Z'_mq T[m,q]
 //   ACCp[cta][Mp][QC] += sum_n ws_nq (L_n Z')[m,q]     (CTA-private, plain RMW)
+// FUSE: the kernel also produces the forward result - it has p = exp(E) in hand for every row, so
+//   P2p[b][r][64][64] = sum_n p (the partial tiles k_psi2_fwd writes, same layout)
+// is accumulated in a CTA-private shared tile (every element is owned by one thread: plain
+// read-modify-write, 16 adds per thread and row) and the separate forward pass with its own
+// stage 1 + exp is not needed.  Usable when the upstream gradients do not depend on the statistics
+// of the same evaluation (the SVI bound, autoreg/inference/svi_vardtc.py:162-169).
 // =====================================================================================
-template <int QC>
+template <int QC, bool FUSE = false>
 __global__ void __launch_bounds__(P2_THREADS, 1)
 k_psi2_bwd(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __restrict__ Zt,
            const double* __restrict__ Ct, const double* __restrict__ wrow,
            const double* __restrict__ HP, double* __restrict__ lam, double* __restrict__ Wq,
-           double* __restrict__ ACCp, int qoff) {
+           double* __restrict__ ACCp, int qoff, double* __restrict__ P2p = nullptr) {
   // qoff: first q column of this pass's stage-2 outputs (0, or 64 for the second pass of QC = 128);
   // lambda is flushed by the qoff == 0 pass only.
   using C = P2Cfg<QC>;
@@ -299,6 +307,7 @@ k_psi2_bwd(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __rest
   double* sLr = sWq + 2 * 4 * QS;                 // [2][2][64]  row-sum partials (per wc)
   double* sLc = sLr + 2 * 2 * 64;                 // [2][4][64]  col-sum partials (per wr)
   double* sT = sLc + 2 * 4 * 64;                  // exp table, 256 entries
+  double* sP = sT + 256;                          // FUSE: Psi2 tile of the block [64][RSL]
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int wr = wid >> 1, wc = wid & 1, g = lane >> 2, t = lane & 3;
@@ -332,6 +341,8 @@ k_psi2_bwd(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __rest
       return hJ[n * 64 + (tid - QC - 64)];
     };
     if (r0 < r1 && tid < VB) sV[(r0 % 3) * VB + tid] = vec_load(r0);
+    if constexpr (FUSE)
+      for (int i = tid; i < 64 * RSL; i += P2_THREADS) sP[i] = 0.0;
     double accI[2][NJ][2], accJ[2][NJ][2];
 #pragma unroll
     for (int i = 0; i < 2; ++i)
@@ -432,8 +443,16 @@ k_psi2_bwd(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __rest
           for (int i = 0; i < 2; ++i) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              double l0 = creg[i][j][0] * exp_tab(acc[i][j][0], sT);
-              double l1 = creg[i][j][1] * exp_tab(acc[i][j][1], sT);
+              const double p0 = exp_tab(acc[i][j][0], sT), p1 = exp_tab(acc[i][j][1], sT);
+              if constexpr (FUSE) {
+                double2* pp = reinterpret_cast<double2*>(sP + (16 * wr + 8 * i + g) * RSL + 32 * wc + 8 * j + 2 * t);
+                double2 o = *pp;
+                o.x += p0;
+                o.y += p1;
+                *pp = o;
+              }
+              double l0 = creg[i][j][0] * p0;
+              double l1 = creg[i][j][1] * p1;
               *reinterpret_cast<double2*>(Lb + (16 * wr + 8 * i + g) * RSL + 32 * wc + 8 * j + 2 * t) =
                   make_double2(l0, l1);
               rs[i] += l0 + l1;
@@ -514,9 +533,17 @@ k_psi2_bwd(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __rest
 #pragma unroll
           for (int s5 = 0; s5 < 5; ++s5)
             if (s5 < cnt) {
-              const double l0 = creg[s5][0] * exp_tab(acc[s5][0], sT);
-              const double l1 = creg[s5][1] * exp_tab(acc[s5][1], sT);
+              const double p0 = exp_tab(acc[s5][0], sT), p1 = exp_tab(acc[s5][1], sT);
+              const double l0 = creg[s5][0] * p0;
+              const double l1 = creg[s5][1] * p1;
               const int m = 8 * ti[s5] + g, mp = 8 * tj[s5] + 2 * t;
+              if constexpr (FUSE) {
+                double2* pp = reinterpret_cast<double2*>(sP + m * RSL + mp);
+                double2 o = *pp;
+                o.x += p0;
+                o.y += p1;
+                *pp = o;
+              }
               *reinterpret_cast<double2*>(Lb + m * RSL + mp) = make_double2(l0, l1);
               if (ti[s5] != tj[s5]) {
                 Lb[mp * RSL + m] = l0;
@@ -543,6 +570,34 @@ k_psi2_bwd(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __rest
     }
     __syncthreads();
     if (r1 > r0) flush_wq(r1 - 1);
+    if constexpr (FUSE) {
+      // every thread writes the tile elements it owns (the ones it accumulated), forward layout;
+      // diagonal blocks mirror their upper tiles like k_psi2_fwd
+      double* out = P2p + ((size_t)b * R + blockIdx.x) * 4096;
+      if (!diag) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int m = 16 * wr + 8 * i + g, mp = 32 * wc + 8 * j + 2 * t;
+            *reinterpret_cast<double2*>(out + m * 64 + mp) = *reinterpret_cast<const double2*>(sP + m * RSL + mp);
+          }
+      } else {
+        int ti[5], tj[5], cnt;
+        diag_tiles(wid, ti, tj, cnt);
+#pragma unroll
+        for (int s5 = 0; s5 < 5; ++s5)
+          if (s5 < cnt) {
+            const int m = 8 * ti[s5] + g, mp = 8 * tj[s5] + 2 * t;
+            const double2 x = *reinterpret_cast<const double2*>(sP + m * RSL + mp);
+            *reinterpret_cast<double2*>(out + m * 64 + mp) = x;
+            if (ti[s5] != tj[s5]) {
+              out[mp * 64 + m] = x.x;
+              out[(mp + 1) * 64 + m] = x.y;
+            }
+          }
+      }
+    }
     // flush the CTA-private dZ accumulators of this block
 #pragma unroll
     for (int i = 0; i < 2; ++i)

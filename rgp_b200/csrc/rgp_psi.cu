@@ -287,6 +287,27 @@ int rgp_psi_backward_dev(rgp_psi_handle_t h, void* stream, int64_t N, int M, int
                           dL_dpsi1, dL_dpsi2, dmu_out, dS_out, dZ_out, dell_out, dvar_out);
 }
 
+int rgp_psi_fused_dev(rgp_psi_handle_t h, void* stream, int64_t N, int M, int Q, const double* mu,
+                      const double* S, const double* Z, const double* ell, double variance,
+                      const double* dL_dpsi0, double dL_dpsi0_const, const double* dL_dpsi1,
+                      const double* dL_dpsi2, double* psi1_out, double* psi2_out, double* dmu_out,
+                      double* dS_out, double* dZ_out, double* dell_out, double* dvar_out) {
+  RGP_TRY(check_common(h, N, M, Q, mu, S, Z, ell, variance));
+  if (!dL_dpsi2 || !psi2_out || !dmu_out || !dS_out || !dZ_out || !dell_out || !dvar_out)
+    return set_error(RGP_PSI_ERR_INVALID, "null dL_dpsi2 or output pointer");
+  RGP_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (h->impl == RGP_PSI_IMPL_FAST && !fast::supported(M, Q))
+    return set_error(RGP_PSI_ERR_INVALID, "fast path does not support M=%d Q=%d", M, Q);
+  if (use_fast(h, M, Q))
+    return fast::backward(h, st, N, M, Q, mu, S, Z, ell, variance, dL_dpsi0, dL_dpsi0_const, dL_dpsi1, dL_dpsi2,
+                          dmu_out, dS_out, dZ_out, dell_out, dvar_out, psi1_out, psi2_out);
+  // reference kernels: two passes
+  RGP_TRY(refdrv::forward(h, st, N, M, Q, mu, S, Z, ell, variance, nullptr, psi1_out, psi2_out));
+  return refdrv::backward(h, st, N, M, Q, mu, S, Z, ell, variance, dL_dpsi0, dL_dpsi0_const, dL_dpsi1, dL_dpsi2,
+                          dmu_out, dS_out, dZ_out, dell_out, dvar_out);
+}
+
 // ------------------------------------------------------------- host-buffer wrappers
 // Rows are streamed in chunks through double-buffered device mirrors on three streams (copy-in,
 // compute, copy-out), so host<->device traffic overlaps the kernels (only truly asynchronous when

@@ -83,3 +83,30 @@ class DevicePsi:
                                  dL_dpsi2.data_ptr(), dmu.data_ptr(), dS.data_ptr(), dZ.data_ptr(),
                                  dell.data_ptr(), dvar.data_ptr())
         return dvar, dell, dZ, dmu, dS
+
+    def fused(self, mu, S, Z, ell, variance: float, dL_dpsi0, dL_dpsi1, dL_dpsi2, want_psi1: bool = True):
+        """Statistics and gradients from one pass (``rgp_psi_fused_dev``): for upstream gradients
+        that do not depend on the statistics of this evaluation (the SVI bound).  Returns
+        ((psi1 | None, psi2), (dvar, dell, dZ, dmu, dS))."""
+        N, Q = mu.shape
+        M = Z.shape[0]
+        _check(mu, "mu"); _check(S, "S", (N, Q)); _check(Z, "Z", (M, Q)); _check(ell, "ell", (Q,))
+        _check(dL_dpsi2, "dL_dpsi2", (M, M))
+        if dL_dpsi1 is not None:
+            _check(dL_dpsi1, "dL_dpsi1", (N, M))
+        dev = mu.device
+        if isinstance(dL_dpsi0, torch.Tensor):
+            _check(dL_dpsi0, "dL_dpsi0", (N,))
+            p0, c0 = dL_dpsi0.data_ptr(), 0.0
+        else:
+            p0, c0 = None, float(dL_dpsi0)
+        f64 = dict(dtype=torch.float64, device=dev)
+        psi1 = torch.empty((N, M), **f64) if want_psi1 else None
+        psi2 = torch.empty((M, M), **f64)
+        dmu, dS = torch.empty((N, Q), **f64), torch.empty((N, Q), **f64)
+        dZ, dell, dvar = torch.empty((M, Q), **f64), torch.empty(Q, **f64), torch.empty(1, **f64)
+        self.handle.fused_dev(self._stream(), N, M, Q, mu.data_ptr(), S.data_ptr(), Z.data_ptr(), ell.data_ptr(),
+                              variance, p0, c0, dL_dpsi1.data_ptr() if dL_dpsi1 is not None else None,
+                              dL_dpsi2.data_ptr(), psi1.data_ptr() if psi1 is not None else None, psi2.data_ptr(),
+                              dmu.data_ptr(), dS.data_ptr(), dZ.data_ptr(), dell.data_ptr(), dvar.data_ptr())
+        return (psi1, psi2), (dvar, dell, dZ, dmu, dS)

@@ -201,13 +201,38 @@ class DeviceBound:
 
     # -------------------------------------------------------------------- SVI
     def svi(self, variance: float, ell, Z, mu, S, Y, noise_variance: float, qU_mean, qU_var,
-            qU_ratio: float = 1.0, Y_var=None) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
+            qU_ratio: float = 1.0, Y_var=None, fused: Optional[bool] = None
+            ) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
         """autoreg/inference/svi_vardtc.py:70-215 plus the KL scaling of layers.py:75-79.
-        ``Y_var`` [N, D]: uncertain outputs (:56-59, :190-193)."""
+        ``Y_var`` [N, D]: uncertain outputs (:56-59, :190-193).
+
+        In this bound the upstream gradients dL_dpsi1 (:167) and dL_dpsi2 (:169) depend on q(U) and
+        K(Z,Z) only, not on the statistics, so they are formed FIRST and the statistics and their
+        gradients come out of ONE pass over the rows (``DevicePsi.fused``, ``rgp_psi_fused_dev``):
+        the separate Psi2 forward pass - a quarter of a two-phase evaluation - is not run.
+        ``fused=False`` forces the two-phase order of the reference."""
         N, D = Y.shape
         M = Z.shape[0]
         beta = 1.0 / float(noise_variance)                                    # :80
-        _, psi1, psi2 = self.psi.forward(mu, S, Z, ell, variance)
+        if fused is None:
+            fused = hasattr(self.psi, "fused")
+        eye = torch.eye(M, dtype=Z.dtype, device=Z.device)
+        Lm = self._chol(rbf_K(variance, ell, Z) + eye * CONST_JITTER)            # :88-93
+        Ls = self._chol(qU_var)                                                  # :96
+        LinvLs = dtrtrs(Lm, Ls)
+        Linvmu = dtrtrs(Lm, qU_mean)
+        B = tdot(LinvLs) * D + tdot(Linvmu)                                   # :112
+        KuuInvmu = dtrtrs(Lm, Linvmu, trans=1)
+        dL_dpsi0 = -D * beta / 2.0                                            # :162
+        dL_dpsi1 = (Y @ KuuInvmu.mT) * beta                                   # :167
+        dL_dpsi2 = beta * backsub_both_sides(Lm, D * eye - B, "left") / 2.0   # :169
+        if fused:
+            (psi1, psi2), (dvar, dl, dZ, dmu, dS) = self.psi.fused(mu, S, Z, ell, variance, dL_dpsi0, dL_dpsi1,
+                                                                   dL_dpsi2)
+            pgrads = (dvar, dl, dZ, dmu, dS)
+        else:
+            _, psi1, psi2 = self.psi.forward(mu, S, Z, ell, variance)
+            pgrads = None
         psi1Y = (Y.mT @ psi1) * beta
         YRY = Y.square().sum() * beta
         if Y_var is not None:
@@ -215,14 +240,8 @@ class DeviceBound:
         N, psi2, psi1Y, YRY = self._gather_stats(N, psi2, psi1Y, YRY)         # :65-67 (allReduceArrays)
         psi0b = variance * N * beta
         psi2b = psi2 * beta
-        eye = torch.eye(M, dtype=Z.dtype, device=Z.device)
-        Lm = self._chol(rbf_K(variance, ell, Z) + eye * CONST_JITTER)            # :88-93
-        Ls = self._chol(qU_var)                                                  # :96
-        LinvLs = dtrtrs(Lm, Ls)
-        Linvmu = dtrtrs(Lm, qU_mean)
         psi1YLinvT = dtrtrs(Lm, psi1Y.mT).mT                                  # :99
         A = backsub_both_sides(Lm, psi2b, "right")                            # :108
-        B = tdot(LinvLs) * D + tdot(Linvmu)                                   # :112
         logL_R = -N * math.log(beta)
         core = -D * psi0b / 2.0 - YRY / 2.0 - (B * A).sum() / 2.0 + torch.trace(A) * D / 2.0 \
             + (Linvmu * psi1YLinvT.mT).sum()
@@ -233,12 +252,8 @@ class DeviceBound:
         dL_dKmm = (tmp1 + tmp1.mT) / 2.0 + tmp3                               # :133
         dL_dthetaL = -D * N * beta / 2.0 - core * beta                        # :139
         t1 = backsub_both_sides(Lm, -A, "left")                               # :145
-        KuuInvmu = dtrtrs(Lm, Linvmu, trans=1)
         dL_dqU_mean = t1 @ qU_mean + dtrtrs(Lm, psi1YLinvT.mT, trans=1)       # :146
         dL_dqU_var = D / 2.0 * t1                                             # :147
-        dL_dpsi0 = -D * beta / 2.0                                            # :162
-        dL_dpsi1 = (Y @ KuuInvmu.mT) * beta                                   # :167
-        dL_dpsi2 = beta * backsub_both_sides(Lm, D * eye - B, "left") / 2.0   # :169
         # KL(q(U) || p(U)), svi_vardtc.py:197-215, scaled by qU_ratio (layers.py:76-79)
         Linv = dtrtrs(Lm, eye)
         KuuInv = Linv.mT @ Linv
@@ -257,11 +272,12 @@ class DeviceBound:
             extra["dL_dYmean"] = (psi1 @ KuuInvmu) * beta - Y * beta
             extra["dL_dYvar"] = torch.full_like(Y, beta / -2.0)               # :193  [N, D]
         return logL, self._finish(variance, ell, Z, mu, S, dL_dpsi0, dL_dpsi1, dL_dpsi2,
-                                  dL_dKmm - dKL_dKuu * qU_ratio, extra)
+                                  dL_dKmm - dKL_dKuu * qU_ratio, extra, pgrads)
 
     # ------------------------------------------------------------ shared tail
-    def _finish(self, variance, ell, Z, mu, S, dL_dpsi0, dL_dpsi1, dL_dpsi2, dL_dKmm, extra):
-        dvar, dl, dZ, dmu, dS = self.psi.backward(mu, S, Z, ell, variance, dL_dpsi0, dL_dpsi1, dL_dpsi2)
+    def _finish(self, variance, ell, Z, mu, S, dL_dpsi0, dL_dpsi1, dL_dpsi2, dL_dKmm, extra, pgrads=None):
+        dvar, dl, dZ, dmu, dS = pgrads if pgrads is not None else \
+            self.psi.backward(mu, S, Z, ell, variance, dL_dpsi0, dL_dpsi1, dL_dpsi2)
         dvar, dl, dZ = self.allsum([dvar, dl, dZ])                            # exchange C2
         kvar, kl, kZ = rbf_K_grads(dL_dKmm, variance, ell, Z)
         out = {"variance": dvar.reshape(()) + kvar, "lengthscale": dl + kl, "Z": dZ + kZ, "mu": dmu, "S": dS,

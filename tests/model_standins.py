@@ -25,6 +25,14 @@ class OraclePsi:
         return (torch.tensor([out[0]]),) + tuple(t(a) for a in out[1:])
 
 
+class OraclePsiFused(OraclePsi):
+    """Adds the one-pass entry point of DevicePsi (oracle arithmetic: simply both phases)."""
+
+    def fused(self, mu, S, Z, ell, variance, dL0, dL1, dL2, want_psi1=True):
+        _, p1, p2 = self.forward(mu, S, Z, ell, variance)
+        return (p1, p2), self.backward(mu, S, Z, ell, variance, dL0, dL1, dL2)
+
+
 class OracleLag:
     """LagWindow stand-in on stacked CPU tensors."""
 

@@ -374,3 +374,38 @@ def test_random_small_shapes_match_oracle(plugins):
             _compare(fwd, bwd, psi_forward(var, ell, Z, mu, S), psi_backward(dL0, dL1, dL2, var, ell, Z, mu, S), TIGHT)
         except AssertionError as e:
             raise AssertionError("shape N=%d M=%d Q=%d: %s" % (N, M, Q, e))
+
+
+@pytest.mark.parametrize("impl", [0, 1])      # 0 = auto (fused kernel), 1 = reference kernels (two passes inside)
+@pytest.mark.parametrize("N,M,Q,chunk", [(257, 65, 17, 0), (502, 100, 20, 0), (640, 192, 64, 0), (192, 512, 64, 0),
+                                         (300, 70, 100, 0), (3000, 130, 33, 1000), (40000, 64, 64, 0)])
+def test_fused_pass_equals_forward_then_backward(impl, N, M, Q, chunk):
+    """rgp_psi_fused_dev: statistics and gradients from one pass (the backward kernel accumulates Psi2
+    on the side) against the oracle and against the two-phase calls; covers block groups (small N),
+    diagonal-only (M = 64), the two-pass Q > 64 case and row chunks."""
+    import torch
+    from rgp_b200.device import DevicePsi
+    if impl == 1 and N > 5000:
+        pytest.skip("reference kernels are slow at this size")
+    dp = DevicePsi(0, impl=impl)
+    if chunk:
+        dp.handle.set_option("row_chunk", chunk)
+    var, ell, Z, mu, S = make_inputs(N, M, Q, seed=N + M, n_control=min(3, Q - 1))
+    _, dL1, dL2 = make_upstream(N, M, seed=Q)
+    dL0 = np.random.default_rng(4).normal(size=N)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    (p1, p2), grads = dp.fused(t(mu), t(S), t(Z), t(ell), var, t(dL0), t(dL1), t(dL2))
+    if N <= 5000:
+        of = psi_forward(var, ell, Z, mu, S)
+        ob = psi_backward(dL0, dL1, dL2, var, ell, Z, mu, S)
+        assert relerr(p1.cpu().numpy(), of[1]) < TIGHT and relerr(p2.cpu().numpy(), of[2]) < TIGHT
+        for name, a, b in zip(["dvar", "dl", "dZ", "dmu", "dS"], grads, ob):
+            assert relerr(a.cpu().numpy(), b) < TIGHT, name
+    _, q1, q2 = dp.forward(t(mu), t(S), t(Z), t(ell), var)
+    two = dp.backward(t(mu), t(S), t(Z), t(ell), var, t(dL0), t(dL1), t(dL2))
+    assert relerr(p1.cpu().numpy(), q1.cpu().numpy()) < 1e-14
+    assert relerr(p2.cpu().numpy(), q2.cpu().numpy()) < 1e-13
+    for a, b in zip(grads, two):
+        assert relerr(a.cpu().numpy(), b.cpu().numpy()) < 1e-12
+    (n1, _), _ = dp.fused(t(mu), t(S), t(Z), t(ell), var, -0.5, None, t(dL2), want_psi1=False)
+    assert n1 is None

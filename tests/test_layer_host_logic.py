@@ -2,7 +2,7 @@
 output branches of rgp_b200/inference.py) with oracle-backed stand-ins for the CUDA pieces."""
 import pytest
 
-from model_standins import OracleLag, OraclePsi, compare_with_oracle, stack_model
+from model_standins import OracleLag, OraclePsi, OraclePsiFused, compare_with_oracle, stack_model
 from rgp_b200.inference import DeviceBound
 from rgp_b200.layer import DeviceDeepAutoreg
 from synth import make_deep_model, relerr
@@ -23,6 +23,20 @@ def test_deep_model_matches_oracle(svi, control, wins, nDims):
                               lag_factory=OracleLag)
     out = model.evaluate(params, Y, latents, controls)
     compare_with_oracle(m, out, relerr, tol=1e-10)
+
+
+def test_svi_fused_order_equals_two_phase_order():
+    """DeviceBound.svi forms the upstream gradients before the statistics when the psi object offers a
+    one-pass entry point; the result must not depend on that order."""
+    m = make_deep_model(svi=True, control=True)
+    Y, latents, controls, params = stack_model(m)
+    outs = []
+    for psi in (OraclePsi(), OraclePsiFused()):
+        model = DeviceDeepAutoreg(m["wins"], (2, 1, 2), [y.shape[0] for y in m["Ys"]], U_win=m["U_win"], ctl_dim=1,
+                                  svi=True, bound=DeviceBound(psi=psi), lag_factory=OracleLag)
+        outs.append(model.evaluate(params, Y, latents, controls))
+        compare_with_oracle(m, outs[-1], relerr, tol=1e-10)
+    assert abs(float(outs[0][0]) - float(outs[1][0])) <= 1e-13 * abs(float(outs[0][0]))
 
 
 def test_rejects_windowed_observed_layer():
