@@ -13,6 +13,8 @@ namespace rgp {
 namespace fast {
 
 static inline bool supported(int M, int Q) { return Q >= 1 && Q <= 128 && M >= 1; }
+// the fused pass keeps one more shared tile; at QC = 128 it does not fit next to the Z' tiles
+static inline bool fused_supported(int Q) { return Q <= 64; }
 static inline int qc_for(int Q) { return Q <= 16 ? 16 : (Q <= 32 ? 32 : (Q <= 64 ? 64 : 128)); }
 
 static int init(rgp_psi_ctx*) {
@@ -25,7 +27,6 @@ static int init(rgp_psi_ctx*) {
   RGP_CUDA(cudaFuncSetAttribute((k_psi2_bwd<16, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<16>::BWD_FUSED_SMEM));
   RGP_CUDA(cudaFuncSetAttribute((k_psi2_bwd<32, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<32>::BWD_FUSED_SMEM));
   RGP_CUDA(cudaFuncSetAttribute((k_psi2_bwd<64, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<64>::BWD_FUSED_SMEM));
-  RGP_CUDA(cudaFuncSetAttribute((k_psi2_bwd<128, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<128>::BWD_FUSED_SMEM));
   RGP_CUDA(cudaFuncSetAttribute(k_psi2_fwd<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<128>::FWD_SMEM));
   RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwd<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<128>::BWD_SMEM));
   RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwd16<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg16<32>::BWD_SMEM));
@@ -105,12 +106,11 @@ template <int QC>
 static int launch_bwd(rgp_psi_ctx* h, cudaStream_t st, const Shape& s, int64_t rows, int R, int G,
                       const double* Zt, const double* Ct, const double* w, const double* HP,
                       double* lam, double* Wq, double* ACCp, double* P2p) {
-  if (P2p) {   // fused forward + backward: the 8-warp kernel also accumulates the Psi2 partial tiles
+  if constexpr (QC == 128) {
+    if (P2p) return set_error(RGP_PSI_ERR_INVALID, "fused pass is not built for Q > 64");
+  } else if (P2p) {   // fused forward + backward: the 8-warp kernel also accumulates the Psi2 partial tiles
     RGP_LAUNCH(h, st, "psi2_bwd_fused", (k_psi2_bwd<QC, true>), dim3(R, G), P2_THREADS, P2Cfg<QC>::BWD_FUSED_SMEM,
                rows, s.Mp, s.nt, s.nblocks, s.qk, Zt, Ct, w, HP, lam, Wq, ACCp, 0, P2p);
-    for (int qoff = P2Cfg<QC>::QS; qoff < QC; qoff += P2Cfg<QC>::QS)
-      RGP_LAUNCH(h, st, "psi2_bwd", (k_psi2_bwd<QC>), dim3(R, G), P2_THREADS, P2Cfg<QC>::BWD_SMEM, rows, s.Mp,
-                 s.nt, s.nblocks, s.qk, Zt, Ct, w, HP, lam, Wq, ACCp, qoff, (double*)nullptr);
     return 0;
   }
   if constexpr (QC <= 64) {

@@ -299,9 +299,14 @@ int rgp_psi_fused_dev(rgp_psi_handle_t h, void* stream, int64_t N, int M, int Q,
   cudaStream_t st = (cudaStream_t)stream;
   if (h->impl == RGP_PSI_IMPL_FAST && !fast::supported(M, Q))
     return set_error(RGP_PSI_ERR_INVALID, "fast path does not support M=%d Q=%d", M, Q);
-  if (use_fast(h, M, Q))
+  if (use_fast(h, M, Q)) {
+    if (fast::fused_supported(Q))
+      return fast::backward(h, st, N, M, Q, mu, S, Z, ell, variance, dL_dpsi0, dL_dpsi0_const, dL_dpsi1, dL_dpsi2,
+                            dmu_out, dS_out, dZ_out, dell_out, dvar_out, psi1_out, psi2_out);
+    RGP_TRY(fast::forward(h, st, N, M, Q, mu, S, Z, ell, variance, nullptr, psi1_out, psi2_out));   // 64 < Q <= 128
     return fast::backward(h, st, N, M, Q, mu, S, Z, ell, variance, dL_dpsi0, dL_dpsi0_const, dL_dpsi1, dL_dpsi2,
-                          dmu_out, dS_out, dZ_out, dell_out, dvar_out, psi1_out, psi2_out);
+                          dmu_out, dS_out, dZ_out, dell_out, dvar_out);
+  }
   // reference kernels: two passes
   RGP_TRY(refdrv::forward(h, st, N, M, Q, mu, S, Z, ell, variance, nullptr, psi1_out, psi2_out));
   return refdrv::backward(h, st, N, M, Q, mu, S, Z, ell, variance, dL_dpsi0, dL_dpsi0_const, dL_dpsi1, dL_dpsi2,
