@@ -254,6 +254,34 @@ def ours(args):
     value = world * N * args.steps / (ms * 1e-3)
     checksum = float(p2.sum().item()) + float(out[2].sum().item())
 
+    # Informational, not the headline: the same rows through the FUSED entry point (statistics and
+    # gradients from one pass; valid when the upstream gradients do not depend on the statistics, i.e.
+    # the SVI bound - DESIGN.md section 9).  One warm pass, one timed pass, max over ranks.
+    fused = None
+    if not args.no_fused:
+        def fstep():
+            (q1, q2), fo = sp.psi.fused(mu, S, Z, ell, variance, -0.5, dL1, dL2, psi1_out=psi1, dmu_out=dmu, dS_out=dS)
+            if world > 1:
+                from rgp_b200.sharded import reduce_forward, reduce_backward
+                _, q2, _ = reduce_forward(torch.full((1,), variance * N, **f64), q2)
+                fo = reduce_backward(fo[0], fo[1], fo[2]) + fo[3:]
+            return q2, fo
+        q2, fo = fstep()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        q2, fo = fstep()
+        f1.record()
+        barrier()
+        tf = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+        fms = float(tf.item())
+        fused = {"value": world * N / (fms * 1e-3), "unit": UNIT, "ms_per_step": fms,
+                 "max_rel_diff_psi2_vs_two_phase": float((q2 - p2).abs().max() / p2.abs().max()),
+                 "max_rel_diff_dZ_vs_two_phase": float((fo[2] - out[2]).abs().max() / out[2].abs().max()),
+                 "note": "rgp_psi_fused_dev: one pass for statistics + gradients (SVI bound); not the headline metric"}
+
     # dominant kernel -> roofline (fp64 CUDA-core pipe; see DESIGN.md "Measurement")
     roof = None
     if ktimes:
@@ -353,7 +381,7 @@ def ours(args):
                              % ((2 * N * Q + 2 * N * M) * 8 / 1e9),
                        "kernels": {0: "auto", 1: "fast", 2: "reference"}[args.kernels]},
             "roofline": roof, "whole_step": whole, "kernel_ms": kshare,
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "cpu_baseline": cpu, "e2e": e2e, "fused_svi_pass": fused, "gpu_launches": launches, "clocks": clocks,
             "checksum": checksum,
         }
         print(json.dumps(line), flush=True)
@@ -375,6 +403,7 @@ def main():
     ap.add_argument("--e2e-rows", type=int, default=2 ** 20)
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-fused", action="store_true", help="skip the informational fused-pass measurement")
     args = ap.parse_args()
     if args.warmup < 3:
         print("warning: contract asks for >= 3 warm-up steps", file=sys.stderr)

@@ -84,7 +84,8 @@ class DevicePsi:
                                  dell.data_ptr(), dvar.data_ptr())
         return dvar, dell, dZ, dmu, dS
 
-    def fused(self, mu, S, Z, ell, variance: float, dL_dpsi0, dL_dpsi1, dL_dpsi2, want_psi1: bool = True):
+    def fused(self, mu, S, Z, ell, variance: float, dL_dpsi0, dL_dpsi1, dL_dpsi2, want_psi1: bool = True,
+              psi1_out=None, dmu_out=None, dS_out=None):
         """Statistics and gradients from one pass (``rgp_psi_fused_dev``): for upstream gradients
         that do not depend on the statistics of this evaluation (the SVI bound).  Returns
         ((psi1 | None, psi2), (dvar, dell, dZ, dmu, dS))."""
@@ -101,9 +102,13 @@ class DevicePsi:
         else:
             p0, c0 = None, float(dL_dpsi0)
         f64 = dict(dtype=torch.float64, device=dev)
-        psi1 = torch.empty((N, M), **f64) if want_psi1 else None
+        psi1 = (psi1_out if psi1_out is not None else torch.empty((N, M), **f64)) if want_psi1 else None
+        if psi1 is not None:
+            _check(psi1, "psi1_out", (N, M))
         psi2 = torch.empty((M, M), **f64)
-        dmu, dS = torch.empty((N, Q), **f64), torch.empty((N, Q), **f64)
+        dmu = dmu_out if dmu_out is not None else torch.empty((N, Q), **f64)
+        dS = dS_out if dS_out is not None else torch.empty((N, Q), **f64)
+        _check(dmu, "dmu_out", (N, Q)); _check(dS, "dS_out", (N, Q))
         dZ, dell, dvar = torch.empty((M, Q), **f64), torch.empty(Q, **f64), torch.empty(1, **f64)
         self.handle.fused_dev(self._stream(), N, M, Q, mu.data_ptr(), S.data_ptr(), Z.data_ptr(), ell.data_ptr(),
                               variance, p0, c0, dL_dpsi1.data_ptr() if dL_dpsi1 is not None else None,
