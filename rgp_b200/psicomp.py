@@ -133,6 +133,8 @@ class PSICOMP_RBF_B200(object):
                 return tuple(a.copy() for a in self._fwd_val)
         N, Q = mu.shape
         M = Z.shape[0]
+        if N == 0:      # no rows: sums over the empty set (what GPy's numpy code returns); nothing to launch
+            return np.empty(0), np.empty((0, M)), np.zeros((M, M))
         psi0 = np.empty(N)
         psi1 = np.empty((N, M))
         psi2 = np.empty((M, M))
@@ -163,6 +165,8 @@ class PSICOMP_RBF_B200(object):
         if dL1.shape != (N, M) or dL2.shape != (M, M):
             raise ValueError("dL_dpsi1 %s / dL_dpsi2 %s do not match N=%d M=%d"
                              % (dL1.shape, dL2.shape, N, M))
+        if N == 0:
+            return 0.0, np.zeros(Q if ard else 1), np.zeros((M, Q)), np.empty((0, Q)), np.empty((0, Q))
         key = None
         if self.cache:
             key = (var,) + _fingerprint(ell, Z, mu, S, dL0, dL1, dL2)

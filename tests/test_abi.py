@@ -102,3 +102,28 @@ def test_inv_lengthscale_chain_rule_matches_reference_kernels():
     kern = RBF(2, ARD=True, inv_l=True, lengthscale=[2.0, 0.5])
     np.testing.assert_allclose(kern.lengthscale, [2.0, 0.5])
     np.testing.assert_allclose(kern.inv_l, [0.25, 4.0])
+
+
+def test_plugin_handles_zero_rows_without_a_device():
+    """Empty q(X) (N = 0): the sums over rows are empty - zeros of the right shapes, as GPy's numpy code
+    returns - and no kernel is launched (so this runs without a GPU)."""
+    import numpy as np
+    from oracle.psi_oracle import psi_backward, psi_forward
+    from rgp_b200.gpy_compat import RBF, NormalPosterior
+    from rgp_b200.psicomp import PSICOMP_RBF_B200
+    M, Q = 5, 3
+    Z = np.random.default_rng(0).normal(size=(M, Q))
+    ell = np.array([1.0, 2.0, 0.5])
+    pc = PSICOMP_RBF_B200(cache=False)
+    kern = RBF(Q, 1.3, ell, ARD=True, psicomp=pc)
+    X = NormalPosterior(np.empty((0, Q)), np.empty((0, Q)))
+    p0, p1, p2 = pc.psicomputations(kern, Z, X)
+    o0, o1, o2 = psi_forward(1.3, ell, Z, X.mean, X.variance)
+    assert p0.shape == o0.shape == (0,) and p1.shape == o1.shape == (0, M)
+    np.testing.assert_array_equal(p2, o2)
+    out = pc.psiDerivativecomputations(kern, np.empty(0), np.empty((0, M)), np.ones((M, M)), Z, X)
+    ref = psi_backward(np.empty(0), np.empty((0, M)), np.ones((M, M)), 1.3, ell, Z, X.mean, X.variance)
+    assert out[0] == 0.0 and float(ref[0]) == 0.0
+    for a, b in zip(out[1:], ref[1:]):
+        assert np.shape(a) == np.shape(b)
+        np.testing.assert_allclose(a, b, atol=0)

@@ -353,10 +353,43 @@ def test_options_are_validated():
     from rgp_b200._lib import Handle
     h = Handle(0)
     h._ensure()
-    for key, val in (("impl", 7), ("bwd_warps", 12), ("row_chunk", -1), ("no_such_option", 1)):
+    for key, val in (("impl", 7), ("bwd_warps", 12), ("row_chunk", -1), ("no_such_option", 1), ("bwd_strip", 2),
+                     ("bwd_mbar", -1)):
         with pytest.raises(PsiError):
             h.set_option(key, val)
         assert key not in h._options
+
+
+def test_bad_arguments_return_status_and_message_not_a_crash():
+    """C-ABI error convention: int status + thread-local message, never abort."""
+    import torch
+    from rgp_b200 import PsiError
+    from rgp_b200._lib import Handle
+    h = Handle(0)
+    f64 = dict(dtype=torch.float64, device="cuda")
+    x = torch.ones((8, 4), **f64)
+    z = torch.ones((3, 4), **f64)
+    e = torch.ones(4, **f64)
+    o = torch.empty((8, 3), **f64)
+    with pytest.raises(PsiError, match="null"):       # fused: psi2_out missing
+        h.fused_dev(0, 8, 3, 4, x.data_ptr(), x.data_ptr(), z.data_ptr(), e.data_ptr(), 1.0, None, 0.0, None,
+                    torch.ones((3, 3), **f64).data_ptr(), None, None, x.data_ptr(), x.data_ptr(), z.data_ptr(),
+                    e.data_ptr(), e.data_ptr())
+    with pytest.raises(PsiError):                     # non-positive variance
+        h.forward_dev(0, 8, 3, 4, x.data_ptr(), x.data_ptr(), z.data_ptr(), e.data_ptr(), -1.0, None, o.data_ptr(),
+                      torch.empty((3, 3), **f64).data_ptr())
+    desc = torch.tensor([[0, 6, 0, 8, 0, 0]], dtype=torch.int64, device="cuda")
+    with pytest.raises(PsiError, match="dyvar_cols"):
+        h.latent_terms(0, 1, desc.data_ptr(), 2, 4, x.data_ptr(), x.data_ptr(), 8, x.data_ptr(), x.data_ptr(), 3,
+                       x.data_ptr(), x.data_ptr(), e.data_ptr())
+    with pytest.raises(PsiError):                     # empty window
+        h.lag_gather(0, 1, desc.data_ptr(), 6, 0, 0, 0, 0, None, None, o.data_ptr())
+    # the handle is still usable afterwards
+    p2 = torch.empty((3, 3), **f64)
+    h.forward_dev(0, 8, 3, 4, x.data_ptr(), x.data_ptr(), z.data_ptr(), e.data_ptr(), 1.0, None, o.data_ptr(),
+                  p2.data_ptr())
+    torch.cuda.synchronize()
+    assert torch.isfinite(p2).all()
 
 
 def test_random_small_shapes_match_oracle(plugins):
