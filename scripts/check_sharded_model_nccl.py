@@ -13,10 +13,9 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from model_standins import stack_model  # noqa: E402
 from rgp_b200.inference import DeviceBound  # noqa: E402
 from rgp_b200.layer import DeviceDeepAutoreg  # noqa: E402
-from synth import make_deep_model  # noqa: E402
+from synth import make_deep_model, stack_model  # noqa: E402
 
 
 def rel(a, b):

@@ -7,6 +7,7 @@ import torch
 from oracle import bound_oracle as bo
 from oracle.lag_oracle import build_rows, scatter_rows_into
 from oracle.psi_oracle import psi_backward, psi_forward
+from synth import stack_model  # noqa: F401  (re-exported)
 
 
 def t(a):
@@ -84,19 +85,6 @@ class OracleLag:
             gv[off + self.X_win:off + T] += b
             off, yoff = off + T, yoff + N
         return t(gm), t(gv), torch.tensor(delta, dtype=torch.float64)
-
-
-def stack_model(m, to=lambda a: t(a)):
-    """Stacked tensors of a tests/synth.make_deep_model instance."""
-    Y = to(np.vstack(m["Ys"]))
-    latents = [(to(np.vstack([s[0] for s in lvl])), to(np.vstack([s[1] for s in lvl]))) for lvl in m["latents"]]
-    controls = None
-    if m["Us"] is not None:
-        controls = (to(np.vstack([u[0] for u in m["Us"]])), to(np.vstack([u[1] for u in m["Us"]])))
-    params = []
-    for p in m["params"]:
-        params.append({k: (to(np.asarray(v)) if isinstance(v, np.ndarray) else v) for k, v in p.items()})
-    return Y, latents, controls, params
 
 
 def compare_with_oracle(m, out, relerr, tol=1e-10, to_np=lambda a: a.numpy()):

@@ -74,3 +74,19 @@ def load_actuator_config1(path=None):
     m = dict(wins=[0, 10], Ys=[g["Y"].copy()], Us=[(g["U"].copy(), np.full(g["U"].shape, 1e-10))], U_win=10,
              latents=[[(g["lat_mean"].copy(), g["lat_var"].copy())]], params=params, svi=False)
     return m, g
+
+
+def stack_model(m, to=None):
+    """Stacked tensors of a make_deep_model instance (``to``: ndarray -> tensor; default CPU torch)."""
+    if to is None:
+        import torch
+        to = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    Y = to(np.vstack(m["Ys"]))
+    latents = [(to(np.vstack([s[0] for s in lvl])), to(np.vstack([s[1] for s in lvl]))) for lvl in m["latents"]]
+    controls = None
+    if m["Us"] is not None:
+        controls = (to(np.vstack([u[0] for u in m["Us"]])), to(np.vstack([u[1] for u in m["Us"]])))
+    params = []
+    for p in m["params"]:
+        params.append({k: (to(np.asarray(v)) if isinstance(v, np.ndarray) else v) for k, v in p.items()})
+    return Y, latents, controls, params

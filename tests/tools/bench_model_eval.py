@@ -1,4 +1,5 @@
-"""Latency of ONE whole objective evaluation (bound + every gradient) of the deep
+"""(Lives under tests/: it times the CPU oracle beside the device path.)
+Latency of ONE whole objective evaluation (bound + every gradient) of the deep
 autoregressive model at the shapes of BASELINE.json configs 1-3, on the device
 (rgp_b200.layer.DeviceDeepAutoreg) with the CPU oracle timed beside it on the host cores.
 Synthetic data of the configs' shapes (the datasets are not needed for timing)."""
@@ -10,7 +11,7 @@ import time
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from model_standins import compare_with_oracle, stack_model  # noqa: E402
