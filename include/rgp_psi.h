@@ -155,6 +155,25 @@ int rgp_latent_terms_dev(rgp_psi_handle_t h, void* stream, int nseq, const int64
                          int64_t lat_total, const double* dL_dYmean, const double* dL_dYvar,
                          int dyvar_cols, double* lat_gmean, double* lat_gvar, double* value_out);
 
+/* MLP back-constraint of a hidden layer (autoreg/layers.py:623-715, network of autoreg/mlp.py): the
+ * first Xwin latent means of a sequence are free, every later one is the output of a tanh MLP on the
+ * window before it and the aligned control window.  One CTA per sequence, weights in shared memory.
+ *   units[0 .. nlayers] (HOST array): layer widths, units[0] = Xwin*Dx + Uwin*Du, units[nlayers] = Dx;
+ *   params (device): for each layer W[down][up] row-major then b[down]; tanh on hidden layers, linear last;
+ *   seq_desc as for the lag-window calls (row_start numbers the generated steps).
+ * freerun     reads lat_mean rows < Xwin of every sequence and WRITES the rest; hidden_acts [N, sum hidden
+ *             widths] keeps the activations for the backward call.
+ * freerun_bwd lat_gmean holds dL/d mean of every step on entry; the call adds the back-propagated part
+ *             (rows < Xwin end up as the initial-mean gradients), ADDS onto ctl_gmean (may be NULL) and
+ *             writes param_grads [nseq, nparams] (sum over the first axis for the total). */
+int rgp_mlp_freerun_dev(rgp_psi_handle_t h, void* stream, int nseq, const int64_t* seq_desc, int Xwin,
+                        int Dx, int Uwin, int Du, int nlayers, const int* units, const double* params,
+                        double* lat_mean, const double* ctl_mean, double* hidden_acts);
+int rgp_mlp_freerun_bwd_dev(rgp_psi_handle_t h, void* stream, int nseq, const int64_t* seq_desc, int Xwin,
+                            int Dx, int Uwin, int Du, int nlayers, const int* units, const double* params,
+                            const double* lat_mean, const double* ctl_mean, const double* hidden_acts,
+                            double* lat_gmean, double* ctl_gmean, double* param_grads);
+
 /* ---- measurement support ------------------------------------------------------- */
 /* Kernel launches issued through this handle since creation (or the last reset). */
 int64_t rgp_psi_launch_count(rgp_psi_handle_t h);

@@ -47,6 +47,11 @@ SIGNATURES = {
     "rgp_latent_terms_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                        C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                        C.c_void_p, C.c_void_p]),
+    "rgp_mlp_freerun_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rgp_mlp_freerun_bwd_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                          C.c_int, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rgp_psi_launch_count": (C.c_int64, [C.c_void_p]),
     "rgp_psi_reset_counters": (C.c_int, [C.c_void_p]),
     "rgp_psi_kernel_times": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), c_double_p,
@@ -200,6 +205,17 @@ class Handle:
                      dyvar_cols, gmean, gvar, value_out) -> None:
         check(load().rgp_latent_terms_dev(self._ensure(), C.c_void_p(stream), nseq, seq_desc, Xwin, D, lat_mean,
                                           lat_var, lat_total, dYmean, dYvar, dyvar_cols, gmean, gvar, value_out))
+
+    def mlp_freerun(self, stream, nseq, seq_desc, Xwin, Dx, Uwin, Du, units, params, lat, ctl, acts) -> None:
+        u = (C.c_int * len(units))(*units)
+        check(load().rgp_mlp_freerun_dev(self._ensure(), C.c_void_p(stream), nseq, seq_desc, Xwin, Dx, Uwin, Du,
+                                         len(units) - 1, u, params, lat, ctl, acts))
+
+    def mlp_freerun_bwd(self, stream, nseq, seq_desc, Xwin, Dx, Uwin, Du, units, params, lat, ctl, acts,
+                        lat_g, ctl_g, pgrad) -> None:
+        u = (C.c_int * len(units))(*units)
+        check(load().rgp_mlp_freerun_bwd_dev(self._ensure(), C.c_void_p(stream), nseq, seq_desc, Xwin, Dx, Uwin, Du,
+                                             len(units) - 1, u, params, lat, ctl, acts, lat_g, ctl_g, pgrad))
 
     def forward_host(self, N, M, Q, mu, S, Z, ell, variance, psi0, psi1, psi2) -> None:
         check(load().rgp_psi_forward_host(self._ensure(), N, M, Q, mu, S, Z, ell, float(variance),

@@ -11,6 +11,7 @@
 #include "fast_path.cuh"
 #include "fp64_peak.cuh"
 #include "lag_kernels.cuh"
+#include "mlp_kernels.cuh"
 
 namespace rgp {
 
@@ -520,6 +521,53 @@ int rgp_latent_terms_dev(rgp_psi_handle_t h, void* stream, int nseq, const int64
   RGP_LAUNCH(h, st, "latent_terms", lag::k_latent_terms, blocks, 256, 0, nseq, seq_desc, Xwin, D, lat_mean,
              lat_var, dL_dYmean, dL_dYvar, dyvar_cols, lat_total, lat_gmean, lat_gvar, partial);
   RGP_LAUNCH(h, st, "latent_terms_sum", lag::k_sum_partials, 1, 256, 0, blocks, partial, value_out);
+  return 0;
+}
+
+static int mlp_common(rgp_psi_handle_t h, int nseq, const int64_t* seq_desc, int Xwin, int Dx, int Uwin, int Du,
+                      int nlayers, const int* units, mlp::Shape* sh) {
+  if (!h) return set_error(RGP_PSI_ERR_INVALID, "null handle");
+  if (nseq <= 0 || !seq_desc || Xwin <= 0 || Dx <= 0 || Uwin < 0 || Du < 0 || !units)
+    return set_error(RGP_PSI_ERR_INVALID, "bad MLP free-run arguments");
+  if (!mlp::make_shape(nlayers, units, sh))
+    return set_error(RGP_PSI_ERR_INVALID, "MLP needs 1..%d layers with positive widths", mlp::MAXL);
+  if (sh->u[0] != Xwin * Dx + Uwin * Du || sh->u[nlayers] != Dx)
+    return set_error(RGP_PSI_ERR_INVALID, "MLP widths [%d ... %d] do not match the window (%d inputs, %d outputs)",
+                     sh->u[0], sh->u[nlayers], Xwin * Dx + Uwin * Du, Dx);
+  if (mlp::bwd_smem(*sh) > 200 * 1024)
+    return set_error(RGP_PSI_ERR_INVALID, "MLP with %d parameters does not fit in shared memory", sh->nparams);
+  return 0;
+}
+
+int rgp_mlp_freerun_dev(rgp_psi_handle_t h, void* stream, int nseq, const int64_t* seq_desc, int Xwin, int Dx,
+                        int Uwin, int Du, int nlayers, const int* units, const double* params, double* lat_mean,
+                        const double* ctl_mean, double* hidden_acts) {
+  mlp::Shape sh;
+  RGP_TRY(mlp_common(h, nseq, seq_desc, Xwin, Dx, Uwin, Du, nlayers, units, &sh));
+  if (!params || !lat_mean || (Uwin > 0 && !ctl_mean) || (sh.nhid > 0 && !hidden_acts))
+    return set_error(RGP_PSI_ERR_INVALID, "null MLP free-run pointer");
+  RGP_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  RGP_CUDA(cudaFuncSetAttribute(mlp::k_freerun, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mlp::fwd_smem(sh)));
+  RGP_LAUNCH(h, st, "mlp_freerun", mlp::k_freerun, nseq, mlp::THREADS, mlp::fwd_smem(sh), sh, seq_desc, Xwin, Dx, Uwin,
+             Du, params, lat_mean, ctl_mean, hidden_acts);
+  return 0;
+}
+
+int rgp_mlp_freerun_bwd_dev(rgp_psi_handle_t h, void* stream, int nseq, const int64_t* seq_desc, int Xwin, int Dx,
+                            int Uwin, int Du, int nlayers, const int* units, const double* params,
+                            const double* lat_mean, const double* ctl_mean, const double* hidden_acts,
+                            double* lat_gmean, double* ctl_gmean, double* param_grads) {
+  mlp::Shape sh;
+  RGP_TRY(mlp_common(h, nseq, seq_desc, Xwin, Dx, Uwin, Du, nlayers, units, &sh));
+  if (!params || !lat_mean || (Uwin > 0 && !ctl_mean) || (sh.nhid > 0 && !hidden_acts) || !lat_gmean || !param_grads)
+    return set_error(RGP_PSI_ERR_INVALID, "null MLP back-propagation pointer");
+  RGP_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  RGP_CUDA(cudaFuncSetAttribute(mlp::k_freerun_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)mlp::bwd_smem(sh)));
+  RGP_LAUNCH(h, st, "mlp_freerun_bwd", mlp::k_freerun_bwd, nseq, mlp::THREADS, mlp::bwd_smem(sh), sh, seq_desc, Xwin,
+             Dx, Uwin, Du, params, lat_mean, ctl_mean, hidden_acts, lat_gmean, ctl_gmean, param_grads);
   return 0;
 }
 

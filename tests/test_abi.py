@@ -21,7 +21,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared_symbols():
     text = open(os.path.join(ROOT, "include", "rgp_psi.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(rgp_(?:psi|lag|latent)_[a-z0-9_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(rgp_(?:psi|lag|latent|mlp)_[a-z0-9_]+)\s*\(", text)))
 
 
 def test_library_builds_loads_and_exports_every_declared_symbol():

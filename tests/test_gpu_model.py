@@ -178,3 +178,81 @@ def test_sharded_model_nccl_matches_single_gpu():
            os.path.join(root, "scripts", "check_sharded_model_nccl.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+@pytest.mark.parametrize("control,units", [(True, None), (False, None), (True, [7]), (True, [16, 9, 5])])
+def test_mlp_back_constraint_freerun_and_backprop(control, units):
+    """rgp_mlp_freerun_dev / _bwd_dev through MLPBackConstraint + autograd against oracle/mlp_oracle.py."""
+    from oracle import mlp_oracle as mo
+    from rgp_b200._lib import Handle
+    from rgp_b200.backconstraint import MLPBackConstraint
+    from rgp_b200.lagwindow import LagWindow
+    from test_mlp_oracle import make_case
+    X_win, X_dim, U_win, U_dim, n_steps = 3, 2, 2, 1, (40, 25, 33)
+    Q = X_win * X_dim + (U_win * U_dim if control else 0)
+    c = make_case(seed=3, X_win=X_win, X_dim=X_dim, U_win=U_win, U_dim=U_dim, n_steps=n_steps, control=control,
+                  units=None if units is None else [Q] + units + [X_dim])
+    lw = LagWindow(Handle(0), [X_win + N for N in n_steps], X_win, X_dim,
+                   [u.shape[0] for u in c["ctl"]] if control else None, U_win, U_dim)
+    enc = MLPBackConstraint(lw, MLP_dims=units)
+    assert enc.units == [W.shape[1] for W, _ in c["params"]] + [X_dim]
+    with torch.no_grad():
+        enc.flat.copy_(_cuda(np.concatenate([np.concatenate([W.ravel(), b]) for W, b in c["params"]])))
+    init = _cuda(np.stack(c["init"])).requires_grad_(True)
+    ctl = _cuda(np.vstack(c["ctl"])).requires_grad_(True) if control else None
+    lat = enc(init, ctl)
+    X = mo.freerun(c["params"], c["init"], c["ctl"], c["n_steps"], X_win, U_win)
+    assert relerr(lat.detach().cpu().numpy(), np.vstack(X)) < 1e-12
+    w = np.vstack(c["weights"])
+    (lat * _cuda(w)).sum().backward()
+    g = [x.copy() for x in c["weights"]]
+    pg, cg = mo.freerun_backward(c["params"], X, c["ctl"], g, X_win, U_win)
+    assert relerr(enc.flat.grad.cpu().numpy(), np.concatenate([np.concatenate([dW.ravel(), db]) for dW, db in pg])) < 1e-11
+    assert relerr(init.grad.cpu().numpy(), np.stack([x[:X_win] for x in g])) < 1e-11
+    if control:
+        assert relerr(ctl.grad.cpu().numpy(), np.vstack(cg)) < 1e-11
+
+
+def test_back_constrained_model_end_to_end_on_device():
+    """DeepAutoreg_new(back_cstr=True) wiring: MLP back-constraints produce the latent means of both
+    hidden levels (the upper level's means are the control window of the lower level's encoder),
+    the device objective consumes them, and .backward() reaches the MLP weights and the initial
+    means.  Checked against the oracle chain (mlp_oracle + model_oracle)."""
+    from oracle import mlp_oracle as mo
+    from oracle.model_oracle import deep_autoreg_oracle
+    from rgp_b200.autograd import deep_autoreg_objective
+    from rgp_b200.backconstraint import MLPBackConstraint
+    from rgp_b200.layer import DeviceDeepAutoreg
+    wins, nDims, T, B, U_win = (0, 2, 3), (2, 1, 2), 30, 2, 2
+    m = make_deep_model(seed=11, wins=wins, nDims=nDims, seq_lens=(T,) * B, U_win=U_win, control=True, M=10)
+    Y, latents, controls, params = stack_model(m, to=_cuda)
+    model = DeviceDeepAutoreg(m["wins"], nDims, [T] * B, U_win=U_win, ctl_dim=1, device=0)
+    torch.manual_seed(0)
+    # level 2 (top): window on itself + the real controls; level 1: window on itself + level 2
+    enc2 = MLPBackConstraint(model.layers[2].lag)
+    enc1 = MLPBackConstraint(model.layers[1].lag)
+    init2 = torch.randn((B, wins[2], nDims[2]), dtype=torch.float64, device="cuda", requires_grad=True)
+    init1 = torch.randn((B, wins[1], nDims[1]), dtype=torch.float64, device="cuda", requires_grad=True)
+    mean2 = enc2(init2, controls[0])
+    mean1 = enc1(init1, mean2)
+    var1, var2 = latents[0][1], latents[1][1]
+    L = deep_autoreg_objective(model, params, Y, [(mean1, var1), (mean2, var2)], controls)
+    L.backward()
+    # ---- oracle chain
+    P2 = [(W.detach().cpu().numpy(), b.detach().cpu().numpy()) for W, b in enc2.layer_params()]
+    P1 = [(W.detach().cpu().numpy(), b.detach().cpu().numpy()) for W, b in enc1.layer_params()]
+    U = [u[0] for u in m["Us"]]
+    X2 = mo.freerun(P2, list(init2.detach().cpu().numpy()), U, [T] * B, wins[2], U_win)
+    X1 = mo.freerun(P1, list(init1.detach().cpu().numpy()), X2, [T] * B, wins[1], wins[2])
+    m["latents"] = [[(X1[s], m["latents"][0][s][1]) for s in range(B)], [(X2[s], m["latents"][1][s][1]) for s in range(B)]]
+    oL, _, olat, _ = deep_autoreg_oracle(m["wins"], m["Ys"], m["latents"], m["params"], Us=m["Us"], U_win=U_win)
+    assert abs(float(L) - oL) <= 1e-10 * abs(oL)
+    g1 = [olat[0][s][0].copy() for s in range(B)]
+    pg1, cg1 = mo.freerun_backward(P1, X1, X2, g1, wins[1], wins[2])
+    g2 = [olat[1][s][0] + cg1[s] for s in range(B)]                 # level 2 also feeds level 1's encoder
+    pg2, _ = mo.freerun_backward(P2, X2, U, g2, wins[2], U_win)
+    flat = lambda pg: np.concatenate([np.concatenate([dW.ravel(), db]) for dW, db in pg])
+    assert relerr(enc1.flat.grad.cpu().numpy(), flat(pg1)) < 1e-8
+    assert relerr(enc2.flat.grad.cpu().numpy(), flat(pg2)) < 1e-8
+    assert relerr(init1.grad.cpu().numpy(), np.stack([x[:wins[1]] for x in g1])) < 1e-8
+    assert relerr(init2.grad.cpu().numpy(), np.stack([x[:wins[2]] for x in g2])) < 1e-8
