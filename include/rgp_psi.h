@@ -163,9 +163,10 @@ int rgp_latent_terms_dev(rgp_psi_handle_t h, void* stream, int nseq, const int64
  *   seq_desc as for the lag-window calls (row_start numbers the generated steps).
  * freerun     reads lat_mean rows < Xwin of every sequence and WRITES the rest; hidden_acts [N, sum hidden
  *             widths] keeps the activations for the backward call.
- * freerun_bwd lat_gmean holds dL/d mean of every step on entry; the call adds the back-propagated part
- *             (rows < Xwin end up as the initial-mean gradients), ADDS onto ctl_gmean (may be NULL) and
- *             writes param_grads [nseq, nparams] (sum over the first axis for the total). */
+ * freerun_bwd lat_gmean holds dL/d mean of every step on entry; on exit its rows < Xwin of every sequence
+ *             hold the initial-mean gradients (objective part + back-propagated part), the other rows
+ *             are unchanged; the call ADDS onto ctl_gmean (may be NULL) and writes param_grads
+ *             [nseq, nparams] (sum over the first axis for the total). */
 int rgp_mlp_freerun_dev(rgp_psi_handle_t h, void* stream, int nseq, const int64_t* seq_desc, int Xwin,
                         int Dx, int Uwin, int Du, int nlayers, const int* units, const double* params,
                         double* lat_mean, const double* ctl_mean, double* hidden_acts);

@@ -49,9 +49,9 @@ inline bool make_shape(int nl, const int* units, Shape* s) {
   return true;
 }
 
-inline size_t fwd_smem(const Shape& s) { return sizeof(double) * ((size_t)s.nparams + 2 * s.maxu); }
-inline size_t bwd_smem(const Shape& s) {
-  return sizeof(double) * (2 * (size_t)s.nparams + s.u[0] + s.nhid + 2 * s.maxu);
+inline size_t fwd_smem(const Shape& s) { return sizeof(double) * ((size_t)s.nparams + 4 * s.maxu); }
+inline size_t bwd_smem(const Shape& s, int Xwin, int Dx) {
+  return sizeof(double) * (2 * (size_t)s.nparams + s.u[0] + s.nhid + 2 * s.maxu + (size_t)(Xwin + 1) * Dx);
 }
 
 // shared copy of the parameters with every W transposed (WT[i][j] = W[j][i]): thread j of a layer
@@ -67,54 +67,108 @@ __device__ __forceinline__ void load_params_T(const Shape& sh, const double* __r
   }
 }
 
-__device__ __forceinline__ void gather_input(int n, int Xwin, int Dx, int Uwin, int Du, int64_t lat0, int64_t ctl0,
-                                             const double* __restrict__ lat, const double* __restrict__ ctl,
-                                             double* in) {
-  const int Qx = Xwin * Dx, Q = Qx + Uwin * Du;
-  for (int i = threadIdx.x; i < Q; i += blockDim.x)
-    in[i] = i < Qx ? lat[(lat0 + n) * Dx + i] : ctl[(ctl0 + n) * Du + (i - Qx)];
+// out[j] = sum_i WT[i][j] * in[i] (+ bias[j]) for j < down, with the dot product of one output split
+// over P adjacent lanes (P = 4, 2 or 1, so that down * P fits the block when it can) and two
+// accumulators per lane: the dependent-FMA chain of a step is what bounds the recurrence, not the
+// flop count.  Every thread of the block must call it; no barrier inside.
+__device__ __forceinline__ int split_for(int down) { return down * 4 <= THREADS ? 4 : (down * 2 <= THREADS ? 2 : 1); }
+
+template <bool TRANSPOSED>
+__device__ __forceinline__ void matvec(const double* __restrict__ Wm, int rows, int cols, const double* __restrict__ bias,
+                                       const double* __restrict__ in, double* __restrict__ out) {
+  // TRANSPOSED = false: out[j] = bias[j] + sum_i Wm[i * rows + j] * in[i]   (j < rows outputs, i < cols inputs)
+  // TRANSPOSED = true : out[i] = sum_j Wm[i * cols + j] * in[j]             (i < rows outputs, j < cols inputs)
+  const int P = split_for(rows);
+  const int per = THREADS / P;
+  const int part = threadIdx.x % P;
+  for (int o = threadIdx.x / P; o < rows + (per - rows % per) % per; o += per) {
+    double a0 = 0.0, a1 = 0.0;
+    if (o < rows) {
+      if (!TRANSPOSED) {
+        int i = part;
+        for (; i + P < cols; i += 2 * P) {
+          a0 = fma(Wm[i * rows + o], in[i], a0);
+          a1 = fma(Wm[(i + P) * rows + o], in[i + P], a1);
+        }
+        if (i < cols) a0 = fma(Wm[i * rows + o], in[i], a0);
+      } else {
+        int j = part;
+        for (; j + P < cols; j += 2 * P) {
+          a0 = fma(Wm[o * cols + j], in[j], a0);
+          a1 = fma(Wm[o * cols + j + P], in[j + P], a1);
+        }
+        if (j < cols) a0 = fma(Wm[o * cols + j], in[j], a0);
+      }
+    }
+    double a = a0 + a1;
+    if (P >= 2) a += __shfl_xor_sync(0xffffffffu, a, 1);
+    if (P >= 4) a += __shfl_xor_sync(0xffffffffu, a, 2);
+    if (o < rows && part == 0) out[o] = bias ? a + bias[o] : a;
+  }
 }
 
+// grid = sequences.  The input vector of a step lives in shared memory: [Xwin latent means | Uwin
+// controls]; after a step the window shifts by one latent step and takes the new mean, so the
+// recurrence never waits for a global round trip.  The control part of the next step is fetched
+// while the layers of the current one run.
 __global__ void __launch_bounds__(THREADS)
 k_freerun(Shape sh, const int64_t* __restrict__ seq, int Xwin, int Dx, int Uwin, int Du,
           const double* __restrict__ params, double* __restrict__ lat, const double* __restrict__ ctl,
           double* __restrict__ acts) {
   extern __shared__ __align__(16) double smem[];
   double* sP = smem;
-  double* bufA = sP + sh.nparams;
+  double* win0 = sP + sh.nparams;                 // two input vectors (ping-pong), each maxu long
+  double* win1 = win0 + sh.maxu;
+  double* bufA = win1 + sh.maxu;
   double* bufB = bufA + sh.maxu;
   const int s = blockIdx.x;
+  const int Qx = Xwin * Dx, Qu = Uwin * Du;
   const int64_t row0 = seq[s * lag::DESC + 0], N = seq[s * lag::DESC + 1];
   const int64_t lat0 = seq[s * lag::DESC + 2], ctl0 = seq[s * lag::DESC + 4];
   load_params_T(sh, params, sP);
+  for (int i = threadIdx.x; i < Qx + Qu; i += blockDim.x)
+    win0[i] = i < Qx ? lat[lat0 * Dx + i] : ctl[ctl0 * Du + (i - Qx)];
   __syncthreads();
   for (int64_t n = 0; n < N; ++n) {
-    double* in = bufA;
-    double* out = bufB;
-    gather_input((int)n, Xwin, Dx, Uwin, Du, lat0, ctl0, lat, ctl, in);
-    __syncthreads();
+    double* in = (n & 1) ? win1 : win0;
+    double* nxt = (n & 1) ? win0 : win1;
+    double cnext = 0.0;                           // this thread's control input of the next step (Q <= THREADS, host-checked)
+    if ((int)threadIdx.x >= Qx && (int)threadIdx.x < Qx + Qu && n + 1 < N)
+      cnext = ctl[(ctl0 + n + 1) * Du + ((int)threadIdx.x - Qx)];
+    const double* x = in;
+    double* out = bufA;
     for (int l = 0; l < sh.nl; ++l) {
       const int up = sh.u[l], down = sh.u[l + 1], o = sh.woff[l];
-      const bool hidden = l < sh.nl - 1;
-      for (int j = threadIdx.x; j < down; j += blockDim.x) {
-        double a = sP[o + down * up + j];
-        for (int i = 0; i < up; ++i) a = fma(sP[o + i * down + j], in[i], a);
-        a = hidden ? tanh(a) : a;
-        out[j] = a;
-        if (hidden) acts[(row0 + n) * sh.nhid + sh.hoff[l] + j] = a;
-      }
+      matvec<false>(sP + o, down, up, sP + o + down * up, x, out);
       __syncthreads();
-      double* tmp = in;
-      in = out;
-      out = tmp;
+      if (l < sh.nl - 1) {
+        for (int j = threadIdx.x; j < down; j += blockDim.x) {
+          const double a = tanh(out[j]);
+          out[j] = a;
+          acts[(row0 + n) * sh.nhid + sh.hoff[l] + j] = a;
+        }
+        __syncthreads();
+      }
+      x = out;
+      out = (out == bufA) ? bufB : bufA;
     }
-    for (int j = threadIdx.x; j < Dx; j += blockDim.x) lat[(lat0 + Xwin + n) * Dx + j] = in[j];
-    __syncthreads();              // the new mean is an input of the next steps
+    // x = the new mean (Dx values): store it, shift the window, append the prefetched controls
+    for (int i = threadIdx.x; i < Qx + Qu; i += blockDim.x) {
+      double v;
+      if (i < Qx - Dx) v = in[i + Dx];
+      else if (i < Qx) v = x[i - (Qx - Dx)];
+      else v = cnext;
+      nxt[i] = v;
+    }
+    for (int j = threadIdx.x; j < Dx; j += blockDim.x) lat[(lat0 + Xwin + n) * Dx + j] = x[j];
+    __syncthreads();
   }
 }
 
-// lat_g: dL/d mean of every step on entry; each step adds its input gradient onto the Xwin rows it read
-// (newest step first), so on exit the first Xwin rows of a sequence are the initial-mean gradients.
+// lat_g: dL/d mean of every step on entry (read only for rows >= Xwin).  A shared ring holds the
+// back-propagated contributions to the Xwin + 1 newest-but-unfinished rows, so the step loop reads
+// nothing it wrote itself from global memory.  On exit rows < Xwin of lat_g hold the initial-mean
+// gradients (objective part + back-propagated part); other rows are unchanged.
 // pgrad[s][nparams]: parameter gradients of sequence s in the packed (untransposed) layout.
 __global__ void __launch_bounds__(THREADS)
 k_freerun_bwd(Shape sh, const int64_t* __restrict__ seq, int Xwin, int Dx, int Uwin, int Du,
@@ -122,22 +176,30 @@ k_freerun_bwd(Shape sh, const int64_t* __restrict__ seq, int Xwin, int Dx, int U
               const double* __restrict__ acts, double* __restrict__ lat_g, double* __restrict__ ctl_g,
               double* __restrict__ pgrad) {
   extern __shared__ __align__(16) double smem[];
-  double* sP = smem;
-  double* sG = sP + sh.nparams;
-  double* sAct = sG + sh.nparams;                 // [Q inputs | hidden outputs]
+  double* sP = smem;                              // transposed weights (WT[i][j]) + biases
+  double* sG = sP + sh.nparams;                   // gradients, packed untransposed layout
+  double* sAct = sG + sh.nparams;                 // [Q inputs | hidden outputs] of the step
   double* d0 = sAct + sh.u[0] + sh.nhid;
   double* d1 = d0 + sh.maxu;
+  double* ring = d1 + sh.maxu;                    // [(Xwin + 1) * Dx] pending contributions, row t at slot t % (Xwin + 1)
   const int s = blockIdx.x;
-  const int Qx = Xwin * Dx, Q = sh.u[0];
+  const int Qx = Xwin * Dx, Q = sh.u[0], RW = Xwin + 1;
   const int64_t row0 = seq[s * lag::DESC + 0], N = seq[s * lag::DESC + 1];
   const int64_t lat0 = seq[s * lag::DESC + 2], ctl0 = seq[s * lag::DESC + 4];
   load_params_T(sh, params, sP);
   for (int i = threadIdx.x; i < sh.nparams; i += blockDim.x) sG[i] = 0.0;
+  for (int i = threadIdx.x; i < RW * Dx; i += blockDim.x) ring[i] = 0.0;
   __syncthreads();
   for (int64_t n = N - 1; n >= 0; --n) {
-    gather_input((int)n, Xwin, Dx, Uwin, Du, lat0, ctl0, lat, ctl, sAct);
+    // inputs, activations and the objective gradient of this step: nothing here was written by this kernel
+    for (int i = threadIdx.x; i < Q; i += blockDim.x)
+      sAct[i] = i < Qx ? lat[(lat0 + n) * Dx + i] : ctl[(ctl0 + n) * Du + (i - Qx)];
     for (int i = threadIdx.x; i < sh.nhid; i += blockDim.x) sAct[Q + i] = acts[(row0 + n) * sh.nhid + i];
-    for (int j = threadIdx.x; j < Dx; j += blockDim.x) d0[j] = lat_g[(lat0 + Xwin + n) * Dx + j];
+    const int slot_out = (int)((Xwin + n) % RW);
+    for (int j = threadIdx.x; j < Dx; j += blockDim.x) {
+      d0[j] = lat_g[(lat0 + Xwin + n) * Dx + j] + ring[slot_out * Dx + j];
+      ring[slot_out * Dx + j] = 0.0;              // the slot is reused by row n - 1
+    }
     __syncthreads();
     double* dl = d0;
     double* dn = d1;
@@ -154,21 +216,25 @@ k_freerun_bwd(Shape sh, const int64_t* __restrict__ seq, int Xwin, int Dx, int U
         sG[o + idx] = fma(dl[j], in[i], sG[o + idx]);
       }
       for (int j = threadIdx.x; j < down; j += blockDim.x) sG[o + down * up + j] += dl[j];
-      for (int i = threadIdx.x; i < up; i += blockDim.x) {
-        double a = 0.0;
-        for (int j = 0; j < down; ++j) a = fma(sP[o + i * down + j], dl[j], a);
-        dn[i] = a;
-      }
+      matvec<true>(sP + o, up, down, nullptr, dl, dn);     // dn[i] = sum_j WT[i][j] dl[j]
       __syncthreads();
       double* tmp = dl;
       dl = dn;
       dn = tmp;
     }
     for (int i = threadIdx.x; i < Q; i += blockDim.x) {
-      if (i < Qx) lat_g[(lat0 + n) * Dx + i] += dl[i];
-      else if (ctl_g) ctl_g[(ctl0 + n) * Du + (i - Qx)] += dl[i];
+      if (i < Qx) {
+        const int k = i / Dx, j = i - k * Dx;     // latent row n + k
+        ring[(int)((n + k) % RW) * Dx + j] += dl[i];
+      } else if (ctl_g) {
+        ctl_g[(ctl0 + n) * Du + (i - Qx)] += dl[i];
+      }
     }
-    __syncthreads();              // older steps read the rows just updated
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < Qx; i += blockDim.x) {
+    const int k = i / Dx, j = i - k * Dx;
+    lat_g[(lat0 + k) * Dx + j] += ring[(k % RW) * Dx + j];
   }
   for (int i = threadIdx.x; i < sh.nparams; i += blockDim.x) pgrad[(size_t)s * sh.nparams + i] = sG[i];
 }

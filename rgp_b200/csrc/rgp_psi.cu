@@ -534,7 +534,9 @@ static int mlp_common(rgp_psi_handle_t h, int nseq, const int64_t* seq_desc, int
   if (sh->u[0] != Xwin * Dx + Uwin * Du || sh->u[nlayers] != Dx)
     return set_error(RGP_PSI_ERR_INVALID, "MLP widths [%d ... %d] do not match the window (%d inputs, %d outputs)",
                      sh->u[0], sh->u[nlayers], Xwin * Dx + Uwin * Du, Dx);
-  if (mlp::bwd_smem(*sh) > 200 * 1024)
+  if (Xwin * Dx + Uwin * Du > mlp::THREADS)
+    return set_error(RGP_PSI_ERR_INVALID, "MLP input of %d values is wider than the block (%d)", Xwin * Dx + Uwin * Du, mlp::THREADS);
+  if (mlp::bwd_smem(*sh, Xwin, Dx) > 200 * 1024)
     return set_error(RGP_PSI_ERR_INVALID, "MLP with %d parameters does not fit in shared memory", sh->nparams);
   return 0;
 }
@@ -565,8 +567,8 @@ int rgp_mlp_freerun_bwd_dev(rgp_psi_handle_t h, void* stream, int nseq, const in
   RGP_CUDA(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   RGP_CUDA(cudaFuncSetAttribute(mlp::k_freerun_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)mlp::bwd_smem(sh)));
-  RGP_LAUNCH(h, st, "mlp_freerun_bwd", mlp::k_freerun_bwd, nseq, mlp::THREADS, mlp::bwd_smem(sh), sh, seq_desc, Xwin,
+                                (int)mlp::bwd_smem(sh, Xwin, Dx)));
+  RGP_LAUNCH(h, st, "mlp_freerun_bwd", mlp::k_freerun_bwd, nseq, mlp::THREADS, mlp::bwd_smem(sh, Xwin, Dx), sh, seq_desc, Xwin,
              Dx, Uwin, Du, params, lat_mean, ctl_mean, hidden_acts, lat_gmean, ctl_gmean, param_grads);
   return 0;
 }
