@@ -49,9 +49,9 @@ inline bool make_shape(int nl, const int* units, Shape* s) {
   return true;
 }
 
-inline size_t fwd_smem(const Shape& s) { return sizeof(double) * ((size_t)s.nparams + 4 * s.maxu); }
+inline size_t fwd_smem(const Shape& s) { return sizeof(double) * ((size_t)s.nparams + 4 * s.maxu) + MAXL * 48; }
 inline size_t bwd_smem(const Shape& s, int Xwin, int Dx) {
-  return sizeof(double) * (2 * (size_t)s.nparams + s.u[0] + s.nhid + 2 * s.maxu + (size_t)(Xwin + 1) * Dx);
+  return sizeof(double) * (2 * (size_t)s.nparams + s.u[0] + s.nhid + 2 * s.maxu + (size_t)(Xwin + 1) * Dx + 1) + MAXL * 48;
 }
 
 // shared copy of the parameters with every W transposed (WT[i][j] = W[j][i]): thread j of a layer
@@ -97,38 +97,60 @@ RGP_DEVINL double tanh_fast(double x) {
 // over P adjacent lanes (P = 4, 2 or 1, so that down * P fits the block when it can) and two
 // accumulators per lane: the dependent-FMA chain of a step is what bounds the recurrence, not the
 // flop count.  Every thread of the block must call it; no barrier inside.
-__device__ __forceinline__ int split_for(int down) { return down * 4 <= THREADS ? 4 : (down * 2 <= THREADS ? 2 : 1); }
+__host__ __device__ inline int log2_split_for(int rows) { return rows * 4 <= THREADS ? 2 : (rows * 2 <= THREADS ? 1 : 0); }
+
+// Per-layer constants, computed once per kernel (the step loop is pure latency: no integer division,
+// no indexed access to the by-value Shape inside it).
+struct LayerK {
+  int up, down, off;        // widths, offset of W in the packed vector
+  int lpF, itF;             // forward mat-vec: log2 of the lanes per output, trips over the outputs
+  int lpT, itT;             // transposed mat-vec (back-propagation): outputs = the layer's inputs
+  int hin, hout;            // offsets of the layer's input / output activations in sAct (backward), -1 = none
+};
+
+__device__ __forceinline__ void layer_constants(const Shape& sh, LayerK* lk) {
+  if ((int)threadIdx.x < sh.nl) {
+    const int l = threadIdx.x;
+    LayerK k;
+    k.up = sh.u[l];
+    k.down = sh.u[l + 1];
+    k.off = sh.woff[l];
+    k.lpF = log2_split_for(k.down);
+    k.itF = (k.down + (THREADS >> k.lpF) - 1) / (THREADS >> k.lpF);
+    k.lpT = log2_split_for(k.up);
+    k.itT = (k.up + (THREADS >> k.lpT) - 1) / (THREADS >> k.lpT);
+    k.hin = l == 0 ? 0 : sh.u[0] + sh.hoff[l - 1];
+    k.hout = l < sh.nl - 1 ? sh.u[0] + sh.hoff[l] : -1;
+    lk[l] = k;
+  }
+}
 
 template <bool TRANSPOSED>
 __device__ __forceinline__ void matvec(const double* __restrict__ Wm, int rows, int cols, const double* __restrict__ bias,
-                                       const double* __restrict__ in, double* __restrict__ out) {
+                                       const double* __restrict__ in, double* __restrict__ out, int lp, int trips) {
   // TRANSPOSED = false: out[j] = bias[j] + sum_i Wm[i * rows + j] * in[i]   (j < rows outputs, i < cols inputs)
   // TRANSPOSED = true : out[i] = sum_j Wm[i * cols + j] * in[j]             (i < rows outputs, j < cols inputs)
-  const int P = split_for(rows);
-  const int per = THREADS / P;
-  const int part = threadIdx.x % P;
-  for (int o = threadIdx.x / P; o < rows + (per - rows % per) % per; o += per) {
-    double a0 = 0.0, a1 = 0.0;
+  // lp = log2(lanes per output), trips = ceil(rows / (THREADS >> lp)); every thread runs every trip
+  const int P = 1 << lp, per = THREADS >> lp;
+  const int part = threadIdx.x & (P - 1);
+  int o = threadIdx.x >> lp;
+  for (int trip = 0; trip < trips; ++trip, o += per) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     if (o < rows) {
-      if (!TRANSPOSED) {
-        int i = part;
-        for (; i + P < cols; i += 2 * P) {
-          a0 = fma(Wm[i * rows + o], in[i], a0);
-          a1 = fma(Wm[(i + P) * rows + o], in[i + P], a1);
-        }
-        if (i < cols) a0 = fma(Wm[i * rows + o], in[i], a0);
-      } else {
-        int j = part;
-        for (; j + P < cols; j += 2 * P) {
-          a0 = fma(Wm[o * cols + j], in[j], a0);
-          a1 = fma(Wm[o * cols + j + P], in[j + P], a1);
-        }
-        if (j < cols) a0 = fma(Wm[o * cols + j], in[j], a0);
+      const double* w = TRANSPOSED ? Wm + o * cols : Wm + o;
+      const int ws = TRANSPOSED ? 1 : rows;
+      int i = part;
+      for (; i + 3 * P < cols; i += 4 * P) {
+        a0 = fma(w[i * ws], in[i], a0);
+        a1 = fma(w[(i + P) * ws], in[i + P], a1);
+        a2 = fma(w[(i + 2 * P) * ws], in[i + 2 * P], a2);
+        a3 = fma(w[(i + 3 * P) * ws], in[i + 3 * P], a3);
       }
+      for (; i < cols; i += P) a0 = fma(w[i * ws], in[i], a0);
     }
-    double a = a0 + a1;
-    if (P >= 2) a += __shfl_xor_sync(0xffffffffu, a, 1);
-    if (P >= 4) a += __shfl_xor_sync(0xffffffffu, a, 2);
+    double a = (a0 + a1) + (a2 + a3);
+    if (lp >= 1) a += __shfl_xor_sync(0xffffffffu, a, 1);
+    if (lp >= 2) a += __shfl_xor_sync(0xffffffffu, a, 2);
     if (o < rows && part == 0) out[o] = bias ? a + bias[o] : a;
   }
 }
@@ -140,13 +162,17 @@ __device__ __forceinline__ void matvec(const double* __restrict__ Wm, int rows, 
 __global__ void __launch_bounds__(THREADS)
 k_freerun(Shape sh, const int64_t* __restrict__ seq, int Xwin, int Dx, int Uwin, int Du,
           const double* __restrict__ params, double* __restrict__ lat, const double* __restrict__ ctl,
-          double* __restrict__ acts) {
+          double* __restrict__ acts, int dbg) {
+  // dbg (timing experiments only, results wrong): 1 no mat-vec, 2 no tanh, 4 no global stores, 8 no control prefetch
   extern __shared__ __align__(16) double smem[];
   double* sP = smem;
   double* win0 = sP + sh.nparams;                 // two input vectors (ping-pong), each maxu long
   double* win1 = win0 + sh.maxu;
   double* bufA = win1 + sh.maxu;
   double* bufB = bufA + sh.maxu;
+  LayerK* lk = reinterpret_cast<LayerK*>(bufB + sh.maxu);
+  layer_constants(sh, lk);
+  const int nl = sh.nl, nhid = sh.nhid;
   const int s = blockIdx.x;
   const int Qx = Xwin * Dx, Qu = Uwin * Du;
   const int64_t row0 = seq[s * lag::DESC + 0], N = seq[s * lag::DESC + 1];
@@ -159,19 +185,20 @@ k_freerun(Shape sh, const int64_t* __restrict__ seq, int Xwin, int Dx, int Uwin,
     double* in = (n & 1) ? win1 : win0;
     double* nxt = (n & 1) ? win0 : win1;
     double cnext = 0.0;                           // this thread's control input of the next step (Q <= THREADS, host-checked)
-    if ((int)threadIdx.x >= Qx && (int)threadIdx.x < Qx + Qu && n + 1 < N)
+    if (!(dbg & 8) && (int)threadIdx.x >= Qx && (int)threadIdx.x < Qx + Qu && n + 1 < N)
       cnext = ctl[(ctl0 + n + 1) * Du + ((int)threadIdx.x - Qx)];
     const double* x = in;
     double* out = bufA;
-    for (int l = 0; l < sh.nl; ++l) {
-      const int up = sh.u[l], down = sh.u[l + 1], o = sh.woff[l];
-      matvec<false>(sP + o, down, up, sP + o + down * up, x, out);
+    for (int l = 0; l < nl; ++l) {
+      const LayerK k = lk[l];
+      const int up = k.up, down = k.down, o = k.off;
+      if (!(dbg & 1)) matvec<false>(sP + o, down, up, sP + o + down * up, x, out, k.lpF, k.itF);
       __syncthreads();
-      if (l < sh.nl - 1) {
+      if (l < nl - 1) {
         for (int j = threadIdx.x; j < down; j += blockDim.x) {
-          const double a = tanh_fast(out[j]);
+          const double a = (dbg & 2) ? out[j] : tanh_fast(out[j]);
           out[j] = a;
-          acts[(row0 + n) * sh.nhid + sh.hoff[l] + j] = a;
+          if (!(dbg & 4)) acts[(row0 + n) * nhid + (k.hout - sh.u[0]) + j] = a;
         }
         __syncthreads();
       }
@@ -186,7 +213,8 @@ k_freerun(Shape sh, const int64_t* __restrict__ seq, int Xwin, int Dx, int Uwin,
       else v = cnext;
       nxt[i] = v;
     }
-    for (int j = threadIdx.x; j < Dx; j += blockDim.x) lat[(lat0 + Xwin + n) * Dx + j] = x[j];
+    if (!(dbg & 4))
+      for (int j = threadIdx.x; j < Dx; j += blockDim.x) lat[(lat0 + Xwin + n) * Dx + j] = x[j];
     __syncthreads();
   }
 }
@@ -208,6 +236,9 @@ k_freerun_bwd(Shape sh, const int64_t* __restrict__ seq, int Xwin, int Dx, int U
   double* d0 = sAct + sh.u[0] + sh.nhid;
   double* d1 = d0 + sh.maxu;
   double* ring = d1 + sh.maxu;                    // [(Xwin + 1) * Dx] pending contributions, row t at slot t % (Xwin + 1)
+  LayerK* lk = reinterpret_cast<LayerK*>(ring + (Xwin + 1) * Dx + ((Xwin + 1) * Dx & 1));
+  layer_constants(sh, lk);
+  const int nl = sh.nl, nhid = sh.nhid;
   const int s = blockIdx.x;
   const int Qx = Xwin * Dx, Q = sh.u[0], RW = Xwin + 1;
   const int64_t row0 = seq[s * lag::DESC + 0], N = seq[s * lag::DESC + 1];
@@ -216,12 +247,14 @@ k_freerun_bwd(Shape sh, const int64_t* __restrict__ seq, int Xwin, int Dx, int U
   for (int i = threadIdx.x; i < sh.nparams; i += blockDim.x) sG[i] = 0.0;
   for (int i = threadIdx.x; i < RW * Dx; i += blockDim.x) ring[i] = 0.0;
   __syncthreads();
+  int slot_out = (int)((Xwin + N) % RW);
+  const int my_k = (int)threadIdx.x / Dx, my_j = (int)threadIdx.x - my_k * Dx;    // latent row / dim of input element tid
   for (int64_t n = N - 1; n >= 0; --n) {
     // inputs, activations and the objective gradient of this step: nothing here was written by this kernel
     for (int i = threadIdx.x; i < Q; i += blockDim.x)
       sAct[i] = i < Qx ? lat[(lat0 + n) * Dx + i] : ctl[(ctl0 + n) * Du + (i - Qx)];
-    for (int i = threadIdx.x; i < sh.nhid; i += blockDim.x) sAct[Q + i] = acts[(row0 + n) * sh.nhid + i];
-    const int slot_out = (int)((Xwin + n) % RW);
+    for (int i = threadIdx.x; i < nhid; i += blockDim.x) sAct[Q + i] = acts[(row0 + n) * nhid + i];
+    slot_out = slot_out == 0 ? RW - 1 : slot_out - 1;           // slot of row Xwin + n, walking down with n
     for (int j = threadIdx.x; j < Dx; j += blockDim.x) {
       d0[j] = lat_g[(lat0 + Xwin + n) * Dx + j] + ring[slot_out * Dx + j];
       ring[slot_out * Dx + j] = 0.0;              // the slot is reused by row n - 1
@@ -229,30 +262,44 @@ k_freerun_bwd(Shape sh, const int64_t* __restrict__ seq, int Xwin, int Dx, int U
     __syncthreads();
     double* dl = d0;
     double* dn = d1;
-    for (int l = sh.nl - 1; l >= 0; --l) {
-      const int up = sh.u[l], down = sh.u[l + 1], o = sh.woff[l];
-      const double* in = l == 0 ? sAct : sAct + Q + sh.hoff[l - 1];
-      if (l < sh.nl - 1) {
-        const double* out = sAct + Q + sh.hoff[l];
+    for (int l = nl - 1; l >= 0; --l) {
+      const LayerK k = lk[l];
+      const int up = k.up, down = k.down, o = k.off;
+      const double* in = sAct + k.hin;
+      if (k.hout >= 0) {
+        const double* out = sAct + k.hout;
         for (int j = threadIdx.x; j < down; j += blockDim.x) dl[j] *= 1.0 - out[j] * out[j];
         __syncthreads();
       }
-      for (int idx = threadIdx.x; idx < down * up; idx += blockDim.x) {
-        const int j = idx / up, i = idx - j * up;
-        sG[o + idx] = fma(dl[j], in[i], sG[o + idx]);
+      // outer product dl in^T -> W gradient: thread owns columns i = tid % up of consecutive rows, no division
+      // in the loop (i and j advance by the fixed stride THREADS = qd * up + rm)
+      {
+        const int qd = THREADS / up, rm = THREADS - qd * up;
+        int j = threadIdx.x / up, i = threadIdx.x - j * up;
+        for (int idx = threadIdx.x; idx < down * up; idx += THREADS) {
+          sG[o + idx] = fma(dl[j], in[i], sG[o + idx]);
+          j += qd;
+          i += rm;
+          if (i >= up) {
+            i -= up;
+            ++j;
+          }
+        }
       }
       for (int j = threadIdx.x; j < down; j += blockDim.x) sG[o + down * up + j] += dl[j];
-      matvec<true>(sP + o, up, down, nullptr, dl, dn);     // dn[i] = sum_j WT[i][j] dl[j]
+      matvec<true>(sP + o, up, down, nullptr, dl, dn, k.lpT, k.itT);     // dn[i] = sum_j WT[i][j] dl[j]
       __syncthreads();
       double* tmp = dl;
       dl = dn;
       dn = tmp;
     }
-    for (int i = threadIdx.x; i < Q; i += blockDim.x) {
-      if (i < Qx) {
-        const int k = i / Dx, j = i - k * Dx;     // latent row n + k
-        ring[(int)((n + k) % RW) * Dx + j] += dl[i];
-      } else if (ctl_g) {
+    {                                             // Q <= THREADS (host-checked): one input element per thread
+      const int i = threadIdx.x;
+      if (i < Qx) {                               // latent row n + my_k lives in slot (slot_out + 1 + my_k) mod RW
+        int sl = slot_out + 1 + my_k;
+        sl -= sl >= RW ? RW : 0;
+        ring[sl * Dx + my_j] += dl[i];
+      } else if (i < Q && ctl_g) {
         ctl_g[(ctl0 + n) * Du + (i - Qx)] += dl[i];
       }
     }

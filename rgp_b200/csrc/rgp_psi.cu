@@ -552,7 +552,7 @@ int rgp_mlp_freerun_dev(rgp_psi_handle_t h, void* stream, int nseq, const int64_
   cudaStream_t st = (cudaStream_t)stream;
   RGP_CUDA(cudaFuncSetAttribute(mlp::k_freerun, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mlp::fwd_smem(sh)));
   RGP_LAUNCH(h, st, "mlp_freerun", mlp::k_freerun, nseq, mlp::THREADS, mlp::fwd_smem(sh), sh, seq_desc, Xwin, Dx, Uwin,
-             Du, params, lat_mean, ctl_mean, hidden_acts);
+             Du, params, lat_mean, ctl_mean, hidden_acts, h->debug_skip);
   return 0;
 }
 
