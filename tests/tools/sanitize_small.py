@@ -37,5 +37,26 @@ gm, gv, val = lw.latent_terms(lat, lat.abs() + 0.1, torch.randn((lw.N, 2), dtype
                               torch.randn(lw.N, dtype=torch.float64, device="cuda"))
 torch.cuda.synchronize()
 print("lag / latent kernels ok", float(val))
+# MLP back-constraint kernels (shared-memory input window, pending-gradient ring)
+from oracle import mlp_oracle as mo
+from rgp_b200.backconstraint import MLPBackConstraint
+from test_mlp_oracle import make_case
+c = make_case(seed=2, X_win=3, X_dim=2, U_win=2, U_dim=1, n_steps=(12, 9), control=True)
+lw2 = LagWindow(dp.handle, [3 + N for N in c["n_steps"]], 3, 2, [u.shape[0] for u in c["ctl"]], 2, 1)
+enc = MLPBackConstraint(lw2)
+with torch.no_grad():
+    enc.flat.copy_(t(np.concatenate([np.concatenate([W.ravel(), b]) for W, b in c["params"]])))
+init = t(np.stack(c["init"])).requires_grad_(True)
+ctl2 = t(np.vstack(c["ctl"])).requires_grad_(True)
+lat2 = enc(init, ctl2)
+(lat2 * t(np.vstack(c["weights"]))).sum().backward()
+Xo = mo.freerun(c["params"], c["init"], c["ctl"], c["n_steps"], 3, 2)
+go = [w.copy() for w in c["weights"]]
+pgo, cgo = mo.freerun_backward(c["params"], Xo, c["ctl"], go, 3, 2)
+e_mlp = max(relerr(lat2.detach().cpu().numpy(), np.vstack(Xo)),
+            relerr(enc.flat.grad.cpu().numpy(), np.concatenate([np.concatenate([dW.ravel(), db]) for dW, db in pgo])),
+            relerr(init.grad.cpu().numpy(), np.stack([x[:3] for x in go])), relerr(ctl2.grad.cpu().numpy(), np.vstack(cgo)))
+print("mlp back-constraint kernels: max rel err %.2e" % e_mlp)
+worst = max(worst, e_mlp)
 assert worst < 1e-10, worst
 print("sanitize_small: all results match the oracle, worst rel err %.2e" % worst)
