@@ -14,7 +14,12 @@ from rgp_b200.lagwindow import LagWindow
 
 t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
 worst = 0.0
-for opts in ({}, {"bwd_warps": 8}, {"bwd_mbar": 1}, {"bwd_strip": 1}):
+# SANITIZE_SKIP_MBARRIER=1: leave out the two experimental kernels that synchronise through mbarrier phases
+# in inline PTX; racecheck does not model those and their reports fill its hazard list
+variants = [{}, {"bwd_warps": 8}]
+if not os.environ.get("SANITIZE_SKIP_MBARRIER"):
+    variants += [{"bwd_mbar": 1}, {"bwd_strip": 1}]
+for opts in variants:
     dp = DevicePsi(0, impl=1)
     for k, v in opts.items():
         dp.handle.set_option(k, v)
