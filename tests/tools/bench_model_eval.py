@@ -25,16 +25,18 @@ CONFIGS = [
     ("config2_ballbeam_2hidden", (0, 10, 10), (1, 1, 1), (490,), 10, 1, 50, 2),
     ("config3_mocap", (0, 20, 20), (59, 1, 1), (102, 102, 102, 102), 20, 1, 200, 1),
     ("synthetic_large", (0, 16), (1, 2), (1 << 17, 1 << 17), 16, 2, 512, 0),
+    ("synthetic_large_svi", (0, 16), (1, 2), (1 << 17, 1 << 17), 16, 2, 512, 0),
 ]
 
 
 def main():
     cuda = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
     for name, wins, nDims, seq_lens, U_win, ctl_dim, M, cpu_reps in CONFIGS:
+        svi = name.endswith("_svi")        # SVI bound: statistics + gradients from one fused pass per layer
         m = make_deep_model(wins=wins, nDims=nDims, seq_lens=seq_lens, U_win=U_win, U_dim=ctl_dim, M=M,
-                            control=ctl_dim > 0)
+                            control=ctl_dim > 0, svi=svi)
         Y, latents, controls, params = stack_model(m, to=cuda)
-        model = DeviceDeepAutoreg(list(wins), nDims, list(seq_lens), U_win=U_win, ctl_dim=ctl_dim, device=0)
+        model = DeviceDeepAutoreg(list(wins), nDims, list(seq_lens), U_win=U_win, ctl_dim=ctl_dim, svi=svi, device=0)
         h = model.bound.psi.handle
         out = model.evaluate(params, Y, latents, controls)
         torch.cuda.synchronize()
