@@ -1,0 +1,62 @@
+"""Config 3 (MoCap walk / run) with the AUTHORS' TRAINED parameters and latents (build container only):
+    python tests/golden/make_mocap_layer1.py
+
+/root/reference/examples/alex_walk_run_m1_sf1.0.h5 is the three-layer model the reference's authors
+trained (examples/walk_run_2_alex.py:550-565), read with rgp_b200.checkpoint (no h5py here).  The
+observations and controls are not part of a checkpoint, but the MIDDLE layer needs neither: its inputs
+are windows of its own latent series and of the top layer's (wins 20 / 20 -> Q = 40, M = 100), its outputs
+are its own latent series (uncertain outputs).  This script builds that layer's input rows (lag windows), evaluates the
+psi statistics, the VarDTC bound with uncertain outputs and the psi gradients for the bound's own
+dL_dpsi* with the CPU oracle, and stores them in tests/golden/mocap_layer1_trained.npz.
+
+Conditioning.  At the trained optimum K(Z,Z) + 1e-6 I is numerically singular: a 1e-15 relative
+perturbation of Z moves the oracle's own bound by 6e-7 and its (near-zero) parameter gradients by
+O(1) relative.  So the fixture pins what is well conditioned - the psi statistics and the psi
+gradients for FIXED upstream dL_dpsi* (the hot path itself, no Cholesky involved) - to full
+precision, and the bound only to its measured sensitivity (``sens_logL``)."""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from rgp_b200.checkpoint import layer_parameters, load_checkpoint  # noqa: E402
+
+if __name__ == "__main__":
+    layers = layer_parameters(load_checkpoint("/root/reference/examples/alex_walk_run_m1_sf1.0.h5"))
+    L1, L2 = layers[1], layers[2]
+    nseq = len([k for k in L1 if k.startswith("qX_") and k.endswith("_mean")])
+    Xs = [(L1["qX_%d_mean" % s].astype(np.float64), L1["qX_%d_variance" % s].astype(np.float64)) for s in range(nseq)]
+    Us = [(L2["qX_%d_mean" % s].astype(np.float64), L2["qX_%d_variance" % s].astype(np.float64)) for s in range(nseq)]
+    X_win = U_win = 20
+    assert L1["Z"].shape[1] == X_win * Xs[0][0].shape[1] + U_win * Us[0][0].shape[1]
+    p = dict(variance=L1["variance"], lengthscale=L1["lengthscale"], Z=L1["Z"], noise_variance=L1["noise_variance"])
+    from oracle import bound_oracle as bo
+    from oracle.lag_oracle import build_rows
+    from oracle.psi_oracle import psi_backward, psi_forward
+    mu = build_rows([x[0] for x in Xs], [u[0] for u in Us], X_win, U_win)
+    S = build_rows([x[1] for x in Xs], [u[1] for u in Us], X_win, U_win)
+    Y = np.vstack([x[0][X_win:] for x in Xs])
+    Y_var = np.vstack([x[1][X_win:] for x in Xs])
+
+    def bound(Z):
+        psi0, psi1, psi2 = psi_forward(p["variance"], p["lengthscale"], Z, mu, S)
+        Kmm = bo.rbf_K(p["variance"], p["lengthscale"], Z)
+        return (psi0, psi1, psi2) + bo.vardtc_inference(psi0, psi1, psi2, Kmm, Y, p["noise_variance"], Y_var=Y_var)
+
+    psi0, psi1, psi2, logL, g = bound(p["Z"])
+    grads = psi_backward(g["dL_dpsi0"], g["dL_dpsi1"], g["dL_dpsi2"], p["variance"], p["lengthscale"], p["Z"], mu, S)
+    rng = np.random.default_rng(0)
+    sens = 0.0
+    for _ in range(3):
+        sens = max(sens, abs(bound(p["Z"] * (1.0 + 1e-15 * rng.normal(size=p["Z"].shape)))[3] - logL) / abs(logL))
+    out = dict(lens=np.array([x[0].shape[0] for x in Xs]), ctl_lens=np.array([u[0].shape[0] for u in Us]),
+               lat_mean=np.vstack([x[0] for x in Xs]), lat_var=np.vstack([x[1] for x in Xs]),
+               ctl_mean=np.vstack([u[0] for u in Us]), ctl_var=np.vstack([u[1] for u in Us]),
+               variance=p["variance"], lengthscale=p["lengthscale"], Z=p["Z"], noise_variance=p["noise_variance"],
+               mu=mu, S=S, psi1=psi1, psi2=psi2, dL0=g["dL_dpsi0"], dL1=g["dL_dpsi1"], dL2=g["dL_dpsi2"],
+               dvar=grads[0], dl=grads[1], dZ=grads[2], dmu=grads[3], dS=grads[4], logL=logL, sens_logL=sens)
+    np.savez_compressed(os.path.join(HERE, "mocap_layer1_trained.npz"), **out)
+    print("mocap_layer1_trained.npz: N =", mu.shape[0], "Q =", mu.shape[1], "M =", p["Z"].shape[0], "logL =", logL,
+          "sens_logL = %.1e" % sens)

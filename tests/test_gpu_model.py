@@ -107,6 +107,36 @@ def test_config1_real_actuator_data_matches_fixture():
     assert relerr(cpu(ctl_grads[0]), g["g_ctl_mean"]) <= tol("g_ctl_mean")
 
 
+def test_trained_mocap_layer_from_the_authors_checkpoint():
+    """Config 3 with the authors' trained parameters and latents (tests/golden/mocap_layer1_trained.npz,
+    made from examples/alex_walk_run_m1_sf1.0.h5 through rgp_b200.checkpoint): lag-window rows bit for bit,
+    psi statistics and psi gradients at full precision, the (ill-conditioned) bound to its measured
+    sensitivity."""
+    import os
+    from rgp_b200.device import DevicePsi
+    from rgp_b200.inference import DeviceBound
+    from rgp_b200.lagwindow import LagWindow
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mocap_layer1_trained.npz"))
+    dp = DevicePsi(0)
+    lw = LagWindow(dp.handle, list(g["lens"]), 20, 1, list(g["ctl_lens"]), 20, 1)
+    mu = lw.gather(_cuda(g["lat_mean"]), _cuda(g["ctl_mean"]))
+    S = lw.gather(_cuda(g["lat_var"]), _cuda(g["ctl_var"]))
+    np.testing.assert_array_equal(mu.cpu().numpy(), g["mu"])
+    np.testing.assert_array_equal(S.cpu().numpy(), g["S"])
+    var, ell, Z = float(g["variance"]), _cuda(g["lengthscale"]), _cuda(g["Z"])
+    _, p1, p2 = dp.forward(mu, S, Z, ell, var)
+    assert relerr(p1.cpu().numpy(), g["psi1"]) < 2e-11 and relerr(p2.cpu().numpy(), g["psi2"]) < 2e-11
+    out = dp.backward(mu, S, Z, ell, var, _cuda(g["dL0"]), _cuda(g["dL1"]), _cuda(g["dL2"]))
+    for name, a in zip(["dvar", "dl", "dZ", "dmu", "dS"], out):
+        assert relerr(a.cpu().numpy(), g[name]) < 2e-11, name
+    Y = _cuda(g["lat_mean"]).index_select(0, torch.cat([torch.arange(o + 20, o + T) for o, T in
+                                                         zip(np.cumsum([0] + list(g["lens"][:-1])), g["lens"])]).cuda())
+    Yv = _cuda(g["lat_var"]).index_select(0, torch.cat([torch.arange(o + 20, o + T) for o, T in
+                                                         zip(np.cumsum([0] + list(g["lens"][:-1])), g["lens"])]).cuda())
+    logL, _ = DeviceBound(psi=dp).vardtc(var, ell, Z, mu, S, Y, float(g["noise_variance"]), Y_var=Yv)
+    assert abs(float(logL) - float(g["logL"])) <= max(1e-9, 50 * float(g["sens_logL"])) * abs(float(g["logL"]))
+
+
 def test_deep_model_is_reproducible_run_to_run():
     from rgp_b200.layer import DeviceDeepAutoreg
     m = make_deep_model(wins=(0, 5, 5), nDims=(3, 2, 2), seq_lens=(700, 650), M=64, control=False)
