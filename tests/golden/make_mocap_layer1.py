@@ -11,9 +11,10 @@ dL_dpsi* with the CPU oracle, and stores them in tests/golden/mocap_layer1_train
 
 Conditioning.  At the trained optimum K(Z,Z) + 1e-6 I is numerically singular: a 1e-15 relative
 perturbation of Z moves the oracle's own bound by 6e-7 and its (near-zero) parameter gradients by
-O(1) relative.  So the fixture pins what is well conditioned - the psi statistics and the psi
-gradients for FIXED upstream dL_dpsi* (the hot path itself, no Cholesky involved) - to full
-precision, and the bound only to its measured sensitivity (``sens_logL``)."""
+O(1) relative.  So the fixture pins what is well conditioned - the lag-window rows and the psi
+statistics - to full precision, the psi gradients for FIXED upstream dL_dpsi* to the measured effect
+of 1e-15 relative noise on those upstream gradients (their entries reach 1e5 and cancel, ``sens_d*``),
+and the bound to its measured sensitivity (``sens_logL``)."""
 import os
 import sys
 
@@ -51,12 +52,25 @@ if __name__ == "__main__":
     sens = 0.0
     for _ in range(3):
         sens = max(sens, abs(bound(p["Z"] * (1.0 + 1e-15 * rng.normal(size=p["Z"].shape)))[3] - logL) / abs(logL))
+    # cancellation in the gradient sums: at the optimum dL_dpsi2 has entries of order 1e5 whose
+    # contributions cancel to O(1e3) results - measure how far 1e-15 relative noise on dL_dpsi1/2 moves them
+    gs = {}
+    for _ in range(3):
+        d1 = g["dL_dpsi1"] * (1.0 + 1e-15 * rng.normal(size=g["dL_dpsi1"].shape))
+        d2 = g["dL_dpsi2"] * (1.0 + 1e-15 * rng.normal(size=g["dL_dpsi2"].shape))
+        d2 = 0.5 * (d2 + d2.T)
+        alt = psi_backward(g["dL_dpsi0"], d1, d2, p["variance"], p["lengthscale"], p["Z"], mu, S)
+        for name, a, b in zip(["dvar", "dl", "dZ", "dmu", "dS"], alt, grads):
+            a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+            gs[name] = max(gs.get(name, 0.0), float(np.abs(a - b).max() / np.abs(b).max()))
+    print("max |dL_dpsi2| = %.1e" % np.abs(g["dL_dpsi2"]).max(), {k: "%.1e" % v for k, v in gs.items()})
     out = dict(lens=np.array([x[0].shape[0] for x in Xs]), ctl_lens=np.array([u[0].shape[0] for u in Us]),
                lat_mean=np.vstack([x[0] for x in Xs]), lat_var=np.vstack([x[1] for x in Xs]),
                ctl_mean=np.vstack([u[0] for u in Us]), ctl_var=np.vstack([u[1] for u in Us]),
                variance=p["variance"], lengthscale=p["lengthscale"], Z=p["Z"], noise_variance=p["noise_variance"],
                mu=mu, S=S, psi1=psi1, psi2=psi2, dL0=g["dL_dpsi0"], dL1=g["dL_dpsi1"], dL2=g["dL_dpsi2"],
-               dvar=grads[0], dl=grads[1], dZ=grads[2], dmu=grads[3], dS=grads[4], logL=logL, sens_logL=sens)
+               dvar=grads[0], dl=grads[1], dZ=grads[2], dmu=grads[3], dS=grads[4], logL=logL, sens_logL=sens,
+               **{"sens_" + k: v for k, v in gs.items()})
     np.savez_compressed(os.path.join(HERE, "mocap_layer1_trained.npz"), **out)
     print("mocap_layer1_trained.npz: N =", mu.shape[0], "Q =", mu.shape[1], "M =", p["Z"].shape[0], "logL =", logL,
           "sens_logL = %.1e" % sens)

@@ -127,8 +127,8 @@ def test_trained_mocap_layer_from_the_authors_checkpoint():
     _, p1, p2 = dp.forward(mu, S, Z, ell, var)
     assert relerr(p1.cpu().numpy(), g["psi1"]) < 2e-11 and relerr(p2.cpu().numpy(), g["psi2"]) < 2e-11
     out = dp.backward(mu, S, Z, ell, var, _cuda(g["dL0"]), _cuda(g["dL1"]), _cuda(g["dL2"]))
-    for name, a in zip(["dvar", "dl", "dZ", "dmu", "dS"], out):
-        assert relerr(a.cpu().numpy(), g[name]) < 2e-11, name
+    for name, a in zip(["dvar", "dl", "dZ", "dmu", "dS"], out):   # upstream entries ~1e5 cancel: see the generator
+        assert relerr(a.cpu().numpy(), g[name]) < max(2e-11, 50 * float(g["sens_" + name])), name
     Y = _cuda(g["lat_mean"]).index_select(0, torch.cat([torch.arange(o + 20, o + T) for o, T in
                                                          zip(np.cumsum([0] + list(g["lens"][:-1])), g["lens"])]).cuda())
     Yv = _cuda(g["lat_var"]).index_select(0, torch.cat([torch.arange(o + 20, o + T) for o, T in
