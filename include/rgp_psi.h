@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define RGP_PSI_ABI_VERSION 1
+#define RGP_PSI_ABI_VERSION 2   /* 2: + fused, latent-terms, MLP free-run entry points */
 
 typedef struct rgp_psi_ctx* rgp_psi_handle_t;
 

@@ -93,7 +93,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.rgp_psi_abi_version() != 1:
+    if lib.rgp_psi_abi_version() != 2:
         raise OSError("librgp_psi ABI version mismatch")
     _lib = lib
     return lib
