@@ -5,6 +5,12 @@ Public surface:
   DevicePsi          device-resident API on torch CUDA tensors   (rgp_b200.device)
   ShardedPsi         row-sharded multi-GPU driver                 (rgp_b200.sharded)
   gpy_compat         duck-typed GPy RBF / NormalPosterior for tests
+  DeviceBound        VarDTC / SVI bounds on the device, row-sharded  (rgp_b200.inference)
+  LagWindow          lag-window gather / scatter, latent terms        (rgp_b200.lagwindow)
+  DeviceDeepAutoreg  one whole model objective on the device          (rgp_b200.layer)
+  RecognitionEncoder, MLPBackConstraint, deep_autoreg_objective       (encoder, backconstraint, autograd)
+  load_checkpoint    numpy reader for the reference's HDF5 checkpoints (rgp_b200.checkpoint)
+(the torch-based modules are imported on demand; importing rgp_b200 needs numpy only)
 
 The arithmetic lives in rgp_b200/_lib/librgp_psi.so, built in-tree by
 ``python -m rgp_b200._build`` (nvcc, sm_100a).  There is no CPU fallback.

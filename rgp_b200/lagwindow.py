@@ -8,7 +8,7 @@ Here both are single kernel launches on the stacked series (librgp_psi, no CPU f
 """
 from __future__ import annotations
 
-from typing import List, Optional, Sequence, Tuple
+from typing import Optional, Sequence, Tuple
 
 import torch
 

@@ -19,7 +19,7 @@ the first call raises.
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional, Tuple
+from typing import Optional
 
 import numpy as np
 
