@@ -67,7 +67,7 @@ int rgp_psi_destroy(rgp_psi_handle_t h);
 
 /* Options: "impl" (rgp_psi_impl), "row_chunk" (rows per internal device pass, 0 = 2^20),
  * "host_chunk" (rows per pipelined host<->device chunk of the *_host calls, 0 = 262144),
- * "bwd_warps" (8 or 16 warps per CTA in the Psi2 backward kernel), "bwd_mbar" (1 = the 8-warp
+ * "bwd_warps" (8 (default) or 16 warps per CTA in the Psi2 backward kernel), "bwd_mbar" (1 = the 8-warp
  * kernel with split-phase tile hand-off instead of a CTA barrier per row, Q <= 64), "bwd_strip" (1 = the
  * strip variant of that kernel with split-phase tile hand-off, Q in (16, 64]), "profile" (1 = record a
  * CUDA-event pair around every kernel launch).  Tuning / experiment knobs, not for production:

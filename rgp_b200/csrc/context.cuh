@@ -39,7 +39,7 @@ struct rgp_psi_ctx {
   int64_t host_chunk = 0;  // rows per pipelined chunk of the *_host entry points (0 = 262144)
   cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;   // *_host pipeline streams
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_cmp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
-  int bwd_warps = 16;     // 8 or 16 warps per CTA in the Psi2 backward kernel (QC >= 32)
+  int bwd_warps = 8;      // 8 (default: 2 % faster at the headline shape) or 16 warps per CTA in the Psi2 backward kernel
   int bwd_mbar = 0;       // 1: 8-warp kernel with split-phase (mbarrier) tile hand-off (psi2_bwdm.cuh), QC <= 64
   int bwd_strip = 0;      // 1: strip kernel with split-phase tile hand-off (psi2_bwds.cuh), QC = 32 / 64
   long long* trace = nullptr;   // optional device buffer for the bwd16 timeline trace (16*16*8 int64)

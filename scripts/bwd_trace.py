@@ -5,6 +5,7 @@ import os, sys, json, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 from rgp_b200.device import DevicePsi
 dp = DevicePsi(0); dev = torch.device("cuda", 0)
+dp.handle.set_option("bwd_warps", 16)   # these experiments instrument the 16-warp kernel
 N, M, Q = 1 << 16, 512, 64
 g = torch.Generator(device=dev).manual_seed(1); f64 = dict(dtype=torch.float64, device=dev)
 mu = torch.randn((N, Q), generator=g, **f64); S = torch.rand((N, Q), generator=g, **f64) * 0.49 + 0.01

@@ -5,6 +5,7 @@ import os, sys, json, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 from rgp_b200.device import DevicePsi
 dp = DevicePsi(0); dev = torch.device("cuda", 0)
+dp.handle.set_option("bwd_warps", 16)   # these experiments instrument the 16-warp kernel
 N, Q = 1 << 20, 64
 res = {}
 for M in (64, 128):

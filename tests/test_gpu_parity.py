@@ -25,14 +25,14 @@ IMPLS = ["reference", "fast"]
 @pytest.fixture(scope="module")
 def plugins():
     from rgp_b200.psicomp import PSICOMP_RBF_B200
-    p8 = PSICOMP_RBF_B200(impl="auto", cache=False)
-    p8.handle.set_option("bwd_warps", 8)             # the 8-warp backward kernel (default is 16)
+    p16 = PSICOMP_RBF_B200(impl="auto", cache=False)
+    p16.handle.set_option("bwd_warps", 16)            # the 16-warp backward kernel (the default is 8 warps)
     ps = PSICOMP_RBF_B200(impl="auto", cache=False)
     ps.handle.set_option("bwd_strip", 1)             # the strip backward kernel (split-phase tile hand-off)
     pm = PSICOMP_RBF_B200(impl="auto", cache=False)
     pm.handle.set_option("bwd_mbar", 1)              # 8-warp kernel, split-phase hand-off instead of a barrier per row
     return {"reference": PSICOMP_RBF_B200(impl="reference", cache=False),
-            "fast": PSICOMP_RBF_B200(impl="auto", cache=False), "fast8": p8, "strip": ps, "mbar": pm}
+            "fast": PSICOMP_RBF_B200(impl="auto", cache=False), "fast16": p16, "strip": ps, "mbar": pm}
 
 
 def _kern(pc, var, ell, ard=True):
@@ -76,7 +76,7 @@ SHAPES = [
 ]
 
 
-@pytest.mark.parametrize("impl", IMPLS + ["fast8", "strip", "mbar"])
+@pytest.mark.parametrize("impl", IMPLS + ["fast16", "strip", "mbar"])
 @pytest.mark.parametrize("N,M,Q,nc", SHAPES)
 def test_forward_and_backward_match_oracle(plugins, impl, N, M, Q, nc):
     var, ell, Z, mu, S = make_inputs(N, M, Q, seed=100 + N + M + Q, n_control=nc)
