@@ -53,9 +53,15 @@ typedef enum {
   RGP_PSI_ERR_NODEVICE = -4   /* no usable sm_100 device */
 } rgp_psi_status;
 
-/* Which kernels serve a call.  AUTO picks FAST when the shape is supported
- * (Q <= 128) and REFERENCE otherwise.  REFERENCE = the simple one-thread-per-output
- * kernels kept as an on-device cross-check. */
+/* Largest input dimension either kernel family handles; larger Q is rejected with
+ * RGP_PSI_ERR_INVALID by every entry point (the reference's configurations use Q = 10 ... 40,
+ * the sweep of BASELINE.json stops at 128). */
+#define RGP_PSI_MAX_Q 128
+
+/* Which kernels serve a call.  AUTO = FAST (the tiled DMMA kernels; every supported shape).
+ * REFERENCE = the simple one-thread-per-output kernels kept as an independent on-device
+ * cross-check (they accumulate with atomicAdd, so their sums are not bit-reproducible; they
+ * are never the served path). */
 typedef enum { RGP_PSI_IMPL_AUTO = 0, RGP_PSI_IMPL_FAST = 1, RGP_PSI_IMPL_REFERENCE = 2 } rgp_psi_impl;
 
 int rgp_psi_abi_version(void);
@@ -67,11 +73,10 @@ int rgp_psi_destroy(rgp_psi_handle_t h);
 
 /* Options: "impl" (rgp_psi_impl), "row_chunk" (rows per internal device pass, 0 = 2^20),
  * "host_chunk" (rows per pipelined host<->device chunk of the *_host calls, 0 = 262144),
- * "bwd_warps" (8 (default) or 16 warps per CTA in the Psi2 backward kernel), "bwd_mbar" (1 = the 8-warp
- * kernel with split-phase tile hand-off instead of a CTA barrier per row, Q <= 64), "bwd_strip" (1 = the
- * strip variant of that kernel with split-phase tile hand-off, Q in (16, 64]), "profile" (1 = record a
- * CUDA-event pair around every kernel launch).  Tuning / experiment knobs, not for production:
- * "fwd_smem_pad", "debug_skip", "trace_ptr". */
+ * "bwd_pipe" (1 (default) = software-pipelined Psi2 backward kernel, 0 = the row-at-a-time kernel it
+ * replaced, kept for A/B measurements), "profile" (1 = record a CUDA-event pair around every kernel
+ * launch).  Experiment knobs that change results or occupancy ("debug_skip", "fwd_smem_pad") exist only
+ * in libraries compiled with -DRGP_DEBUG. */
 int rgp_psi_set_option(rgp_psi_handle_t h, const char* key, int64_t value);
 
 /* ---- forward: Psi0 (optional N-vector), Psi1 (optional), Psi2 -------------------

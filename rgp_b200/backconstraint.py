@@ -37,13 +37,18 @@ class _FreeRun(torch.autograd.Function):
         lw.handle.mlp_freerun(lw._stream(), lw.nseq, lw.desc.data_ptr(), lw.X_win, lw.X_dim, lw.U_win, lw.U_dim,
                               mod.units, flat.data_ptr(), lat.data_ptr(), ctl.data_ptr() if ctl is not None else None,
                               acts.data_ptr())
-        ctx.mod, ctx.saved = mod, (flat, lat, ctl, acts)
+        # save_for_backward (not a plain attribute): the output `lat` is among the saved tensors, and a
+        # Python attribute would close an output -> grad_fn -> ctx -> output cycle the GC cannot see
+        ctx.mod, ctx.has_ctl = mod, ctl is not None
+        ctx.save_for_backward(flat, lat, acts, *((ctl,) if ctl is not None else ()))
         ctx.init_shape = init_means.shape
         return lat
 
     @staticmethod
     def backward(ctx, g_lat):
-        mod, (flat, lat, ctl, acts) = ctx.mod, ctx.saved
+        mod = ctx.mod
+        flat, lat, acts = ctx.saved_tensors[:3]
+        ctl = ctx.saved_tensors[3] if ctx.has_ctl else None
         lw: LagWindow = mod.lag
         g = g_lat.contiguous().clone()                              # updated in place by the kernel
         g_ctl = torch.zeros_like(ctl) if ctl is not None else None

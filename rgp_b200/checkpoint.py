@@ -147,10 +147,13 @@ class _Reader:
             fver, nf = self.b[fb], self.b[fb + 1]
             p = fb + (8 if fver == 1 else 2)
             for _ in range(nf):
-                fid, nlen, _fl, ncd = self.u16(p), self.u16(p + 2), self.u16(p + 4), self.u16(p + 6)
-                p += 8
-                if fver == 1 or fid >= 256:
-                    p += (nlen + 7) // 8 * 8 if fver == 1 else nlen
+                fid = self.u16(p)
+                if fver == 1 or fid >= 256:          # id, name length, flags, #client values, name
+                    nlen, ncd = self.u16(p + 2), self.u16(p + 6)
+                    p += 8 + ((nlen + 7) // 8 * 8 if fver == 1 else nlen)
+                else:                                # version 2, library filter: NO name-length field
+                    ncd = self.u16(p + 4)            # id, flags, #client values
+                    p += 6
                 p += 4 * ncd
                 if fver == 1 and ncd % 2:
                     p += 4

@@ -39,12 +39,9 @@ struct rgp_psi_ctx {
   int64_t host_chunk = 0;  // rows per pipelined chunk of the *_host entry points (0 = 262144)
   cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;   // *_host pipeline streams
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_cmp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
-  int bwd_warps = 8;      // 8 (default: 2 % faster at the headline shape) or 16 warps per CTA in the Psi2 backward kernel
-  int bwd_mbar = 0;       // 1: 8-warp kernel with split-phase (mbarrier) tile hand-off (psi2_bwdm.cuh), QC <= 64
-  int bwd_strip = 0;      // 1: strip kernel with split-phase tile hand-off (psi2_bwds.cuh), QC = 32 / 64
-  long long* trace = nullptr;   // optional device buffer for the bwd16 timeline trace (16*16*8 int64)
-  int debug_skip = 0;     // timing experiments only (see psi2_bwd16.cuh); 0 in production
-  int fwd_smem_pad = 0;   // tuning knob: extra dynamic smem for k_psi2_fwd (forces 1 CTA/SM)
+  int bwd_pipe = 1;       // 1 (default): software-pipelined Psi2 backward kernel (psi2_bwdp.cuh); 0: row-at-a-time kernel
+  int debug_skip = 0;     // timing experiments only, settable in RGP_DEBUG builds; always 0 in production
+  int fwd_smem_pad = 0;   // tuning knob (RGP_DEBUG builds): extra dynamic smem for k_psi2_fwd (forces 1 CTA/SM)
   // device workspace arena (grow-only) and a bump pointer valid for one call
   char* ws = nullptr;
   size_t ws_bytes = 0;

@@ -5,9 +5,7 @@
 #include "context.cuh"
 #include "fast_prep.cuh"
 #include "psi2_kernels.cuh"
-#include "psi2_bwd16.cuh"
-#include "psi2_bwds.cuh"
-#include "psi2_bwdm.cuh"
+#include "psi2_bwdp.cuh"
 
 namespace rgp {
 namespace fast {
@@ -17,25 +15,26 @@ static inline bool supported(int M, int Q) { return Q >= 1 && Q <= 128 && M >= 1
 static inline bool fused_supported(int Q) { return Q <= 64; }
 static inline int qc_for(int Q) { return Q <= 16 ? 16 : (Q <= 32 ? 32 : (Q <= 64 ? 64 : 128)); }
 
+template <int QC>
+static int init_qc() {
+  RGP_CUDA(cudaFuncSetAttribute(k_psi2_fwd<QC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                P2Cfg<QC>::FWD_SMEM + (QC == 64 ? 65536 : 0)));
+  RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwd<QC>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<QC>::BWD_SMEM));
+  RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwdp<QC>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2CfgP<QC>::SMEM));
+  if constexpr (QC <= 64) {
+    RGP_CUDA(cudaFuncSetAttribute((k_psi2_bwd<QC, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  P2Cfg<QC>::BWD_FUSED_SMEM));
+    RGP_CUDA(cudaFuncSetAttribute((k_psi2_bwdp<QC, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  P2CfgP<QC>::FUSED_SMEM));
+  }
+  return 0;
+}
+
 static int init(rgp_psi_ctx*) {
-  RGP_CUDA(cudaFuncSetAttribute(k_psi2_fwd<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<16>::FWD_SMEM));
-  RGP_CUDA(cudaFuncSetAttribute(k_psi2_fwd<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<32>::FWD_SMEM));
-  RGP_CUDA(cudaFuncSetAttribute(k_psi2_fwd<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<64>::FWD_SMEM + 65536));
-  RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwd<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<16>::BWD_SMEM));
-  RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwd<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<32>::BWD_SMEM));
-  RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwd<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<64>::BWD_SMEM));
-  RGP_CUDA(cudaFuncSetAttribute((k_psi2_bwd<16, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<16>::BWD_FUSED_SMEM));
-  RGP_CUDA(cudaFuncSetAttribute((k_psi2_bwd<32, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<32>::BWD_FUSED_SMEM));
-  RGP_CUDA(cudaFuncSetAttribute((k_psi2_bwd<64, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<64>::BWD_FUSED_SMEM));
-  RGP_CUDA(cudaFuncSetAttribute(k_psi2_fwd<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<128>::FWD_SMEM));
-  RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwd<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<128>::BWD_SMEM));
-  RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwd16<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg16<32>::BWD_SMEM));
-  RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwd16<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg16<64>::BWD_SMEM));
-  RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwdm<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2CfgM<16>::SMEM));
-  RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwdm<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2CfgM<32>::SMEM));
-  RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwdm<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2CfgM<64>::SMEM));
-  RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwds<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2CfgS<32>::SMEM));
-  RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwds<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2CfgS<64>::SMEM));
+  RGP_TRY(init_qc<16>());
+  RGP_TRY(init_qc<32>());
+  RGP_TRY(init_qc<64>());
+  RGP_TRY(init_qc<128>());
   return 0;
 }
 
@@ -106,35 +105,27 @@ template <int QC>
 static int launch_bwd(rgp_psi_ctx* h, cudaStream_t st, const Shape& s, int64_t rows, int R, int G,
                       const double* Zt, const double* Ct, const double* w, const double* HP,
                       double* lam, double* Wq, double* ACCp, double* P2p) {
+  // bwd_pipe = 1 (default): the software-pipelined kernel (psi2_bwdp.cuh); 0: the row-at-a-time kernel
+  const bool pipe = h->bwd_pipe != 0;
   if constexpr (QC == 128) {
     if (P2p) return set_error(RGP_PSI_ERR_INVALID, "fused pass is not built for Q > 64");
-  } else if (P2p) {   // fused forward + backward: the 8-warp kernel also accumulates the Psi2 partial tiles
-    RGP_LAUNCH(h, st, "psi2_bwd_fused", (k_psi2_bwd<QC, true>), dim3(R, G), P2_THREADS, P2Cfg<QC>::BWD_FUSED_SMEM,
-               rows, s.Mp, s.nt, s.nblocks, s.qk, Zt, Ct, w, HP, lam, Wq, ACCp, 0, P2p);
+  } else if (P2p) {   // fused forward + backward: the kernel also accumulates the Psi2 partial tiles
+    if (pipe)
+      RGP_LAUNCH(h, st, "psi2_bwd_fused", (k_psi2_bwdp<QC, true>), dim3(R, G), P2_THREADS, P2CfgP<QC>::FUSED_SMEM,
+                 rows, s.Mp, s.nt, s.nblocks, s.qk, Zt, Ct, w, HP, lam, Wq, ACCp, 0, P2p);
+    else
+      RGP_LAUNCH(h, st, "psi2_bwd_fused", (k_psi2_bwd<QC, true>), dim3(R, G), P2_THREADS, P2Cfg<QC>::BWD_FUSED_SMEM,
+                 rows, s.Mp, s.nt, s.nblocks, s.qk, Zt, Ct, w, HP, lam, Wq, ACCp, 0, P2p);
     return 0;
   }
-  if constexpr (QC <= 64) {
-    if (h->bwd_mbar) {
-      RGP_LAUNCH(h, st, "psi2_bwd", (k_psi2_bwdm<QC>), dim3(R, G), P2_THREADS, P2CfgM<QC>::SMEM, rows, s.Mp, s.nt,
-                 s.nblocks, s.qk, Zt, Ct, w, HP, lam, Wq, ACCp, 0, h->debug_skip);
-      return 0;
-    }
+  for (int qoff = 0; qoff < QC; qoff += P2Cfg<QC>::QS) {   // two passes for QC = 128
+    if (pipe)
+      RGP_LAUNCH(h, st, "psi2_bwd", (k_psi2_bwdp<QC>), dim3(R, G), P2_THREADS, P2CfgP<QC>::SMEM, rows,
+                 s.Mp, s.nt, s.nblocks, s.qk, Zt, Ct, w, HP, lam, Wq, ACCp, qoff, (double*)nullptr);
+    else
+      RGP_LAUNCH(h, st, "psi2_bwd", (k_psi2_bwd<QC>), dim3(R, G), P2_THREADS, P2Cfg<QC>::BWD_SMEM, rows,
+                 s.Mp, s.nt, s.nblocks, s.qk, Zt, Ct, w, HP, lam, Wq, ACCp, qoff, (double*)nullptr);
   }
-  if constexpr (QC == 32 || QC == 64) {
-    if (h->bwd_strip) {
-      RGP_LAUNCH(h, st, "psi2_bwd", (k_psi2_bwds<QC>), dim3(R, G), SW * 32, P2CfgS<QC>::SMEM, rows, s.Mp, s.nt,
-                 s.nblocks, s.qk, Zt, Ct, w, HP, lam, Wq, ACCp, 0);
-      return 0;
-    }
-    if (h->bwd_warps == 16) {
-      RGP_LAUNCH(h, st, "psi2_bwd", (k_psi2_bwd16<QC>), dim3(R, G), P2_THREADS16, P2Cfg16<QC>::BWD_SMEM, rows,
-                 s.Mp, s.nt, s.nblocks, s.qk, Zt, Ct, w, HP, lam, Wq, ACCp, h->debug_skip, h->trace);
-      return 0;
-    }
-  }
-  for (int qoff = 0; qoff < QC; qoff += P2Cfg<QC>::QS)   // two passes for QC = 128
-    RGP_LAUNCH(h, st, "psi2_bwd", (k_psi2_bwd<QC>), dim3(R, G), P2_THREADS, P2Cfg<QC>::BWD_SMEM, rows,
-               s.Mp, s.nt, s.nblocks, s.qk, Zt, Ct, w, HP, lam, Wq, ACCp, qoff, (double*)nullptr);
   return 0;
 }
 

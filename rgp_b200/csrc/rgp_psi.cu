@@ -35,6 +35,8 @@ static int check_common(rgp_psi_ctx* h, int64_t N, int M, int Q, const void* mu,
   if (!(variance > 0.0)) return set_error(RGP_PSI_ERR_INVALID, "variance must be positive");
   if ((int64_t)M * M > (int64_t)1 << 30)
     return set_error(RGP_PSI_ERR_INVALID, "M = %d too large", M);
+  if (Q > RGP_PSI_MAX_Q)
+    return set_error(RGP_PSI_ERR_INVALID, "Q = %d is larger than the supported maximum of %d", Q, RGP_PSI_MAX_Q);
   return 0;
 }
 
@@ -95,8 +97,6 @@ static int backward(rgp_psi_ctx* h, cudaStream_t st, int64_t N, int M, int Q, co
                     const double* S, const double* Z, const double* ell, double variance,
                     const double* dL0, double dL0c, const double* dL1, const double* dL2,
                     double* dmu, double* dS, double* dZ, double* dell, double* dvar) {
-  if (Q > 128)
-    return set_error(RGP_PSI_ERR_INVALID, "reference backward supports Q <= 128 (got %d)", Q);
   const int64_t rc = pick_chunk(h, N, M, Q);
   size_t need = bump_size(rc, 8) * 2 + bump_size(rc * Q, 8) + bump_size((size_t)M * M, 8) * 3 +
                 bump_size(rc * M, 8);
@@ -234,21 +234,18 @@ int rgp_psi_set_option(rgp_psi_handle_t h, const char* key, int64_t value) {
     h->host_chunk = value;
   } else if (!strcmp(key, "profile")) {
     h->profile = value != 0;
-  } else if (!strcmp(key, "bwd_warps")) {
-    if (value != 8 && value != 16) return set_error(RGP_PSI_ERR_INVALID, "bwd_warps must be 8 or 16");
-    h->bwd_warps = (int)value;
-  } else if (!strcmp(key, "bwd_mbar")) {
-    if (value != 0 && value != 1) return set_error(RGP_PSI_ERR_INVALID, "bwd_mbar must be 0 or 1");
-    h->bwd_mbar = (int)value;
-  } else if (!strcmp(key, "bwd_strip")) {
-    if (value != 0 && value != 1) return set_error(RGP_PSI_ERR_INVALID, "bwd_strip must be 0 or 1");
-    h->bwd_strip = (int)value;
-  } else if (!strcmp(key, "trace_ptr")) {
-    h->trace = (long long*)(uintptr_t)value;
+  } else if (!strcmp(key, "bwd_pipe")) {
+    if (value != 0 && value != 1) return set_error(RGP_PSI_ERR_INVALID, "bwd_pipe must be 0 or 1");
+    h->bwd_pipe = (int)value;
+#ifdef RGP_DEBUG
+  // experiment knobs: they make kernels skip work (wrong results) or change occupancy, so the
+  // production library does not know them
   } else if (!strcmp(key, "debug_skip")) {
     h->debug_skip = (int)value;
   } else if (!strcmp(key, "fwd_smem_pad")) {
+    if (value < 0 || value > 100000) return set_error(RGP_PSI_ERR_INVALID, "fwd_smem_pad must be in [0, 100000]");
     h->fwd_smem_pad = (int)value;
+#endif
   } else {
     return set_error(RGP_PSI_ERR_INVALID, "unknown option '%s'", key);
   }

@@ -13,6 +13,7 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from ._lib import Handle
+from .device import _check
 
 
 class LagWindow:
@@ -52,8 +53,15 @@ class LagWindow:
     def gather(self, lat: torch.Tensor, ctl: Optional[torch.Tensor] = None,
                out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """lat [lat_total, X_dim] (means or variances), ctl [ctl_total, U_dim] -> X [N, Q]."""
+        if self.X_win:
+            _check(lat, "lat", (self.lat_total, self.X_dim))
+        if self.U_win:
+            if ctl is None:
+                raise ValueError("this window has a control part: ctl is required")
+            _check(ctl, "ctl", (self.ctl_total, self.U_dim))
         if out is None:
             out = torch.empty((self.N, self.Q), dtype=torch.float64, device=self.device)
+        _check(out, "out", (self.N, self.Q))
         self.handle.lag_gather(self._stream(), self.nseq, self.desc.data_ptr(), self.N, self.X_win, self.X_dim,
                                self.U_win, self.U_dim, lat.data_ptr() if self.X_win else None,
                                ctl.data_ptr() if (ctl is not None and self.U_win) else None, out.data_ptr())
@@ -65,6 +73,11 @@ class LagWindow:
         """Adds dX [N, Q] onto lat_grad [lat_total, X_dim] / ctl_grad [ctl_total, U_dim], every
         element in the reference's order of ``+=`` (layers.py:552-571).  Omitted targets are
         allocated as zeros (``allocate=True``) or skipped."""
+        _check(dX, "dX", (self.N, self.Q))
+        if lat_grad is not None:
+            _check(lat_grad, "lat_grad", (self.lat_total, self.X_dim))
+        if ctl_grad is not None:
+            _check(ctl_grad, "ctl_grad", (self.ctl_total, self.U_dim))
         if lat_grad is None and allocate and self.X_win:
             lat_grad = torch.zeros((self.lat_total, self.X_dim), dtype=torch.float64, device=self.device)
         if ctl_grad is None and allocate and self.U_win:
@@ -85,9 +98,13 @@ class LagWindow:
         cols = 1 if dL_dYvar.dim() == 1 else int(dL_dYvar.shape[1])
         if tuple(dL_dYmean.shape) != (self.N, D) or dL_dYvar.shape[0] != self.N or cols not in (1, D):
             raise ValueError("dL_dYmean must be [N, D] and dL_dYvar [N] or [N, D]")
+        _check(lat_mean, "lat_mean", (self.lat_total, D))
+        _check(lat_var, "lat_var", (self.lat_total, D))
         gm, gv = torch.empty_like(lat_mean), torch.empty_like(lat_var)
         val = torch.empty((), dtype=torch.float64, device=self.device)
         dym, dyv = dL_dYmean.contiguous(), dL_dYvar.contiguous()
+        _check(dym, "dL_dYmean")
+        _check(dyv, "dL_dYvar")
         self.handle.latent_terms(self._stream(), self.nseq, self.desc.data_ptr(), self.X_win, D,
                                  lat_mean.data_ptr(), lat_var.data_ptr(), self.lat_total,
                                  dym.data_ptr(), dyv.data_ptr(), cols, gm.data_ptr(), gv.data_ptr(), val.data_ptr())

@@ -19,6 +19,8 @@ the first call raises.
 from __future__ import annotations
 
 import ctypes as C
+import hashlib
+import os
 from typing import Optional
 
 import numpy as np
@@ -37,17 +39,45 @@ def _ptr(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+# ---------------------------------------------------------------------------------------
+# Cache key.  GPy wraps both psicomp methods in ``Cache_this(limit=10)`` and the three forward
+# accessors / three gradient accessors of one ELBO evaluation rely on it.  GPy's cacher is valid
+# because it subscribes to paramz change notifications; without paramz the only valid key is the
+# CONTENT: the layer rewrites X.mean / X.variance in place every evaluation (layers.py:528-550)
+# - with the same rows in a new order in the permuted-minibatch tests
+# (testing/minibatch_tests.py:281-296) - and paramz mutates Z / lengthscale / variance in place.
+# So the key is an ORDER-SENSITIVE cryptographic digest of the raw bytes (blake2b; slices of
+# large arrays are hashed on a thread pool - hashlib releases the GIL - and the slice digests
+# are hashed in order).  A wrapping sum / XOR of the words, which round 1 used, is permutation
+# invariant and returned stale row-ordered results.
+# ---------------------------------------------------------------------------------------
+_HASH_SLICE = 8 << 20            # bytes per pool task
+_pool = None
+
+
+def _hash_pool():
+    global _pool
+    if _pool is None:
+        from concurrent.futures import ThreadPoolExecutor
+        n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        _pool = ThreadPoolExecutor(max_workers=max(1, min(32, n)), thread_name_prefix="rgp-hash")
+    return _pool
+
+
+def _digest(a: np.ndarray) -> bytes:
+    buf = memoryview(np.ascontiguousarray(a)).cast("B")
+    if buf.nbytes <= 2 * _HASH_SLICE:
+        return hashlib.blake2b(buf, digest_size=16).digest()
+    parts = [buf[o:o + _HASH_SLICE] for o in range(0, buf.nbytes, _HASH_SLICE)]
+    top = hashlib.blake2b(digest_size=16)
+    for d in _hash_pool().map(lambda b: hashlib.blake2b(b, digest_size=16).digest(), parts):
+        top.update(d)                       # slice digests in slice order: order-sensitive
+    return top.digest()
+
+
 def _fingerprint(*arrays) -> tuple:
-    """Content fingerprint (shape + wrapping sum + xor of the raw 64-bit words).  The
-    layer mutates X.mean / X.variance IN PLACE every evaluation (layers.py:537-543) and
-    paramz mutates Z / lengthscale / variance in place, so array identity cannot key
-    the cache ("Memoisation")."""
-    out = []
-    for a in arrays:
-        w = a.reshape(-1).view(np.uint64)
-        out.append((a.shape, int(np.add.reduce(w, dtype=np.uint64)) if w.size else 0,
-                    int(np.bitwise_xor.reduce(w)) if w.size else 0))
-    return tuple(out)
+    """Order-sensitive content fingerprint: (shape, blake2b-128 of the bytes) per array."""
+    return tuple((a.shape, _digest(a)) for a in arrays)
 
 
 class PSICOMP_RBF_B200(object):
@@ -59,15 +89,22 @@ class PSICOMP_RBF_B200(object):
     impl   : 'auto' | 'fast' | 'reference' - kernel family (see include/rgp_psi.h).
     cache  : keep the last forward / backward result, as GPy's ``Cache_this`` does; the
              three forward accessors and the three gradient accessors of one ELBO
-             evaluation then cost one device evaluation each.
+             evaluation then cost one device evaluation each.  Keyed on an order-sensitive
+             digest of the input bytes (see ``_fingerprint``).
+    cache_copy_bytes : results up to this many bytes are handed out as fresh copies (a caller
+             may then mutate what it got).  Above it the cached arrays THEMSELVES are returned
+             on a hit - exactly what GPy's cacher does (it returns the stored tuple) - so an
+             N x M Psi1 of 17 GB is neither duplicated in host memory nor copied per accessor.
     """
 
-    def __init__(self, device: int = 0, impl: str = "auto", cache: bool = True):
+    def __init__(self, device: int = 0, impl: str = "auto", cache: bool = True,
+                 cache_copy_bytes: int = 64 << 20):
         if impl not in _IMPL:
             raise ValueError("impl must be one of %s" % sorted(_IMPL))
         self.device = int(device)
         self.impl = impl
         self.cache = bool(cache)
+        self.cache_copy_bytes = int(cache_copy_bytes)
         self._handle = Handle(self.device)
         self._handle.set_option("impl", _IMPL[impl])
         self._fwd_key = self._fwd_val = None
@@ -75,13 +112,27 @@ class PSICOMP_RBF_B200(object):
 
     # pickling / deepcopy: drop device state and cached arrays (ownership)
     def __getstate__(self):
-        return {"device": self.device, "impl": self.impl, "cache": self.cache}
+        return {"device": self.device, "impl": self.impl, "cache": self.cache,
+                "cache_copy_bytes": self.cache_copy_bytes}
 
     def __setstate__(self, state):
         self.__init__(**state)
 
     def __deepcopy__(self, memo):
-        return PSICOMP_RBF_B200(self.device, self.impl, self.cache)
+        return PSICOMP_RBF_B200(self.device, self.impl, self.cache, self.cache_copy_bytes)
+
+    # cache entries: (values, copy?) - small results are stored and handed out as copies, large
+    # ones by reference (GPy's Cache_this semantics)
+    def _store(self, vals):
+        nbytes = sum(a.nbytes for a in vals if isinstance(a, np.ndarray))
+        if nbytes <= self.cache_copy_bytes:
+            return tuple(a.copy() if isinstance(a, np.ndarray) else a for a in vals), True
+        return tuple(vals), False
+
+    @staticmethod
+    def _hand_out(entry):
+        vals, copy = entry
+        return tuple(a.copy() if (copy and isinstance(a, np.ndarray)) else a for a in vals)
 
     @property
     def handle(self) -> Handle:
@@ -130,7 +181,7 @@ class PSICOMP_RBF_B200(object):
         if self.cache:
             key = (var,) + _fingerprint(ell, Z, mu, S)
             if key == self._fwd_key:
-                return tuple(a.copy() for a in self._fwd_val)
+                return self._hand_out(self._fwd_val)
         N, Q = mu.shape
         M = Z.shape[0]
         if N == 0:      # no rows: sums over the empty set (what GPy's numpy code returns); nothing to launch
@@ -141,7 +192,7 @@ class PSICOMP_RBF_B200(object):
         self._handle.forward_host(N, M, Q, _ptr(mu), _ptr(S), _ptr(Z), _ptr(ell), var,
                                   _ptr(psi0), _ptr(psi1), _ptr(psi2))
         if self.cache:
-            self._fwd_key, self._fwd_val = key, (psi0.copy(), psi1.copy(), psi2.copy())
+            self._fwd_key, self._fwd_val = key, self._store((psi0, psi1, psi2))
         return psi0, psi1, psi2
 
     # ----------------------------------------------------------------------- backward
@@ -158,8 +209,13 @@ class PSICOMP_RBF_B200(object):
         var, ell, ard, Z, mu, S = self._prepare(variance, lengthscale, Z, vp)
         N, Q = mu.shape
         M = Z.shape[0]
-        dL0 = np.ascontiguousarray(np.broadcast_to(_f64(dL0).reshape(-1) if np.ndim(dL0) else
-                                                   np.float64(dL0), (N,)))
+        dL0c = 0.0
+        if np.size(dL0) == 1:                     # a constant dL_dpsi0 (vardtc.py:175: -D beta/2 for every row)
+            dL0c, dL0 = float(np.asarray(dL0, dtype=np.float64).reshape(-1)[0]), None
+        else:
+            dL0 = _f64(dL0).reshape(-1)
+            if dL0.shape != (N,):
+                raise ValueError("dL_dpsi0 has %d entries for N=%d" % (dL0.size, N))
         dL1 = _f64(dL1)
         dL2 = _f64(dL2)
         if dL1.shape != (N, M) or dL2.shape != (M, M):
@@ -169,21 +225,19 @@ class PSICOMP_RBF_B200(object):
             return 0.0, np.zeros(Q if ard else 1), np.zeros((M, Q)), np.empty((0, Q)), np.empty((0, Q))
         key = None
         if self.cache:
-            key = (var,) + _fingerprint(ell, Z, mu, S, dL0, dL1, dL2)
+            key = (var, dL0c) + _fingerprint(ell, Z, mu, S, dL1, dL2) + (() if dL0 is None else _fingerprint(dL0))
             if key == self._bwd_key:
-                v = self._bwd_val
-                return (v[0],) + tuple(a.copy() for a in v[1:])
+                return self._hand_out(self._bwd_val)
         dmu = np.empty((N, Q))
         dS = np.empty((N, Q))
         dZ = np.empty((M, Q))
         dell = np.empty(Q)
         dvar = np.empty(1)
         self._handle.backward_host(N, M, Q, _ptr(mu), _ptr(S), _ptr(Z), _ptr(ell), var,
-                                   _ptr(dL0), 0.0, _ptr(dL1), _ptr(dL2),
+                                   _ptr(dL0), dL0c, _ptr(dL1), _ptr(dL2),
                                    _ptr(dmu), _ptr(dS), _ptr(dZ), _ptr(dell), _ptr(dvar))
         dl = dell if ard else np.array([dell.sum()])
         out = (float(dvar[0]), dl, dZ, dmu, dS)
         if self.cache:
-            self._bwd_key = key
-            self._bwd_val = (out[0],) + tuple(a.copy() for a in out[1:])
+            self._bwd_key, self._bwd_val = key, self._store(out)
         return out

@@ -27,7 +27,9 @@ def row_partition(N: int, world_size: int, rank: int, align: int = 1,
     Blocks differ by at most ``align`` rows.  If ``boundaries`` (sorted row indices where
     sequences start, autoreg/layers.py:481-482 stacks sequences row-wise) is given, cuts
     snap to the nearest boundary so the later latent-gradient scatter
-    (layers.py:552-571) needs no halo.
+    (layers.py:552-571) needs no halo.  Snapping is strictly monotone: every rank keeps at least
+    one whole sequence, and a world larger than the number of sequences raises on EVERY rank (the
+    same arguments give the same answer everywhere), so no rank can enter a collective alone.
     """
     if not (0 <= rank < world_size):
         raise ValueError("rank %d outside world of %d" % (rank, world_size))
@@ -37,12 +39,20 @@ def row_partition(N: int, world_size: int, rank: int, align: int = 1,
     for r in range(world_size):
         cuts.append(cuts[-1] + (base + (1 if r < extra else 0)) * align)
     cuts = [min(c, N) for c in cuts]
-    if boundaries:
-        b = sorted(set(int(x) for x in boundaries) | {0, N})
-        snapped = [0]
-        for c in cuts[1:-1]:
-            snapped.append(max(min(b, key=lambda x: abs(x - c)), snapped[-1]))
-        cuts = snapped + [N]
+    if boundaries is not None and len(boundaries):
+        b = sorted(set(int(x) for x in boundaries if 0 < int(x) < N) | {0, N})
+        nseq = len(b) - 1
+        if nseq < world_size:
+            raise ValueError("cannot give each of %d ranks a whole sequence: only %d sequences" % (world_size, nseq))
+        idx = [0]                                   # indices into b, strictly increasing
+        for r, c in enumerate(cuts[1:-1], start=1):
+            k = min(range(len(b)), key=lambda i: abs(b[i] - c))
+            k = max(k, idx[-1] + 1)                  # at least one sequence for rank r-1
+            k = min(k, nseq - (world_size - r))      # and one for every rank still to come
+            idx.append(k)
+        cuts = [b[i] for i in idx] + [N]
+    elif N < world_size:
+        raise ValueError("cannot shard %d rows over %d ranks" % (N, world_size))
     return cuts[rank], cuts[rank + 1]
 
 

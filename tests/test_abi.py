@@ -98,6 +98,56 @@ def test_fingerprint_sees_in_place_mutation():
     assert _fingerprint(a.copy()) == _fingerprint(a)
 
 
+def test_fingerprint_is_order_sensitive():
+    """The layer rewrites X in place with the same rows in a NEW ORDER in the reference's permuted
+    minibatch tests (testing/minibatch_tests.py:281-296, autoreg/layers.py:528-550): a row permutation,
+    a swap of two rows and a swap of two elements must all change the key (round 1's sum/xor key did not)."""
+    rng = np.random.default_rng(3)
+    mu, S = rng.normal(size=(50, 7)), rng.uniform(0.1, 1, size=(50, 7))
+    f0 = _fingerprint(mu, S)
+    perm = rng.permutation(50)
+    assert _fingerprint(mu[perm], S[perm]) != f0
+    assert _fingerprint(mu[::-1], S) != f0
+    mu2 = mu.copy()
+    mu2[[3, 17]] = mu2[[17, 3]]                       # two rows of mu alone
+    assert _fingerprint(mu2, S) != f0
+    mu3 = mu.copy()
+    mu3[4, 1], mu3[4, 2] = mu3[4, 2], mu3[4, 1]       # two elements
+    assert _fingerprint(mu3, S) != f0
+    mu.flat[:] = mu[perm].ravel()                     # in place, same object
+    assert _fingerprint(mu, S) != f0
+    assert _fingerprint(mu.reshape(7, 50)) != _fingerprint(mu)          # shape is part of the key
+
+
+def test_fingerprint_large_arrays_are_hashed_in_ordered_slices(monkeypatch):
+    """Arrays above two hash slices go through the thread pool; swapping two SLICES (a permutation of
+    whole blocks) must still change the key, and the key must not depend on the slice size being
+    hit exactly."""
+    import rgp_b200.psicomp as pcm
+    monkeypatch.setattr(pcm, "_HASH_SLICE", 1 << 10)
+    a = np.arange(4096, dtype=np.float64)               # 32 KiB = 32 slices of 1 KiB
+    f0 = pcm._fingerprint(a)
+    b = a.copy()
+    b[:128], b[128:256] = a[128:256], a[:128]           # exchange the first two slices
+    assert pcm._fingerprint(b) != f0
+    assert pcm._fingerprint(a.copy()) == f0
+    c = np.arange(4096 + 5, dtype=np.float64)           # ragged last slice
+    assert pcm._fingerprint(c) == pcm._fingerprint(c.copy()) != f0
+
+
+def test_cache_hands_out_copies_below_the_threshold_and_the_stored_arrays_above():
+    pc = PSICOMP_RBF_B200(cache=True, cache_copy_bytes=100)
+    small = (np.zeros(3), 1.5)
+    entry = pc._store(small)
+    out = pc._hand_out(entry)
+    assert out[0] is not small[0] and entry[0][0] is not small[0] and out[1] == 1.5
+    big = (np.zeros(100),)
+    entry = pc._store(big)
+    assert pc._hand_out(entry)[0] is big[0]             # GPy's Cache_this returns the stored object
+    k = pickle.loads(pickle.dumps(pc))
+    assert k.cache_copy_bytes == 100
+
+
 def test_inv_lengthscale_chain_rule_matches_reference_kernels():
     kern = RBF(2, ARD=True, inv_l=True, lengthscale=[2.0, 0.5])
     np.testing.assert_allclose(kern.lengthscale, [2.0, 0.5])

@@ -25,14 +25,10 @@ IMPLS = ["reference", "fast"]
 @pytest.fixture(scope="module")
 def plugins():
     from rgp_b200.psicomp import PSICOMP_RBF_B200
-    p16 = PSICOMP_RBF_B200(impl="auto", cache=False)
-    p16.handle.set_option("bwd_warps", 16)            # the 16-warp backward kernel (the default is 8 warps)
-    ps = PSICOMP_RBF_B200(impl="auto", cache=False)
-    ps.handle.set_option("bwd_strip", 1)             # the strip backward kernel (split-phase tile hand-off)
-    pm = PSICOMP_RBF_B200(impl="auto", cache=False)
-    pm.handle.set_option("bwd_mbar", 1)              # 8-warp kernel, split-phase hand-off instead of a barrier per row
+    rowloop = PSICOMP_RBF_B200(impl="auto", cache=False)
+    rowloop.handle.set_option("bwd_pipe", 0)          # the row-at-a-time backward kernel (default: software-pipelined)
     return {"reference": PSICOMP_RBF_B200(impl="reference", cache=False),
-            "fast": PSICOMP_RBF_B200(impl="auto", cache=False), "fast16": p16, "strip": ps, "mbar": pm}
+            "fast": PSICOMP_RBF_B200(impl="auto", cache=False), "rowloop": rowloop}
 
 
 def _kern(pc, var, ell, ard=True):
@@ -76,7 +72,7 @@ SHAPES = [
 ]
 
 
-@pytest.mark.parametrize("impl", IMPLS + ["fast16", "strip", "mbar"])
+@pytest.mark.parametrize("impl", IMPLS + ["rowloop"])
 @pytest.mark.parametrize("N,M,Q,nc", SHAPES)
 def test_forward_and_backward_match_oracle(plugins, impl, N, M, Q, nc):
     var, ell, Z, mu, S = make_inputs(N, M, Q, seed=100 + N + M + Q, n_control=nc)
@@ -85,7 +81,7 @@ def test_forward_and_backward_match_oracle(plugins, impl, N, M, Q, nc):
     _compare(fwd, bwd, psi_forward(var, ell, Z, mu, S), psi_backward(dL0, dL1, dL2, var, ell, Z, mu, S), TIGHT)
 
 
-@pytest.mark.parametrize("impl", IMPLS + ["strip", "mbar"])
+@pytest.mark.parametrize("impl", IMPLS + ["rowloop"])
 def test_headline_tile_shape_small_n(plugins, impl):
     # M=512, Q=64 (the headline kernel configuration) at an N the oracle finishes in seconds
     N, M, Q = 192, 512, 64
@@ -208,6 +204,52 @@ def test_plugin_cache_and_inplace_mutation(plugins):
     ob = psi_backward(dL0, dL1, dL2, var, kern.lengthscale, Z, X.mean, X.variance)
     assert relerr(dZ, ob[2]) < TIGHT and relerr(dmu, ob[3]) < TIGHT and relerr(dS, ob[4]) < TIGHT
     assert relerr(kern.inv_l_gradient, ob[1] * (kern.lengthscale ** 3 / -2.0)) < TIGHT
+
+
+def test_plugin_cache_sees_rows_permuted_in_place():
+    """testing/minibatch_tests.py:281-296 at plugin level: the layer rewrites X in place with the same
+    rows in a new order (autoreg/layers.py:528-550).  With the default cache the row-indexed results
+    (Psi1, dmu, dS) must come back in the NEW order against the new dL_dpsi1, and the row sums
+    (Psi2, dZ, dl, dvar) must not move (the reference asserts rtol 1e-14 on the bound, 1e-11 on the
+    gradients; both are asserted at 1e-12 here)."""
+    from rgp_b200.gpy_compat import RBF, NormalPosterior
+    from rgp_b200.psicomp import PSICOMP_RBF_B200
+    N, M, Q = 203, 37, 9
+    pc = PSICOMP_RBF_B200(cache=True)
+    var, ell, Z, mu, S = make_inputs(N, M, Q, seed=77, n_control=2)
+    dL0, dL1, dL2 = make_upstream(N, M)
+    kern = RBF(Q, var, ell, ARD=True, psicomp=pc)
+    X = NormalPosterior(mu, S)
+    p1, p2 = kern.psi1(Z, X), kern.psi2(Z, X)
+    kern.update_gradients_expectations(dL0, dL1, dL2, Z, X)
+    dvar, dl = kern.variance_gradient.copy(), kern.lengthscale_gradient.copy()
+    dZ = kern.gradients_Z_expectations(dL0, dL1, dL2, Z, X)
+    dmu, dS = kern.gradients_qX_expectations(dL0, dL1, dL2, Z, X)
+    n_before = pc.handle.launch_count()
+    perm = np.random.default_rng(5).permutation(N)
+    X.mean[:] = X.mean[perm]                                            # in place: same objects, same multiset of rows
+    X.variance[:] = X.variance[perm]
+    dL1[:] = dL1[perm]
+    q1, q2 = kern.psi1(Z, X), kern.psi2(Z, X)
+    assert pc.handle.launch_count() > n_before, "permuted rows were served from the cache"
+    kern.update_gradients_expectations(dL0, dL1, dL2, Z, X)
+    eZ = kern.gradients_Z_expectations(dL0, dL1, dL2, Z, X)
+    emu, eS = kern.gradients_qX_expectations(dL0, dL1, dL2, Z, X)
+    assert relerr(q1, p1[perm]) < 1e-12 and relerr(emu, dmu[perm]) < 1e-12 and relerr(eS, dS[perm]) < 1e-12
+    assert relerr(q1, p1) > 1e-3                                         # and NOT the stale order
+    assert relerr(q2, p2) < 1e-12 and relerr(eZ, dZ) < 1e-12
+    assert relerr(kern.lengthscale_gradient, dl) < 1e-12 and relerr(kern.variance_gradient, dvar) < 1e-12
+    # swapping two rows of the mean alone is also a new input
+    n_before = pc.handle.launch_count()
+    X.mean[[3, 17]] = X.mean[[17, 3]]
+    r1 = kern.psi1(Z, X)
+    assert pc.handle.launch_count() > n_before
+    assert relerr(r1, psi_forward(var, ell, Z, X.mean, X.variance)[1]) < TIGHT
+    # large results are handed out by reference (GPy's Cache_this), small ones as copies
+    pb = PSICOMP_RBF_B200(cache=True, cache_copy_bytes=0)
+    kb = RBF(Q, var, ell, ARD=True, psicomp=pb)
+    assert kb.psi1(Z, X) is pb.psicomputations(kb, Z, X)[1]
+    assert relerr(kb.psi1(Z, X), r1) < 1e-14
 
 
 def test_device_api_scalar_dL0_and_null_outputs():
@@ -353,8 +395,9 @@ def test_options_are_validated():
     from rgp_b200._lib import Handle
     h = Handle(0)
     h._ensure()
-    for key, val in (("impl", 7), ("bwd_warps", 12), ("row_chunk", -1), ("no_such_option", 1), ("bwd_strip", 2),
-                     ("bwd_mbar", -1)):
+    # the experiment knobs of round 1 (debug_skip, trace_ptr, fwd_smem_pad) are not options of the production library
+    for key, val in (("impl", 7), ("bwd_pipe", 2), ("row_chunk", -1), ("no_such_option", 1), ("debug_skip", 1),
+                     ("trace_ptr", 4096), ("fwd_smem_pad", 1024), ("bwd_warps", 16)):
         with pytest.raises(PsiError):
             h.set_option(key, val)
         assert key not in h._options

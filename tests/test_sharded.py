@@ -21,6 +21,10 @@ from synth import make_inputs, make_upstream, relerr
 def test_row_partition_covers_rows_exactly_once():
     for N in (1, 7, 64, 1000, 4194304):
         for w in (1, 2, 3, 4, 8):
+            if w > N:
+                with pytest.raises(ValueError):           # every rank raises, none enters a collective alone
+                    row_partition(N, w, 0)
+                continue
             cuts = [row_partition(N, w, r) for r in range(w)]
             assert cuts[0][0] == 0 and cuts[-1][1] == N
             for a, b in zip(cuts[:-1], cuts[1:]):
@@ -36,6 +40,28 @@ def test_row_partition_snaps_to_sequence_boundaries():
     # three sequences of 40, 25 and 35 rows stacked (layers.py:481-482)
     cuts = [row_partition(100, 2, r, boundaries=[0, 40, 65]) for r in range(2)]
     assert cuts == [(0, 40), (40, 100)]
+
+
+def test_row_partition_never_hands_out_an_empty_block():
+    """Snapping used to collapse cuts ([0, 0, 9, 9, 10] for N = 10, 4 ranks, boundaries [0, 9]): a rank
+    with zero rows then raised inside DevicePsi while its peers sat in all_reduce.  Now every rank
+    owns at least one sequence, or every rank raises."""
+    for r in range(4):
+        with pytest.raises(ValueError, match="only 2 sequences"):
+            row_partition(10, 4, r, boundaries=[0, 9])
+    rng = np.random.default_rng(0)
+    for trial in range(200):
+        nseq = int(rng.integers(1, 12))
+        lens = rng.integers(1, 50, size=nseq)
+        starts = np.concatenate([[0], np.cumsum(lens)[:-1]])
+        N = int(lens.sum())
+        for w in range(1, nseq + 1):
+            cuts = [row_partition(N, w, r, boundaries=starts) for r in range(w)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == N
+            for (a0, a1), (b0, b1) in zip(cuts[:-1], cuts[1:]):
+                assert a1 == b0
+            for a0, a1 in cuts:
+                assert a1 > a0 and a0 in set(starts.tolist()) | {N}
 
 
 def test_pack_unpack_roundtrip():

@@ -1,7 +1,7 @@
 """Tiny runs of every kernel family for compute-sanitizer (memcheck / racecheck / synccheck):
     compute-sanitizer --tool memcheck python tests/tools/sanitize_small.py
-Covers the default fast path, the 8-warp, split-phase (mbar) and strip backward kernels, the fused
-pass, the lag-window kernels and the latent-terms kernel; results are checked against the oracle."""
+Covers the default fast path (software-pipelined backward kernel with TMA row-vector staging), the
+row-at-a-time backward kernel, the fused pass, the lag-window kernels and the latent-terms kernel; results are checked against the oracle."""
 import os, sys
 import numpy as np
 import torch
@@ -14,11 +14,7 @@ from rgp_b200.lagwindow import LagWindow
 
 t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
 worst = 0.0
-# SANITIZE_SKIP_MBARRIER=1: leave out the two experimental kernels that synchronise through mbarrier phases
-# in inline PTX; racecheck does not model those and their reports fill its hazard list
-variants = [{}, {"bwd_warps": 8}]
-if not os.environ.get("SANITIZE_SKIP_MBARRIER"):
-    variants += [{"bwd_mbar": 1}, {"bwd_strip": 1}]
+variants = [{}, {"bwd_pipe": 0}]
 for opts in variants:
     dp = DevicePsi(0, impl=1)
     for k, v in opts.items():
