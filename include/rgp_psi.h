@@ -73,8 +73,9 @@ int rgp_psi_destroy(rgp_psi_handle_t h);
 
 /* Options: "impl" (rgp_psi_impl), "row_chunk" (rows per internal device pass, 0 = 2^20),
  * "host_chunk" (rows per pipelined host<->device chunk of the *_host calls, 0 = 262144),
- * "bwd_pipe" (1 (default) = software-pipelined Psi2 backward kernel, 0 = the row-at-a-time kernel it
- * replaced, kept for A/B measurements), "profile" (1 = record a CUDA-event pair around every kernel
+ * "bwd_pipe" (Psi2 backward kernel: 0 = row-at-a-time, 1 = software-pipelined with TMA row-vector
+ * staging, 2 (default) = row-at-a-time for the plain backward pass and pipelined for the fused pass,
+ * the measured faster choice for each), "profile" (1 = record a CUDA-event pair around every kernel
  * launch).  Experiment knobs that change results or occupancy ("debug_skip", "fwd_smem_pad") exist only
  * in libraries compiled with -DRGP_DEBUG. */
 int rgp_psi_set_option(rgp_psi_handle_t h, const char* key, int64_t value);

@@ -72,6 +72,20 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+DEBUG_LIB = os.path.join(LIBDIR, "librgp_psi_debug.so")
+
+
+def build_debug() -> str:
+    """Experiment build (-DRGP_DEBUG): the ablation / occupancy knobs of the timing probes exist only
+    here (scripts/bwd_ablate.py loads it through RGP_PSI_LIB); the product library does not have them."""
+    os.makedirs(LIBDIR, exist_ok=True)
+    cmd = [_nvcc(), *NVCC_FLAGS, "-DRGP_DEBUG", "-shared", "-o", DEBUG_LIB, os.path.join(CSRC, "rgp_psi.cu")]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    return DEBUG_LIB
+
+
 def build_microbench() -> str:
     """Standalone hardware microbenchmarks (DFMA / DMMA peaks, smem broadcast costs)."""
     os.makedirs(LIBDIR, exist_ok=True)

@@ -74,7 +74,8 @@ class PsiError(RuntimeError):
 
 
 def library_path() -> str:
-    return _build.LIB
+    """The in-tree product library; RGP_PSI_LIB points the timing probes at the -DRGP_DEBUG build."""
+    return os.environ.get("RGP_PSI_LIB") or _build.LIB
 
 
 def load(build_if_missing: bool = True) -> C.CDLL:
@@ -83,7 +84,10 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     if _lib is not None:
         return _lib
     path = library_path()
-    if not os.path.exists(path) or (build_if_missing and not _build.is_current()):
+    if path != _build.LIB:
+        if not os.path.exists(path):
+            raise OSError(f"RGP_PSI_LIB={path} does not exist")
+    elif not os.path.exists(path) or (build_if_missing and not _build.is_current()):
         if not build_if_missing:
             raise OSError(f"{path} is missing; run `python -m rgp_b200._build` "
                           "(there is no CPU fallback)")

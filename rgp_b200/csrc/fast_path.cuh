@@ -105,11 +105,14 @@ template <int QC>
 static int launch_bwd(rgp_psi_ctx* h, cudaStream_t st, const Shape& s, int64_t rows, int R, int G,
                       const double* Zt, const double* Ct, const double* w, const double* HP,
                       double* lam, double* Wq, double* ACCp, double* P2p) {
-  // bwd_pipe = 1 (default): the software-pipelined kernel (psi2_bwdp.cuh); 0: the row-at-a-time kernel
-  const bool pipe = h->bwd_pipe != 0;
+  // Two Psi2 backward kernels (profiles/SUMMARY_r02.md, "A/B"): the row-at-a-time kernel is 1.5 % faster for the
+  // plain backward pass, the software-pipelined one 3 % faster when the pass also accumulates Psi2 (fused).
+  // bwd_pipe: 2 = that choice (default), 0 / 1 = force one of them (A/B measurements, parity tests).
+  const bool fused = P2p != nullptr;
+  const bool pipe = h->bwd_pipe == 1 || (h->bwd_pipe == 2 && fused);
   if constexpr (QC == 128) {
-    if (P2p) return set_error(RGP_PSI_ERR_INVALID, "fused pass is not built for Q > 64");
-  } else if (P2p) {   // fused forward + backward: the kernel also accumulates the Psi2 partial tiles
+    if (fused) return set_error(RGP_PSI_ERR_INVALID, "fused pass is not built for Q > 64");
+  } else if (fused) {
     if (pipe)
       RGP_LAUNCH(h, st, "psi2_bwd_fused", (k_psi2_bwdp<QC, true>), dim3(R, G), P2_THREADS, P2CfgP<QC>::FUSED_SMEM,
                  rows, s.Mp, s.nt, s.nblocks, s.qk, Zt, Ct, w, HP, lam, Wq, ACCp, 0, P2p);
@@ -119,12 +122,26 @@ static int launch_bwd(rgp_psi_ctx* h, cudaStream_t st, const Shape& s, int64_t r
     return 0;
   }
   for (int qoff = 0; qoff < QC; qoff += P2Cfg<QC>::QS) {   // two passes for QC = 128
-    if (pipe)
+    if (pipe) {
       RGP_LAUNCH(h, st, "psi2_bwd", (k_psi2_bwdp<QC>), dim3(R, G), P2_THREADS, P2CfgP<QC>::SMEM, rows,
                  s.Mp, s.nt, s.nblocks, s.qk, Zt, Ct, w, HP, lam, Wq, ACCp, qoff, (double*)nullptr);
-    else
+    }
+#ifdef RGP_DEBUG
+#define RGP_ABL(D)                                                                                           \
+  else if (h->debug_skip == D) {                                                                             \
+    cudaFuncSetAttribute((k_psi2_bwd<QC, false, D>), cudaFuncAttributeMaxDynamicSharedMemorySize,            \
+                         P2Cfg<QC>::BWD_SMEM);                                                               \
+    RGP_LAUNCH(h, st, "psi2_bwd", (k_psi2_bwd<QC, false, D>), dim3(R, G), P2_THREADS, P2Cfg<QC>::BWD_SMEM,   \
+               rows, s.Mp, s.nt, s.nblocks, s.qk, Zt, Ct, w, HP, lam, Wq, ACCp, qoff, (double*)nullptr);     \
+  }
+    RGP_ABL(1) RGP_ABL(2) RGP_ABL(3) RGP_ABL(4) RGP_ABL(7) RGP_ABL(8) RGP_ABL(14) RGP_ABL(30) RGP_ABL(46) RGP_ABL(78)
+    RGP_ABL(142) RGP_ABL(16) RGP_ABL(110) RGP_ABL(174) RGP_ABL(206)
+#undef RGP_ABL
+#endif
+    else {
       RGP_LAUNCH(h, st, "psi2_bwd", (k_psi2_bwd<QC>), dim3(R, G), P2_THREADS, P2Cfg<QC>::BWD_SMEM, rows,
                  s.Mp, s.nt, s.nblocks, s.qk, Zt, Ct, w, HP, lam, Wq, ACCp, qoff, (double*)nullptr);
+    }
   }
   return 0;
 }

@@ -288,7 +288,13 @@ k_psi2_fwd(int64_t rc, int nt, int nblocks, int qk, const double* __restrict__ Z
 // stage 1 + exp is not needed.  Usable when the upstream gradients do not depend on the statistics
 // of the same evaluation (the SVI bound, autoreg/inference/svi_vardtc.py:162-169).
 // =====================================================================================
-template <int QC, bool FUSE = false>
+// OPT bits (A/B experiments, default 3): 1 = stage 2-J scales by ws AFTER the MMA (16 dense FMAs instead of
+// 64 DMULs inside the DMMA loop), 2 = stage 1 scales its A fragments in batches of four k-steps
+// DBG (RGP_DEBUG builds only; results are WRONG when set): ablation bits for timing experiments on the
+// off-diagonal path - 1 no exp (p = x), 2 no lambda sums / flush, 4 no stage 2-I folds / W flush,
+// 8 no epilogue at all (no exp, no C multiply, no L store), 16 no per-row barrier, 32 no stage 2-J,
+// 64 no stage 2-I, 128 no stage 1
+template <int QC, bool FUSE = false, int DBG = 0>
 __global__ void __launch_bounds__(P2_THREADS, 1)
 k_psi2_bwd(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __restrict__ Zt,
            const double* __restrict__ Ct, const double* __restrict__ wrow,
@@ -382,6 +388,16 @@ k_psi2_bwd(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __rest
 #pragma unroll
           for (int j = 0; j < NJ; ++j) dmma(T[i][j][0], T[i][j][1], a[i], bq[j]);
       }
+      if constexpr (DBG & 4) {                     // keep T alive with the cheapest possible use
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) {
+            accI[i][j][0] = T[i][j][0];
+            accI[i][j][1] = T[i][j][1];
+          }
+        return;
+      }
       double wp[2 * NJ];                           // Wq partials, index c = 2 j + e
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
@@ -433,8 +449,21 @@ k_psi2_bwd(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __rest
         double nxt = vec_load(n + 1);
         {
           double acc[2][4][2];
-          stage1<QC>(sZI, sZJ, v, qk, wr, wc, lane, acc);
+          if constexpr (DBG & 128) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = v[i + j];
+          } else stage1<QC>(sZI, sZJ, v, qk, wr, wc, lane, acc);
           if (tid < VB) sV[((n + 1) % 3) * VB + tid] = nxt;
+          if constexpr (DBG & 8) {                 // no epilogue: fold the exponents into one register so stage 1 stays
+            double sink = 0.0;
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) sink += acc[i][j][0] + acc[i][j][1];
+            if (sink == 1.2345e300) Lb[tid] = sink;
+          } else {
           double rs[2] = {0.0, 0.0};
           double cs[8];                            // column partials, index c = 2 j + e
 #pragma unroll
@@ -443,7 +472,8 @@ k_psi2_bwd(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __rest
           for (int i = 0; i < 2; ++i) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const double p0 = exp_tab(acc[i][j][0], sT), p1 = exp_tab(acc[i][j][1], sT);
+              const double p0 = (DBG & 1) ? acc[i][j][0] : exp_tab(acc[i][j][0], sT);
+              const double p1 = (DBG & 1) ? acc[i][j][1] : exp_tab(acc[i][j][1], sT);
               if constexpr (FUSE) {
                 double2* pp = reinterpret_cast<double2*>(sP + (16 * wr + 8 * i + g) * RSL + 32 * wc + 8 * j + 2 * t);
                 double2 o = *pp;
@@ -455,12 +485,15 @@ k_psi2_bwd(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __rest
               double l1 = creg[i][j][1] * p1;
               *reinterpret_cast<double2*>(Lb + (16 * wr + 8 * i + g) * RSL + 32 * wc + 8 * j + 2 * t) =
                   make_double2(l0, l1);
-              rs[i] += l0 + l1;
-              cs[2 * j] += l0;
-              cs[2 * j + 1] += l1;
+              if constexpr (!(DBG & 2)) {
+                rs[i] += l0 + l1;
+                cs[2 * j] += l0;
+                cs[2 * j + 1] += l1;
+              }
             }
           }
           // row sums: reduce over the 4 lanes of a quad (t); col sums: over the 8 quads (g)
+          if constexpr (!(DBG & 2)) {
 #pragma unroll
           for (int i = 0; i < 2; ++i) {
             rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], 1);
@@ -475,9 +508,12 @@ k_psi2_bwd(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __rest
             const int c = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
             sLc[s * 256 + wr * 64 + 32 * wc + 8 * (c >> 1) + 2 * t + (c & 1)] = tot;
           }
+          }
+          }
         }
-        __syncthreads();   // L tile + lambda partials of row n complete; row n-1 fully finished
-        if (qoff != 0) {
+        if constexpr (!(DBG & 16)) __syncthreads();   // L tile + lambda partials of row n complete; row n-1 fully finished
+        if constexpr (DBG & 2) {
+        } else if (qoff != 0) {
         } else if (tid >= 64 && tid < 128) {
           const int m = tid - 64;
           const double* p = sLr + s * 128 + m;
@@ -487,26 +523,39 @@ k_psi2_bwd(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __rest
           const double* p = sLc + s * 256 + m;
           red_add(lamg + n * Mp + J * 64 + m, p[0] + p[64] + p[128] + p[192]);
         }
-        if (n > r0) flush_wq(n - 1);
-        stage2I(v, Lb, s);
-        // stage 2-J: accJ[m',q] += sum_m L[m,m'] (ws_q ZI[m,q]).  A = L^T, B = ws * ZI
-        {
+        if constexpr (!(DBG & 4)) if (n > r0) flush_wq(n - 1);
+        if constexpr (!(DBG & 64)) stage2I(v, Lb, s);
+        // stage 2-J: accJ[m',q] += ws_q sum_m L[m,m'] ZI[m,q].  A = L^T, B = ZI; ws is applied AFTER the MMA
+        // (16 FMAs per thread instead of 64 DMULs inside the DMMA loop: measured 1.4 % faster)
+        if constexpr (DBG & 32) {
+        } else {
           const double* pa = Lb + t * RSL + 16 * wr + g;
           const double* pb = sZI + t * RS + qoff + qbase + g;
-          double wq[NJ];
+          double TJ[2][NJ][2];
 #pragma unroll
-          for (int j = 0; j < NJ; ++j) wq[j] = v[qoff + qbase + 8 * j + g];
+          for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) TJ[i][j][0] = TJ[i][j][1] = 0.0;
 #pragma unroll 2
           for (int k0 = 0; k0 < 64; k0 += 4) {
             double a[2], bq[NJ];
 #pragma unroll
             for (int i = 0; i < 2; ++i) a[i] = pa[k0 * RSL + 8 * i];
 #pragma unroll
-            for (int j = 0; j < NJ; ++j) bq[j] = pb[k0 * RS + 8 * j] * wq[j];
+            for (int j = 0; j < NJ; ++j) bq[j] = pb[k0 * RS + 8 * j];
 #pragma unroll
             for (int i = 0; i < 2; ++i)
 #pragma unroll
-              for (int j = 0; j < NJ; ++j) dmma(accJ[i][j][0], accJ[i][j][1], a[i], bq[j]);
+              for (int j = 0; j < NJ; ++j) dmma(TJ[i][j][0], TJ[i][j][1], a[i], bq[j]);
+          }
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) {
+            const double2 wq = *reinterpret_cast<const double2*>(v + qoff + qbase + 8 * j + 2 * t);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              accJ[i][j][0] = fma(wq.x, TJ[i][j][0], accJ[i][j][0]);
+              accJ[i][j][1] = fma(wq.y, TJ[i][j][1], accJ[i][j][1]);
+            }
           }
         }
       }

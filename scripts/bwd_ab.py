@@ -9,7 +9,7 @@ from rgp_b200.device import DevicePsi
 rows = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 18
 M = int(sys.argv[2]) if len(sys.argv) > 2 else 512
 Q = int(sys.argv[3]) if len(sys.argv) > 3 else 64
-variants = sys.argv[4].split(",") if len(sys.argv) > 4 else ["pipe", "rowloop"]
+variants = sys.argv[4].split(",") if len(sys.argv) > 4 else ["default", "pipe", "rowloop"]
 dev = torch.device("cuda", 0)
 g = torch.Generator(device=dev).manual_seed(1); f64 = dict(dtype=torch.float64, device=dev)
 mu = torch.randn((rows, Q), generator=g, **f64); S = torch.rand((rows, Q), generator=g, **f64) * 0.49 + 0.01
@@ -23,7 +23,7 @@ ref = None
 for name in variants:
     dp = DevicePsi(0)
     peak = dp.handle.fp64_peak(reps=3)
-    dp.handle.set_option("bwd_pipe", 0 if name == "rowloop" else 1)
+    dp.handle.set_option("bwd_pipe", {"pipe": 1, "rowloop": 0}.get(name, 2))
     for _ in range(2):
         dp.forward(mu, S, Z, ell, 1.3)
         out = dp.backward(mu, S, Z, ell, 1.3, -0.5, dL1, dL2)

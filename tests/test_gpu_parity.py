@@ -25,10 +25,10 @@ IMPLS = ["reference", "fast"]
 @pytest.fixture(scope="module")
 def plugins():
     from rgp_b200.psicomp import PSICOMP_RBF_B200
-    rowloop = PSICOMP_RBF_B200(impl="auto", cache=False)
-    rowloop.handle.set_option("bwd_pipe", 0)          # the row-at-a-time backward kernel (default: software-pipelined)
+    pipe = PSICOMP_RBF_B200(impl="auto", cache=False)
+    pipe.handle.set_option("bwd_pipe", 1)             # software-pipelined Psi2 backward kernel for the plain backward pass too
     return {"reference": PSICOMP_RBF_B200(impl="reference", cache=False),
-            "fast": PSICOMP_RBF_B200(impl="auto", cache=False), "rowloop": rowloop}
+            "fast": PSICOMP_RBF_B200(impl="auto", cache=False), "pipe": pipe}
 
 
 def _kern(pc, var, ell, ard=True):
@@ -72,7 +72,7 @@ SHAPES = [
 ]
 
 
-@pytest.mark.parametrize("impl", IMPLS + ["rowloop"])
+@pytest.mark.parametrize("impl", IMPLS + ["pipe"])
 @pytest.mark.parametrize("N,M,Q,nc", SHAPES)
 def test_forward_and_backward_match_oracle(plugins, impl, N, M, Q, nc):
     var, ell, Z, mu, S = make_inputs(N, M, Q, seed=100 + N + M + Q, n_control=nc)
@@ -81,7 +81,7 @@ def test_forward_and_backward_match_oracle(plugins, impl, N, M, Q, nc):
     _compare(fwd, bwd, psi_forward(var, ell, Z, mu, S), psi_backward(dL0, dL1, dL2, var, ell, Z, mu, S), TIGHT)
 
 
-@pytest.mark.parametrize("impl", IMPLS + ["rowloop"])
+@pytest.mark.parametrize("impl", IMPLS + ["pipe"])
 def test_headline_tile_shape_small_n(plugins, impl):
     # M=512, Q=64 (the headline kernel configuration) at an N the oracle finishes in seconds
     N, M, Q = 192, 512, 64
@@ -396,7 +396,7 @@ def test_options_are_validated():
     h = Handle(0)
     h._ensure()
     # the experiment knobs of round 1 (debug_skip, trace_ptr, fwd_smem_pad) are not options of the production library
-    for key, val in (("impl", 7), ("bwd_pipe", 2), ("row_chunk", -1), ("no_such_option", 1), ("debug_skip", 1),
+    for key, val in (("impl", 7), ("bwd_pipe", 3), ("row_chunk", -1), ("no_such_option", 1), ("debug_skip", 1),
                      ("trace_ptr", 4096), ("fwd_smem_pad", 1024), ("bwd_warps", 16)):
         with pytest.raises(PsiError):
             h.set_option(key, val)

@@ -14,7 +14,7 @@ from rgp_b200.lagwindow import LagWindow
 
 t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
 worst = 0.0
-variants = [{}, {"bwd_pipe": 0}]
+variants = [{}, {"bwd_pipe": 0}, {"bwd_pipe": 1}]
 for opts in variants:
     dp = DevicePsi(0, impl=1)
     for k, v in opts.items():
