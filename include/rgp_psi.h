@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define RGP_PSI_ABI_VERSION 2   /* 2: + fused, latent-terms, MLP free-run entry points */
+#define RGP_PSI_ABI_VERSION 3   /* 2: + fused, latent-terms, MLP free-run entry points; 3: + rgp_host_digest */
 
 typedef struct rgp_psi_ctx* rgp_psi_handle_t;
 
@@ -72,7 +72,9 @@ int rgp_psi_create(int device, rgp_psi_handle_t* out);
 int rgp_psi_destroy(rgp_psi_handle_t h);
 
 /* Options: "impl" (rgp_psi_impl), "row_chunk" (rows per internal device pass, 0 = 2^20),
- * "host_chunk" (rows per pipelined host<->device chunk of the *_host calls, 0 = 262144),
+ * "host_chunk" (rows per pipelined host<->device chunk of the *_host calls, 0 = 262144 for page-locked
+ * caller buffers, 131072 when pageable buffers go through the pinned staging ring), "host_threads"
+ * (threads of the pageable <-> pinned copies, 0 = min(8, cores / 2)),
  * "bwd_pipe" (Psi2 backward kernel: 0 = row-at-a-time, 1 = software-pipelined with TMA row-vector
  * staging, 2 (default) = row-at-a-time for the plain backward pass and pipelined for the fused pass,
  * the measured faster choice for each), "profile" (1 = record a CUDA-event pair around every kernel
@@ -102,10 +104,21 @@ int rgp_psi_backward_dev(rgp_psi_handle_t h, void* stream, int64_t N, int M, int
                          double* dmu_out, double* dS_out, double* dZ_out,
                          double* dell_out, double* dvar_out);
 
+/* ---- content digest of a host buffer (memoisation key of the plugin) -----------------------
+ * GPy wraps psicomputations / psiDerivativecomputations in Cache_this(limit=10), valid because the
+ * cacher observes paramz change notifications.  Without paramz the key must be the CONTENT: the layer
+ * rewrites X.mean / X.variance in place on every evaluation (autoreg/layers.py:528-550; with the same
+ * rows in a new order in testing/minibatch_tests.py:281-296).  out[0..1] = 128-bit order-sensitive
+ * digest of data[0..nbytes); threads = 0 picks min(16, cores).  Pure host code, no device needed. */
+int rgp_host_digest(const void* data, int64_t nbytes, int threads, uint64_t out[2]);
+
 /* ---- host-buffer wrappers (the numpy-in / numpy-out plugin path) -------------------
  * Rows are streamed through double-buffered device mirrors on three streams (copy-in, compute,
- * copy-out); copies overlap the kernels when the host buffers are pinned.  Device memory is
- * bounded by "host_chunk", not by N.  Synchronises before returning. */
+ * copy-out) so the copies overlap the kernels.  Caller buffers may be ordinary pageable memory (what
+ * numpy / GPy hand over): those are bounced through a pinned staging ring owned by the handle, filled
+ * and drained by the calling thread (a few helper threads) while the GPU works on the neighbouring
+ * chunk; page-locked caller buffers are used in place.  Device and pinned memory are bounded by
+ * "host_chunk", not by N.  Synchronises before returning. */
 int rgp_psi_forward_host(rgp_psi_handle_t h, int64_t N, int M, int Q,
                          const double* mu, const double* S, const double* Z,
                          const double* ell, double variance,

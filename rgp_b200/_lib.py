@@ -52,6 +52,7 @@ SIGNATURES = {
     "rgp_mlp_freerun_bwd_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                           C.c_int, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rgp_host_digest": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_uint64)]),
     "rgp_psi_launch_count": (C.c_int64, [C.c_void_p]),
     "rgp_psi_reset_counters": (C.c_int, [C.c_void_p]),
     "rgp_psi_kernel_times": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), c_double_p,
@@ -97,10 +98,17 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.rgp_psi_abi_version() != 2:
+    if lib.rgp_psi_abi_version() != 3:
         raise OSError("librgp_psi ABI version mismatch")
     _lib = lib
     return lib
+
+
+def host_digest(a) -> bytes:
+    """128-bit order-sensitive content digest of a C-contiguous numpy array (rgp_host_digest)."""
+    out = (C.c_uint64 * 2)()
+    check(load().rgp_host_digest(C.c_void_p(a.ctypes.data), a.nbytes, 0, out))
+    return bytes(out)
 
 
 def check(status: int) -> None:

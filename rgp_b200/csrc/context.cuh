@@ -50,6 +50,10 @@ struct rgp_psi_ctx {
   char* io = nullptr;
   size_t io_bytes = 0;
   size_t io_off = 0;
+  // pinned host staging ring of the *_host entry points (used for caller buffers that are pageable)
+  char* pin = nullptr;
+  size_t pin_bytes = 0;
+  int host_threads = 0;    // threads of the pageable <-> pinned copies (0 = min(8, cores / 2))
   int64_t launches = 0;
   std::vector<rgp::KernelStat> stats;
   std::vector<rgp::PendingEvent> pending;

@@ -4,6 +4,8 @@
 
 #include <algorithm>
 #include <new>
+#include <thread>
+#include <vector>
 
 #include "context.cuh"
 #include "common.cuh"
@@ -217,6 +219,7 @@ int rgp_psi_destroy(rgp_psi_handle_t h) {
   if (h->s_out) cudaStreamDestroy(h->s_out);
   if (h->ws) cudaFree(h->ws);
   if (h->io) cudaFree(h->io);
+  if (h->pin) cudaFreeHost(h->pin);
   delete h;
   return 0;
 }
@@ -232,6 +235,9 @@ int rgp_psi_set_option(rgp_psi_handle_t h, const char* key, int64_t value) {
   } else if (!strcmp(key, "host_chunk")) {
     if (value < 0) return set_error(RGP_PSI_ERR_INVALID, "host_chunk must be >= 0");
     h->host_chunk = value;
+  } else if (!strcmp(key, "host_threads")) {
+    if (value < 0 || value > 256) return set_error(RGP_PSI_ERR_INVALID, "host_threads must be in [0, 256]");
+    h->host_threads = (int)value;
   } else if (!strcmp(key, "profile")) {
     h->profile = value != 0;
   } else if (!strcmp(key, "bwd_pipe")) {
@@ -313,8 +319,12 @@ int rgp_psi_fused_dev(rgp_psi_handle_t h, void* stream, int64_t N, int M, int Q,
 
 // ------------------------------------------------------------- host-buffer wrappers
 // Rows are streamed in chunks through double-buffered device mirrors on three streams (copy-in,
-// compute, copy-out), so host<->device traffic overlaps the kernels (only truly asynchronous when
-// the caller's buffers are pinned) and device memory is bounded by the chunk size, not by N.
+// compute, copy-out), so host<->device traffic overlaps the kernels and device memory is bounded by
+// the chunk size, not by N.  The copies are only asynchronous from page-locked memory, and GPy hands
+// over ordinary (pageable) numpy arrays: every caller buffer that is not page-locked is therefore
+// bounced through a pinned staging ring owned by the handle - the calling thread copies chunk c+1
+// into the ring (several threads, memory-bandwidth bound) while the GPU works on chunk c, and drains
+// the results of chunk c-1 out of it.  Page-locked caller buffers are used in place.
 } // extern "C"
 
 namespace rgp {
@@ -330,15 +340,72 @@ static int host_pipeline_init(rgp_psi_ctx* h) {
   }
   return 0;
 }
-static int64_t host_chunk_rows(const rgp_psi_ctx* h, int64_t N) {
-  int64_t c = h->host_chunk > 0 ? h->host_chunk : 262144;
+static bool is_pinned(const void* p) {
+  if (!p) return true;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+static int64_t host_chunk_rows(const rgp_psi_ctx* h, int64_t N, bool staged) {
+  // staged chunks are half as long: the pinned ring holds two chunks of every pageable array
+  int64_t c = h->host_chunk > 0 ? h->host_chunk : (staged ? 131072 : 262144);
   return std::min<int64_t>(N, c);
+}
+static int pin_reserve(rgp_psi_ctx* h, size_t need) {
+  if (need <= h->pin_bytes) return 0;
+  if (h->pin) {
+    RGP_CUDA(cudaDeviceSynchronize());
+    RGP_CUDA(cudaFreeHost(h->pin));
+    h->pin = nullptr;
+    h->pin_bytes = 0;
+  }
+  cudaError_t e = cudaHostAlloc((void**)&h->pin, need, cudaHostAllocDefault);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    h->pin = nullptr;
+    return set_error(RGP_PSI_ERR_NOMEM, "cudaHostAlloc of %zu staging bytes failed: %s", need, cudaGetErrorString(e));
+  }
+  h->pin_bytes = need;
+  return 0;
+}
+// memcpy split over a few threads (a single thread moves ~10 GB/s; the host side of a 17 GB Psi1 must
+// keep up with the GPU).  Small copies stay on the calling thread.
+static void par_memcpy(const rgp_psi_ctx* h, void* dst, const void* src, size_t bytes) {
+  if (!bytes) return;
+  int nt = h->host_threads > 0 ? h->host_threads : (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+  if (bytes < (size_t)8 << 20 || nt <= 1) {
+    memcpy(dst, src, bytes);
+    return;
+  }
+  const size_t per = ((bytes + nt - 1) / nt + 4095) & ~size_t(4095);
+  std::vector<std::thread> th;
+  for (int i = 1; i < nt; ++i) {
+    const size_t off = per * i;
+    if (off >= bytes) break;
+    th.emplace_back([=] { memcpy((char*)dst + off, (const char*)src + off, std::min(per, bytes - off)); });
+  }
+  memcpy(dst, src, std::min(per, bytes));
+  for (auto& t : th) t.join();
 }
 struct AccumulateGuard {       // restores the handle's accumulate flag on every exit path
   rgp_psi_ctx* h;
   int saved;
   explicit AccumulateGuard(rgp_psi_ctx* c) : h(c), saved(c->accumulate) {}
   ~AccumulateGuard() { h->accumulate = saved; }
+};
+// One row-indexed caller array ([N][width] doubles) of a *_host call: where its chunks live on the host
+// side of the DMA (the caller's own memory if page-locked, else a slot of the staging ring).
+struct HostArray {
+  const double* in = nullptr;   // caller input (or null)
+  double* out = nullptr;        // caller output (or null)
+  int64_t width = 0;
+  bool staged = false;
+  double* slot[2] = {nullptr, nullptr};
+  const double* src(int k, int64_t r0) const { return staged ? slot[k] : in + r0 * width; }
+  double* dst(int k, int64_t r0) const { return staged ? slot[k] : out + r0 * width; }
 };
 }  // namespace rgp
 
@@ -351,12 +418,19 @@ int rgp_psi_forward_host(rgp_psi_handle_t h, int64_t N, int M, int Q, const doub
   if (!psi2_out) return set_error(RGP_PSI_ERR_INVALID, "psi2_out must not be null");
   RGP_CUDA(cudaSetDevice(h->device));
   RGP_TRY(host_pipeline_init(h));
-  const int64_t R = host_chunk_rows(h, N);
+  HostArray a_mu, a_S, a_p1;
+  a_mu.in = mu; a_mu.width = Q; a_mu.staged = !is_pinned(mu);
+  a_S.in = S; a_S.width = Q; a_S.staged = !is_pinned(S);
+  a_p1.out = psi1_out; a_p1.width = M; a_p1.staged = psi1_out && !is_pinned(psi1_out);
+  const bool any_staged = a_mu.staged || a_S.staged || a_p1.staged;
+  const int64_t R = host_chunk_rows(h, N, any_staged);
   size_t rq = (size_t)R * Q, rm = (size_t)R * M, mq = (size_t)M * Q, mm = (size_t)M * M;
   size_t need = bump_size(mq, 8) + bump_size(Q, 8) + bump_size(mm, 8) +
                 2 * (bump_size(rq, 8) * 2 + (psi1_out ? bump_size(rm, 8) : 0));
   RGP_TRY(arena_reserve(&h->io, &h->io_bytes, need));
-  Bump b(h->io, h->io_bytes);
+  RGP_TRY(pin_reserve(h, 2 * ((a_mu.staged ? bump_size(rq, 8) : 0) + (a_S.staged ? bump_size(rq, 8) : 0) +
+                              (a_p1.staged ? bump_size(rm, 8) : 0))));
+  Bump b(h->io, h->io_bytes), pb(h->pin, h->pin_bytes);
   double* d_Z = b.take<double>(mq);
   double* d_ell = b.take<double>(Q);
   double* d_p2 = b.take<double>(mm);
@@ -365,17 +439,31 @@ int rgp_psi_forward_host(rgp_psi_handle_t h, int64_t N, int M, int Q, const doub
     d_mu[i] = b.take<double>(rq);
     d_S[i] = b.take<double>(rq);
     d_p1[i] = psi1_out ? b.take<double>(rm) : nullptr;
+    if (a_mu.staged) a_mu.slot[i] = pb.take<double>(rq);
+    if (a_S.staged) a_S.slot[i] = pb.take<double>(rq);
+    if (a_p1.staged) a_p1.slot[i] = pb.take<double>(rm);
   }
   AccumulateGuard guard(h);
   RGP_CUDA(cudaMemcpyAsync(d_Z, Z, mq * 8, cudaMemcpyHostToDevice, h->s_cmp));
   RGP_CUDA(cudaMemcpyAsync(d_ell, ell, (size_t)Q * 8, cudaMemcpyHostToDevice, h->s_cmp));
+  // results of chunk (c, rows) staged in slot k go back to the caller once their D2H copy has landed
+  auto drain = [&](int k, int64_t r0, int64_t rows) -> int {
+    if (!a_p1.staged) return 0;
+    RGP_CUDA(cudaEventSynchronize(h->ev_out[k]));
+    par_memcpy(h, psi1_out + r0 * M, a_p1.slot[k], (size_t)rows * M * 8);
+    return 0;
+  };
   int c = 0;
+  int64_t prev_r0 = 0, prev_rows = 0;
   for (int64_t r0 = 0; r0 < N; r0 += R, ++c) {
     const int64_t rows = std::min(R, N - r0);
     const int k = c & 1;
-    if (c >= 2) RGP_CUDA(cudaStreamWaitEvent(h->s_in, h->ev_cmp[k], 0));     // inputs of chunk c-2 consumed
-    RGP_CUDA(cudaMemcpyAsync(d_mu[k], mu + r0 * Q, (size_t)rows * Q * 8, cudaMemcpyHostToDevice, h->s_in));
-    RGP_CUDA(cudaMemcpyAsync(d_S[k], S + r0 * Q, (size_t)rows * Q * 8, cudaMemcpyHostToDevice, h->s_in));
+    if (c >= 2) RGP_CUDA(cudaStreamWaitEvent(h->s_in, h->ev_cmp[k], 0));     // device inputs of chunk c-2 consumed
+    if (c >= 2 && (a_mu.staged || a_S.staged)) RGP_CUDA(cudaEventSynchronize(h->ev_in[k]));   // ring slot k copied out
+    if (a_mu.staged) par_memcpy(h, a_mu.slot[k], mu + r0 * Q, (size_t)rows * Q * 8);
+    if (a_S.staged) par_memcpy(h, a_S.slot[k], S + r0 * Q, (size_t)rows * Q * 8);
+    RGP_CUDA(cudaMemcpyAsync(d_mu[k], a_mu.src(k, r0), (size_t)rows * Q * 8, cudaMemcpyHostToDevice, h->s_in));
+    RGP_CUDA(cudaMemcpyAsync(d_S[k], a_S.src(k, r0), (size_t)rows * Q * 8, cudaMemcpyHostToDevice, h->s_in));
     RGP_CUDA(cudaEventRecord(h->ev_in[k], h->s_in));
     RGP_CUDA(cudaStreamWaitEvent(h->s_cmp, h->ev_in[k], 0));
     if (c >= 2) RGP_CUDA(cudaStreamWaitEvent(h->s_cmp, h->ev_out[k], 0));    // psi1 of chunk c-2 drained
@@ -385,13 +473,17 @@ int rgp_psi_forward_host(rgp_psi_handle_t h, int64_t N, int M, int Q, const doub
     RGP_CUDA(cudaEventRecord(h->ev_cmp[k], h->s_cmp));
     if (psi1_out) {
       RGP_CUDA(cudaStreamWaitEvent(h->s_out, h->ev_cmp[k], 0));
-      RGP_CUDA(cudaMemcpyAsync(psi1_out + r0 * M, d_p1[k], (size_t)rows * M * 8, cudaMemcpyDeviceToHost, h->s_out));
+      RGP_CUDA(cudaMemcpyAsync(a_p1.dst(k, r0), d_p1[k], (size_t)rows * M * 8, cudaMemcpyDeviceToHost, h->s_out));
       RGP_CUDA(cudaEventRecord(h->ev_out[k], h->s_out));
     }
+    if (c >= 1) RGP_TRY(drain(k ^ 1, prev_r0, prev_rows));   // the GPU is busy with chunk c meanwhile
+    prev_r0 = r0;
+    prev_rows = rows;
   }
   RGP_CUDA(cudaMemcpyAsync(psi2_out, d_p2, mm * 8, cudaMemcpyDeviceToHost, h->s_cmp));
   if (psi0_out)
     for (int64_t i = 0; i < N; ++i) psi0_out[i] = variance;                 // Psi0[n] = variance
+  RGP_TRY(drain((c - 1) & 1, prev_r0, prev_rows));
   RGP_CUDA(cudaStreamSynchronize(h->s_in));
   RGP_CUDA(cudaStreamSynchronize(h->s_cmp));
   RGP_CUDA(cudaStreamSynchronize(h->s_out));
@@ -408,12 +500,28 @@ int rgp_psi_backward_host(rgp_psi_handle_t h, int64_t N, int M, int Q, const dou
     return set_error(RGP_PSI_ERR_INVALID, "null dL_dpsi2 or output pointer");
   RGP_CUDA(cudaSetDevice(h->device));
   RGP_TRY(host_pipeline_init(h));
-  const int64_t R = host_chunk_rows(h, N);
+  HostArray a_mu, a_S, a_d0, a_d1, a_gm, a_gs;
+  a_mu.in = mu; a_mu.width = Q; a_mu.staged = !is_pinned(mu);
+  a_S.in = S; a_S.width = Q; a_S.staged = !is_pinned(S);
+  a_d0.in = dL_dpsi0; a_d0.width = 1; a_d0.staged = dL_dpsi0 && !is_pinned(dL_dpsi0);
+  a_d1.in = dL_dpsi1; a_d1.width = M; a_d1.staged = dL_dpsi1 && !is_pinned(dL_dpsi1);
+  a_gm.out = dmu_out; a_gm.width = Q; a_gm.staged = !is_pinned(dmu_out);
+  a_gs.out = dS_out; a_gs.width = Q; a_gs.staged = !is_pinned(dS_out);
+  HostArray* ins[4] = {&a_mu, &a_S, &a_d0, &a_d1};
+  HostArray* outs[2] = {&a_gm, &a_gs};
+  bool in_staged = false, out_staged = false;
+  for (auto* a : ins) in_staged |= a->staged;
+  for (auto* a : outs) out_staged |= a->staged;
+  const int64_t R = host_chunk_rows(h, N, in_staged || out_staged);
   size_t rq = (size_t)R * Q, rm = (size_t)R * M, mq = (size_t)M * Q, mm = (size_t)M * M;
   size_t need = bump_size(mq, 8) * 2 + bump_size(Q, 8) * 2 + bump_size(mm, 8) + bump_size(1, 8) +
                 2 * (bump_size(rq, 8) * 4 + (dL_dpsi0 ? bump_size(R, 8) : 0) + (dL_dpsi1 ? bump_size(rm, 8) : 0));
   RGP_TRY(arena_reserve(&h->io, &h->io_bytes, need));
-  Bump b(h->io, h->io_bytes);
+  size_t pneed = 0;
+  for (auto* a : ins) if (a->staged) pneed += 2 * bump_size((size_t)R * a->width, 8);
+  for (auto* a : outs) if (a->staged) pneed += 2 * bump_size((size_t)R * a->width, 8);
+  RGP_TRY(pin_reserve(h, pneed));
+  Bump b(h->io, h->io_bytes), pb(h->pin, h->pin_bytes);
   double* d_Z = b.take<double>(mq);
   double* d_dZ = b.take<double>(mq);
   double* d_ell = b.take<double>(Q);
@@ -428,22 +536,35 @@ int rgp_psi_backward_host(rgp_psi_handle_t h, int64_t N, int M, int Q, const dou
     d_dS[i] = b.take<double>(rq);
     d_dL0[i] = dL_dpsi0 ? b.take<double>(R) : nullptr;
     d_dL1[i] = dL_dpsi1 ? b.take<double>(rm) : nullptr;
+    for (auto* a : ins) if (a->staged) a->slot[i] = pb.take<double>((size_t)R * a->width);
+    for (auto* a : outs) if (a->staged) a->slot[i] = pb.take<double>((size_t)R * a->width);
   }
   AccumulateGuard guard(h);
   RGP_CUDA(cudaMemcpyAsync(d_Z, Z, mq * 8, cudaMemcpyHostToDevice, h->s_cmp));
   RGP_CUDA(cudaMemcpyAsync(d_ell, ell, (size_t)Q * 8, cudaMemcpyHostToDevice, h->s_cmp));
   RGP_CUDA(cudaMemcpyAsync(d_dL2, dL_dpsi2, mm * 8, cudaMemcpyHostToDevice, h->s_cmp));
+  auto drain = [&](int k, int64_t r0, int64_t rows) -> int {
+    if (!out_staged) return 0;
+    RGP_CUDA(cudaEventSynchronize(h->ev_out[k]));
+    for (auto* a : outs)
+      if (a->staged) par_memcpy(h, a->out + r0 * a->width, a->slot[k], (size_t)rows * a->width * 8);
+    return 0;
+  };
   int c = 0;
+  int64_t prev_r0 = 0, prev_rows = 0;
   for (int64_t r0 = 0; r0 < N; r0 += R, ++c) {
     const int64_t rows = std::min(R, N - r0);
     const int k = c & 1;
     if (c >= 2) RGP_CUDA(cudaStreamWaitEvent(h->s_in, h->ev_cmp[k], 0));
-    RGP_CUDA(cudaMemcpyAsync(d_mu[k], mu + r0 * Q, (size_t)rows * Q * 8, cudaMemcpyHostToDevice, h->s_in));
-    RGP_CUDA(cudaMemcpyAsync(d_S[k], S + r0 * Q, (size_t)rows * Q * 8, cudaMemcpyHostToDevice, h->s_in));
+    if (c >= 2 && in_staged) RGP_CUDA(cudaEventSynchronize(h->ev_in[k]));    // ring slot k copied out
+    for (auto* a : ins)
+      if (a->staged) par_memcpy(h, a->slot[k], a->in + r0 * a->width, (size_t)rows * a->width * 8);
+    RGP_CUDA(cudaMemcpyAsync(d_mu[k], a_mu.src(k, r0), (size_t)rows * Q * 8, cudaMemcpyHostToDevice, h->s_in));
+    RGP_CUDA(cudaMemcpyAsync(d_S[k], a_S.src(k, r0), (size_t)rows * Q * 8, cudaMemcpyHostToDevice, h->s_in));
     if (dL_dpsi0)
-      RGP_CUDA(cudaMemcpyAsync(d_dL0[k], dL_dpsi0 + r0, (size_t)rows * 8, cudaMemcpyHostToDevice, h->s_in));
+      RGP_CUDA(cudaMemcpyAsync(d_dL0[k], a_d0.src(k, r0), (size_t)rows * 8, cudaMemcpyHostToDevice, h->s_in));
     if (dL_dpsi1)
-      RGP_CUDA(cudaMemcpyAsync(d_dL1[k], dL_dpsi1 + r0 * M, (size_t)rows * M * 8, cudaMemcpyHostToDevice, h->s_in));
+      RGP_CUDA(cudaMemcpyAsync(d_dL1[k], a_d1.src(k, r0), (size_t)rows * M * 8, cudaMemcpyHostToDevice, h->s_in));
     RGP_CUDA(cudaEventRecord(h->ev_in[k], h->s_in));
     RGP_CUDA(cudaStreamWaitEvent(h->s_cmp, h->ev_in[k], 0));
     if (c >= 2) RGP_CUDA(cudaStreamWaitEvent(h->s_cmp, h->ev_out[k], 0));    // dmu/dS of chunk c-2 drained
@@ -452,13 +573,17 @@ int rgp_psi_backward_host(rgp_psi_handle_t h, int64_t N, int M, int Q, const dou
                                  dL_dpsi0_const, d_dL1[k], d_dL2, d_dmu[k], d_dS[k], d_dZ, d_dell, d_dvar));
     RGP_CUDA(cudaEventRecord(h->ev_cmp[k], h->s_cmp));
     RGP_CUDA(cudaStreamWaitEvent(h->s_out, h->ev_cmp[k], 0));
-    RGP_CUDA(cudaMemcpyAsync(dmu_out + r0 * Q, d_dmu[k], (size_t)rows * Q * 8, cudaMemcpyDeviceToHost, h->s_out));
-    RGP_CUDA(cudaMemcpyAsync(dS_out + r0 * Q, d_dS[k], (size_t)rows * Q * 8, cudaMemcpyDeviceToHost, h->s_out));
+    RGP_CUDA(cudaMemcpyAsync(a_gm.dst(k, r0), d_dmu[k], (size_t)rows * Q * 8, cudaMemcpyDeviceToHost, h->s_out));
+    RGP_CUDA(cudaMemcpyAsync(a_gs.dst(k, r0), d_dS[k], (size_t)rows * Q * 8, cudaMemcpyDeviceToHost, h->s_out));
     RGP_CUDA(cudaEventRecord(h->ev_out[k], h->s_out));
+    if (c >= 1) RGP_TRY(drain(k ^ 1, prev_r0, prev_rows));
+    prev_r0 = r0;
+    prev_rows = rows;
   }
   RGP_CUDA(cudaMemcpyAsync(dZ_out, d_dZ, mq * 8, cudaMemcpyDeviceToHost, h->s_cmp));
   RGP_CUDA(cudaMemcpyAsync(dell_out, d_dell, (size_t)Q * 8, cudaMemcpyDeviceToHost, h->s_cmp));
   RGP_CUDA(cudaMemcpyAsync(dvar_out, d_dvar, 8, cudaMemcpyDeviceToHost, h->s_cmp));
+  RGP_TRY(drain((c - 1) & 1, prev_r0, prev_rows));
   RGP_CUDA(cudaStreamSynchronize(h->s_in));
   RGP_CUDA(cudaStreamSynchronize(h->s_cmp));
   RGP_CUDA(cudaStreamSynchronize(h->s_out));
@@ -567,6 +692,76 @@ int rgp_mlp_freerun_bwd_dev(rgp_psi_handle_t h, void* stream, int nseq, const in
                                 (int)mlp::bwd_smem(sh, Xwin, Dx)));
   RGP_LAUNCH(h, st, "mlp_freerun_bwd", mlp::k_freerun_bwd, nseq, mlp::THREADS, mlp::bwd_smem(sh, Xwin, Dx), sh, seq_desc, Xwin,
              Dx, Uwin, Du, params, lat_mean, ctl_mean, hidden_acts, lat_gmean, ctl_gmean, param_grads);
+  return 0;
+}
+
+// ------------------------------------------------------------------ host-side content digest
+// 128-bit order-sensitive digest of a host buffer (two xxh64-style lanes sets with different seeds over
+// 8 MiB slices hashed on several threads; slice digests are folded in slice order).  The plugin keys its
+// result cache on it: the layer rewrites q(X) IN PLACE every evaluation (autoreg/layers.py:528-550), so
+// only the content identifies an input, and at the headline shape the key covers 21 GB per call.
+}  // extern "C"
+namespace rgp {
+static inline uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+static const uint64_t HP1 = 0x9E3779B185EBCA87ull, HP2 = 0xC2B2AE3D27D4EB4Full, HP3 = 0x165667B19E3779F9ull;
+static inline uint64_t hround(uint64_t acc, uint64_t w) { return rotl64(acc + w * HP2, 31) * HP1; }
+static inline uint64_t havalanche(uint64_t h) {
+  h ^= h >> 33; h *= HP2; h ^= h >> 29; h *= HP3; h ^= h >> 32;
+  return h;
+}
+static void digest_slice(const unsigned char* p, size_t n, uint64_t seed, uint64_t out[2]) {
+  uint64_t a[4] = {seed + HP1 + HP2, seed + HP2, seed, seed - HP1};
+  uint64_t b[4] = {~seed + HP3, seed ^ HP1, seed * HP2 + 1, seed + HP3 * 3};
+  size_t i = 0;
+  for (; i + 32 <= n; i += 32) {
+    uint64_t w[4];
+    memcpy(w, p + i, 32);
+    for (int j = 0; j < 4; ++j) {
+      a[j] = hround(a[j], w[j]);
+      b[j] = hround(b[j], rotl64(w[(j + 1) & 3], 17) ^ HP3);
+    }
+  }
+  uint64_t tail[4] = {0, 0, 0, 0};
+  memcpy(tail, p + i, n - i);
+  for (int j = 0; j < 4; ++j) {
+    a[j] = hround(a[j], tail[j] ^ (uint64_t)(n - i));
+    b[j] = hround(b[j], rotl64(tail[(j + 1) & 3], 17) + (uint64_t)n);
+  }
+  uint64_t ha = rotl64(a[0], 1) + rotl64(a[1], 7) + rotl64(a[2], 12) + rotl64(a[3], 18) + (uint64_t)n;
+  uint64_t hb = rotl64(b[0], 3) ^ rotl64(b[1], 11) ^ rotl64(b[2], 27) ^ rotl64(b[3], 41) ^ ((uint64_t)n * HP1);
+  out[0] = havalanche(ha);
+  out[1] = havalanche(hb);
+}
+}  // namespace rgp
+extern "C" {
+
+int rgp_host_digest(const void* data, int64_t nbytes, int threads, uint64_t out[2]) {
+  if (!out || nbytes < 0 || (!data && nbytes > 0)) return set_error(RGP_PSI_ERR_INVALID, "bad digest arguments");
+  const size_t SL = (size_t)8 << 20;
+  const size_t n = (size_t)nbytes, nsl = n ? (n + SL - 1) / SL : 1;
+  std::vector<uint64_t> part(2 * nsl);
+  int nt = threads > 0 ? threads : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+  nt = (int)std::min<size_t>(nt, nsl);
+  auto work = [&](int tix) {
+    for (size_t sl = tix; sl < nsl; sl += nt) {
+      const size_t off = sl * SL;
+      digest_slice((const unsigned char*)data + off, std::min(SL, n - off), 0x5DEECE66Dull + sl, &part[2 * sl]);
+    }
+  };
+  if (nt <= 1) {
+    work(0);
+  } else {
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& t : th) t.join();
+  }
+  if (nsl == 1) {
+    out[0] = part[0];
+    out[1] = part[1];
+  } else {
+    digest_slice((const unsigned char*)part.data(), part.size() * 8, 0x2545F4914F6CDD1Dull ^ (uint64_t)n, out);
+  }
   return 0;
 }
 

@@ -19,13 +19,11 @@ the first call raises.
 from __future__ import annotations
 
 import ctypes as C
-import hashlib
-import os
 from typing import Optional
 
 import numpy as np
 
-from ._lib import Handle, IMPL_AUTO, IMPL_FAST, IMPL_REFERENCE
+from ._lib import Handle, IMPL_AUTO, IMPL_FAST, IMPL_REFERENCE, host_digest
 
 _IMPL = {"auto": IMPL_AUTO, "fast": IMPL_FAST, "reference": IMPL_REFERENCE}
 
@@ -46,37 +44,18 @@ def _ptr(a: Optional[np.ndarray]):
 # CONTENT: the layer rewrites X.mean / X.variance in place every evaluation (layers.py:528-550)
 # - with the same rows in a new order in the permuted-minibatch tests
 # (testing/minibatch_tests.py:281-296) - and paramz mutates Z / lengthscale / variance in place.
-# So the key is an ORDER-SENSITIVE cryptographic digest of the raw bytes (blake2b; slices of
-# large arrays are hashed on a thread pool - hashlib releases the GIL - and the slice digests
-# are hashed in order).  A wrapping sum / XOR of the words, which round 1 used, is permutation
-# invariant and returned stale row-ordered results.
+# So the key is an ORDER-SENSITIVE 128-bit digest of the raw bytes, computed by librgp_psi's
+# rgp_host_digest (xxh64-style lanes over 8 MiB slices on several threads, slice digests folded in
+# order: memory-bandwidth bound, because at the headline shape one backward key covers 21 GB).  A
+# wrapping sum / XOR of the words, which round 1 used, is permutation invariant and returned stale
+# row-ordered results.
 # ---------------------------------------------------------------------------------------
-_HASH_SLICE = 8 << 20            # bytes per pool task
-_pool = None
-
-
-def _hash_pool():
-    global _pool
-    if _pool is None:
-        from concurrent.futures import ThreadPoolExecutor
-        n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-        _pool = ThreadPoolExecutor(max_workers=max(1, min(32, n)), thread_name_prefix="rgp-hash")
-    return _pool
-
-
 def _digest(a: np.ndarray) -> bytes:
-    buf = memoryview(np.ascontiguousarray(a)).cast("B")
-    if buf.nbytes <= 2 * _HASH_SLICE:
-        return hashlib.blake2b(buf, digest_size=16).digest()
-    parts = [buf[o:o + _HASH_SLICE] for o in range(0, buf.nbytes, _HASH_SLICE)]
-    top = hashlib.blake2b(digest_size=16)
-    for d in _hash_pool().map(lambda b: hashlib.blake2b(b, digest_size=16).digest(), parts):
-        top.update(d)                       # slice digests in slice order: order-sensitive
-    return top.digest()
+    return host_digest(np.ascontiguousarray(a))
 
 
 def _fingerprint(*arrays) -> tuple:
-    """Order-sensitive content fingerprint: (shape, blake2b-128 of the bytes) per array."""
+    """Order-sensitive content fingerprint: (shape, 128-bit digest of the bytes) per array."""
     return tuple((a.shape, _digest(a)) for a in arrays)
 
 

@@ -21,7 +21,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared_symbols():
     text = open(os.path.join(ROOT, "include", "rgp_psi.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(rgp_(?:psi|lag|latent|mlp)_[a-z0-9_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(rgp_(?:psi|lag|latent|mlp|host)_[a-z0-9_]+)\s*\(", text)))
 
 
 def test_library_builds_loads_and_exports_every_declared_symbol():
@@ -31,7 +31,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), "missing export " + n
     assert sorted(_lib.SIGNATURES) == names           # the ctypes table covers the header exactly
-    assert lib.rgp_psi_abi_version() == 2
+    assert lib.rgp_psi_abi_version() == 3
 
 
 def test_shared_object_contains_sm100a_code_only():
@@ -119,20 +119,40 @@ def test_fingerprint_is_order_sensitive():
     assert _fingerprint(mu.reshape(7, 50)) != _fingerprint(mu)          # shape is part of the key
 
 
-def test_fingerprint_large_arrays_are_hashed_in_ordered_slices(monkeypatch):
-    """Arrays above two hash slices go through the thread pool; swapping two SLICES (a permutation of
-    whole blocks) must still change the key, and the key must not depend on the slice size being
-    hit exactly."""
-    import rgp_b200.psicomp as pcm
-    monkeypatch.setattr(pcm, "_HASH_SLICE", 1 << 10)
-    a = np.arange(4096, dtype=np.float64)               # 32 KiB = 32 slices of 1 KiB
-    f0 = pcm._fingerprint(a)
+def test_fingerprint_large_arrays_are_hashed_in_ordered_slices():
+    """Arrays above one 8 MiB slice are hashed slice by slice on several threads; exchanging two whole
+    slices, or two words inside one slice, must change the key; equal content gives equal keys whatever
+    the thread count."""
+    import ctypes as C
+    from rgp_b200._lib import load
+    a = np.arange(3 * (1 << 20) + 5, dtype=np.float64)            # 24 MiB + a ragged tail: 4 slices
+    f0 = _fingerprint(a)
     b = a.copy()
-    b[:128], b[128:256] = a[128:256], a[:128]           # exchange the first two slices
-    assert pcm._fingerprint(b) != f0
-    assert pcm._fingerprint(a.copy()) == f0
-    c = np.arange(4096 + 5, dtype=np.float64)           # ragged last slice
-    assert pcm._fingerprint(c) == pcm._fingerprint(c.copy()) != f0
+    n = 1 << 20                                                    # doubles per slice
+    b[:n], b[n:2 * n] = a[n:2 * n], a[:n]
+    assert _fingerprint(b) != f0
+    c = a.copy()
+    c[5], c[6] = a[6], a[5]
+    assert _fingerprint(c) != f0
+    assert _fingerprint(a.copy()) == f0
+    lib = load()
+    outs = []
+    for threads in (1, 2, 7):
+        out = (C.c_uint64 * 2)()
+        assert lib.rgp_host_digest(C.c_void_p(a.ctypes.data), a.nbytes, threads, out) == 0
+        outs.append(bytes(out))
+    assert outs[0] == outs[1] == outs[2]
+    out = (C.c_uint64 * 2)()
+    assert lib.rgp_host_digest(None, 0, 0, out) == 0                # empty buffer is fine
+    assert lib.rgp_host_digest(None, 8, 0, out) == -1 and b"digest" in lib.rgp_psi_last_error()
+    # every single-bit flip of a short buffer changes both halves of the digest
+    base = np.arange(40, dtype=np.uint8)
+    d0 = _fingerprint(base)[0][1]
+    for byte in range(40):
+        x = base.copy()
+        x[byte] ^= 1
+        d = _fingerprint(x)[0][1]
+        assert d[:8] != d0[:8] and d[8:] != d0[8:]
 
 
 def test_cache_hands_out_copies_below_the_threshold_and_the_stored_arrays_above():

@@ -286,3 +286,16 @@ def test_back_constrained_model_end_to_end_on_device():
     assert relerr(enc2.flat.grad.cpu().numpy(), flat(pg2)) < 1e-8
     assert relerr(init1.grad.cpu().numpy(), np.stack([x[:wins[1]] for x in g1])) < 1e-8
     assert relerr(init2.grad.cpu().numpy(), np.stack([x[:wins[2]] for x in g2])) < 1e-8
+
+
+def test_svi_minibatch_additivity_and_permutation_on_device():
+    """BASELINE.json config 4 at test size: the SVI bound and every parameter gradient of a minibatch equal the sum
+    over its two halves evaluated with half the KL weight each (testing/minibatch_tests.py:288-296), and do not depend
+    on the order of the sequences (:281-286).  The reference asserts rtol 1e-14 / 1e-11; 1e-9 is the gate here."""
+    import torch
+    import svi_workload
+    par = svi_workload.parity(1, 0, torch.device("cuda", 0), T=700)
+    assert par["two_halves_vs_whole_bound"] < 1e-11, par
+    assert par["two_halves_vs_whole_grads"] < 1e-9, par
+    assert par["permuted_vs_ordered_bound"] < 1e-11, par
+    assert par["permuted_vs_ordered_grads"] < 1e-9, par

@@ -327,6 +327,71 @@ def test_large_shard_additivity_and_fast_vs_reference_kernels():
         assert relerr(a.cpu().numpy(), b.cpu().numpy()) < 1e-10
 
 
+@pytest.mark.parametrize("N,M,Q,ref_rows", [
+    ((1 << 20) + 37, 512, 64, 4096),     # the headline launch geometry: default row_chunk -> a 2^20-row launch (148 row
+                                         # ranges x 7085 rows, 36 block passes) plus a 37-row remainder chunk
+    (65536 + 5, 1024, 128, 1024),        # sweep corner: 136 block passes, two q halves in the backward kernel
+    (200_003, 500, 60, 2048),            # ragged M and Q (padding inside the tiles)
+])
+def test_parity_at_launch_geometry(N, M, Q, ref_rows):
+    """Parity where the oracle cannot go as a whole: (i) Psi1 / dmu / dS are row-local given dL_dpsi2, so a
+    random 256-row subset is compared with the CPU oracle EXACTLY as in the small tests; (ii) the row sums
+    (Psi2, dZ, dl, dvar) of the full launch equal the sum over 8 row shards (each a different launch
+    geometry) - the reference's own minibatch additivity check (testing/minibatch_tests.py:288-296: rtol 1e-14
+    on the bound, 1e-11 on gradients); (iii) on a sub-range they equal the independent one-thread-per-output
+    kernel family; (iv) the row-at-a-time and the software-pipelined backward kernels agree."""
+    import torch
+    from rgp_b200.device import DevicePsi
+    fast, ref = DevicePsi(0, impl=0), DevicePsi(0, impl=2)
+    mu, S, Z, ell, dL1, dL2 = _device_inputs(N, M, Q, seed=11)
+    var = 1.3
+    np_ = lambda t: t.cpu().numpy()
+    _, p1, p2 = fast.forward(mu, S, Z, ell, var)
+    full = fast.backward(mu, S, Z, ell, var, -0.5, dL1, dL2)
+    p2, full = p2.clone(), [t.clone() for t in full]
+    # (i) random rows against the oracle
+    idx = torch.from_numpy(np.sort(np.random.default_rng(5).choice(N, 256, replace=False))).cuda()
+    sub = lambda t: np_(t.index_select(0, idx))
+    of = psi_forward(var, np_(ell), np_(Z), sub(mu), sub(S))
+    ob = psi_backward(np.full(256, -0.5), sub(dL1), np_(dL2), var, np_(ell), np_(Z), sub(mu), sub(S))
+    assert relerr(sub(p1), of[1]) < TIGHT
+    assert relerr(sub(full[3]), ob[3]) < TIGHT and relerr(sub(full[4]), ob[4]) < TIGHT
+    # (ii) 8-way additivity
+    acc2 = torch.zeros_like(p2)
+    accs = [torch.zeros(1, device="cuda", dtype=torch.float64), torch.zeros_like(ell), torch.zeros_like(Z)]
+    cuts = np.linspace(0, N, 9).astype(np.int64)
+    for s, e in zip(cuts[:-1], cuts[1:]):
+        acc2 += fast.forward(mu[s:e], S[s:e], Z, ell, var, want_psi1=False)[2]
+        b = fast.backward(mu[s:e], S[s:e], Z, ell, var, -0.5, dL1[s:e], dL2)
+        for a, x in zip(accs, b[:3]):
+            a += x
+        assert relerr(np_(b[3]), np_(full[3][s:e])) < 1e-12 and relerr(np_(b[4]), np_(full[4][s:e])) < 1e-12
+    assert relerr(np_(acc2), np_(p2)) < 1e-12
+    for a, x in zip(accs, full[:3]):
+        assert relerr(np_(a), np_(x)) < 1e-11
+    # (iii) the independent kernel family on a sub-range (its atomics make it slow and order-dependent)
+    s0 = N // 3
+    sl = slice(s0, s0 + ref_rows)
+    rp = ref.forward(mu[sl], S[sl], Z, ell, var)
+    fp = fast.forward(mu[sl], S[sl], Z, ell, var)
+    assert relerr(np_(fp[1]), np_(rp[1])) < TIGHT and relerr(np_(fp[2]), np_(rp[2])) < TIGHT
+    rb = ref.backward(mu[sl], S[sl], Z, ell, var, -0.5, dL1[sl], dL2)
+    fb = fast.backward(mu[sl], S[sl], Z, ell, var, -0.5, dL1[sl], dL2)
+    for a, b in zip(fb, rb):
+        assert relerr(np_(a), np_(b)) < 1e-10
+    # (iv) both backward kernels, full launch
+    other = DevicePsi(0, impl=0)
+    other.handle.set_option("bwd_pipe", 1)
+    ob2 = other.backward(mu, S, Z, ell, var, -0.5, dL1, dL2)
+    for a, b in zip(ob2, full):
+        assert relerr(np_(a), np_(b)) < 1e-12
+    if Q <= 64:     # and the fused pass (statistics + gradients from one launch)
+        (q1, q2), fo = fast.fused(mu, S, Z, ell, var, -0.5, dL1, dL2)
+        assert relerr(np_(q2), np_(p2)) < 1e-12 and relerr(np_(q1), np_(p1)) < 1e-13
+        for a, b in zip(fo, full):
+            assert relerr(np_(a), np_(b)) < 1e-12
+
+
 def test_psi2_is_symmetric_psd_and_bounded():
     import torch
     from rgp_b200.device import DevicePsi

@@ -115,3 +115,18 @@ def test_two_rank_gloo_reduction_reproduces_full_batch(tmp_path):
         rows1.append(g["psi1"]); rowsmu.append(g["dmu"]); rowsS.append(g["dS"])
     assert relerr(np.vstack(rows1), f[1]) < 1e-14
     assert relerr(np.vstack(rowsmu), b[3]) < 1e-13 and relerr(np.vstack(rowsS), b[4]) < 1e-13
+
+
+def test_minibatch_sequences_are_dealt_in_contiguous_blocks():
+    """svi_workload.deal_sequences (config 4): every sequence of a minibatch goes to exactly one rank, blocks are
+    contiguous (so a rank's latent gradients are one slice of the single-GPU result) and differ by at most one."""
+    import os, sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from svi_workload import deal_sequences
+    ids = list(range(100, 164))
+    for world in (1, 2, 3, 8):
+        parts = [deal_sequences(ids, world, r) for r in range(world)]
+        assert sum(parts, []) == ids
+        assert max(map(len, parts)) - min(map(len, parts)) <= 1
+    with pytest.raises(ValueError):
+        deal_sequences(ids[:3], 4, 0)
