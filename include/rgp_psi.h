@@ -109,7 +109,7 @@ int rgp_psi_backward_dev(rgp_psi_handle_t h, void* stream, int64_t N, int M, int
  * cacher observes paramz change notifications.  Without paramz the key must be the CONTENT: the layer
  * rewrites X.mean / X.variance in place on every evaluation (autoreg/layers.py:528-550; with the same
  * rows in a new order in testing/minibatch_tests.py:281-296).  out[0..1] = 128-bit order-sensitive
- * digest of data[0..nbytes); threads = 0 picks min(16, cores).  Pure host code, no device needed. */
+ * digest of data[0..nbytes); threads = 0 picks min(32, cores).  Pure host code, no device needed. */
 int rgp_host_digest(const void* data, int64_t nbytes, int threads, uint64_t out[2]);
 
 /* ---- host-buffer wrappers (the numpy-in / numpy-out plugin path) -------------------

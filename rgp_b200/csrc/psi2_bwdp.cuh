@@ -188,7 +188,14 @@ k_psi2_bwdp(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __res
   }
   exp_table_init(sT, tid);
   uint32_t phase_bits = 0u;                        // bit s: parity of the next completion of slot s's mbarrier
-  if (r0 >= r1) return;                            // (uniform) an empty row range has nothing to add
+  if (r0 >= r1) {                                  // (uniform) an empty row range adds nothing, but the Psi2 reduction
+    if constexpr (FUSE)                            // sums one partial tile per row range: write zeros
+      for (int b = blockIdx.y; b < nblocks; b += G) {
+        double* out = P2p + ((size_t)b * R + blockIdx.x) * 4096;
+        for (int i = tid; i < 4096; i += P2_THREADS) out[i] = 0.0;
+      }
+    return;
+  }
 
   int curI = -1, curJ = -1;
   for (int b = blockIdx.y; b < nblocks; b += G) {

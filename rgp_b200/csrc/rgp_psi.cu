@@ -709,16 +709,29 @@ static inline uint64_t havalanche(uint64_t h) {
   h ^= h >> 33; h *= HP2; h ^= h >> 29; h *= HP3; h ^= h >> 32;
   return h;
 }
+// Two independent 64-bit digests per slice.  Lanes a: XXH3-style accumulate - one 32x32->64 multiply per
+// 8 input bytes plus the neighbouring word added in, scrambled every 1 KiB - strong and memory-bound on a
+// few threads.  Lanes b: rotate / xor / add only, with different lane pairing.  Word position matters in
+// both (lane index, rotation count), so permuted input gives another digest.
 static void digest_slice(const unsigned char* p, size_t n, uint64_t seed, uint64_t out[2]) {
-  uint64_t a[4] = {seed + HP1 + HP2, seed + HP2, seed, seed - HP1};
+  uint64_t a[4] = {seed + HP1 + HP2, seed + HP2, seed ^ HP3, seed - HP1};
   uint64_t b[4] = {~seed + HP3, seed ^ HP1, seed * HP2 + 1, seed + HP3 * 3};
+  const uint64_t k[4] = {0xBE4BA423396CFEB8ull, 0x1CAD21F72C81017Cull, 0xDB979083E96DD4DEull, 0x1F67B3B7A4A44072ull};
   size_t i = 0;
-  for (; i + 32 <= n; i += 32) {
-    uint64_t w[4];
-    memcpy(w, p + i, 32);
-    for (int j = 0; j < 4; ++j) {
-      a[j] = hround(a[j], w[j]);
-      b[j] = hround(b[j], rotl64(w[(j + 1) & 3], 17) ^ HP3);
+  while (i + 32 <= n) {
+    const size_t stop = std::min(n - 31, i + 1024);
+    for (; i < stop; i += 32) {
+      uint64_t w[4];
+      memcpy(w, p + i, 32);
+      for (int j = 0; j < 4; ++j) {
+        const uint64_t dk = w[j] ^ k[j];
+        a[j] += (dk & 0xFFFFFFFFull) * (dk >> 32) + w[j ^ 1];
+        b[j] = (rotl64(b[j], 29) ^ w[(j + 1) & 3]) + w[(j + 2) & 3];
+      }
+    }
+    for (int j = 0; j < 4; ++j) {                       // scramble: keep the accumulators from staying linear
+      a[j] = (a[j] ^ (a[j] >> 47) ^ k[(j + 1) & 3]) * HP1;
+      b[j] = (b[j] ^ (b[j] >> 31)) * HP2;
     }
   }
   uint64_t tail[4] = {0, 0, 0, 0};
@@ -740,7 +753,7 @@ int rgp_host_digest(const void* data, int64_t nbytes, int threads, uint64_t out[
   const size_t SL = (size_t)8 << 20;
   const size_t n = (size_t)nbytes, nsl = n ? (n + SL - 1) / SL : 1;
   std::vector<uint64_t> part(2 * nsl);
-  int nt = threads > 0 ? threads : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+  int nt = threads > 0 ? threads : (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
   nt = (int)std::min<size_t>(nt, nsl);
   auto work = [&](int tix) {
     for (size_t sl = tix; sl < nsl; sl += nt) {
