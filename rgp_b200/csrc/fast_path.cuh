@@ -15,18 +15,24 @@ static inline bool supported(int M, int Q) { return Q >= 1 && Q <= 128 && M >= 1
 static inline bool fused_supported(int Q) { return Q <= 64; }
 static inline int qc_for(int Q) { return Q <= 16 ? 16 : (Q <= 32 ? 32 : (Q <= 64 ? 64 : 128)); }
 
+template <int QC, int NJ>
+static int init_bwdp() {
+  RGP_CUDA(cudaFuncSetAttribute((k_psi2_bwdp<QC, NJ, false>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                P2CfgP<QC, NJ>::SMEM));
+  if constexpr (QC <= 64)
+    RGP_CUDA(cudaFuncSetAttribute((k_psi2_bwdp<QC, NJ, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  P2CfgP<QC, NJ>::FUSED_SMEM));
+  return 0;
+}
+
 template <int QC>
 static int init_qc() {
   RGP_CUDA(cudaFuncSetAttribute(k_psi2_fwd<QC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 P2Cfg<QC>::FWD_SMEM + (QC == 64 ? 65536 : 0)));
   RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwd<QC>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Cfg<QC>::BWD_SMEM));
-  RGP_CUDA(cudaFuncSetAttribute(k_psi2_bwdp<QC>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2CfgP<QC>::SMEM));
-  if constexpr (QC <= 64) {
+  if constexpr (QC <= 64)
     RGP_CUDA(cudaFuncSetAttribute((k_psi2_bwd<QC, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   P2Cfg<QC>::BWD_FUSED_SMEM));
-    RGP_CUDA(cudaFuncSetAttribute((k_psi2_bwdp<QC, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  P2CfgP<QC>::FUSED_SMEM));
-  }
   return 0;
 }
 
@@ -35,6 +41,11 @@ static int init(rgp_psi_ctx*) {
   RGP_TRY(init_qc<32>());
   RGP_TRY(init_qc<64>());
   RGP_TRY(init_qc<128>());
+  RGP_TRY((init_bwdp<16, 1>()));
+  RGP_TRY((init_bwdp<32, 2>()));
+  RGP_TRY((init_bwdp<64, 3>()));
+  RGP_TRY((init_bwdp<64, 4>()));
+  RGP_TRY((init_bwdp<128, 4>()));
   return 0;
 }
 
@@ -97,7 +108,24 @@ template <int QC>
 static int launch_fwd(rgp_psi_ctx* h, cudaStream_t st, const Shape& s, int64_t rows, int R, int G,
                       const double* Zt, const double* w, const double* HP, double* P2p) {
   RGP_LAUNCH(h, st, "psi2_fwd", (k_psi2_fwd<QC>), dim3(R, G), P2_THREADS, P2Cfg<QC>::FWD_SMEM + h->fwd_smem_pad, rows,
-             s.nt, s.nblocks, s.qk, Zt, w, HP, P2p);
+             s.M, s.nt, s.nblocks, s.qk, Zt, w, HP, P2p);
+  return 0;
+}
+
+template <int QC, int NJ>
+static int launch_bwdp(rgp_psi_ctx* h, cudaStream_t st, const Shape& s, int64_t rows, int R, int G,
+                       const double* Zt, const double* Ct, const double* w, const double* HP,
+                       double* lam, double* Wq, double* ACCp, double* P2p) {
+  if constexpr (QC <= 64) {
+    if (P2p) {     // fused forward + backward: the kernel also accumulates the Psi2 partial tiles
+      RGP_LAUNCH(h, st, "psi2_bwd_fused", (k_psi2_bwdp<QC, NJ, true>), dim3(R, G), P2_THREADS,
+                 (P2CfgP<QC, NJ>::FUSED_SMEM), rows, s.M, s.Mp, s.nt, s.nblocks, s.qk, Zt, Ct, w, HP, lam, Wq, ACCp, 0, P2p);
+      return 0;
+    }
+  }
+  for (int qoff = 0; qoff < s.Q; qoff += 16 * NJ)   // two passes for 64 < Q <= 128 (one if Q <= 64)
+    RGP_LAUNCH(h, st, "psi2_bwd", (k_psi2_bwdp<QC, NJ, false>), dim3(R, G), P2_THREADS, (P2CfgP<QC, NJ>::SMEM), rows,
+               s.M, s.Mp, s.nt, s.nblocks, s.qk, Zt, Ct, w, HP, lam, Wq, ACCp, qoff, (double*)nullptr);
   return 0;
 }
 
@@ -105,26 +133,34 @@ template <int QC>
 static int launch_bwd(rgp_psi_ctx* h, cudaStream_t st, const Shape& s, int64_t rows, int R, int G,
                       const double* Zt, const double* Ct, const double* w, const double* HP,
                       double* lam, double* Wq, double* ACCp, double* P2p) {
-  // Two Psi2 backward kernels (profiles/SUMMARY_r02.md, "A/B"): the row-at-a-time kernel is 1.5 % faster for the
-  // plain backward pass, the software-pipelined one 3 % faster when the pass also accumulates Psi2 (fused).
+  // Two Psi2 backward kernels (profiles/SUMMARY_r02.md, "A/B").  The software-pipelined kernel (psi2_bwdp.cuh)
+  // computes only the valid 8 x 8 tiles of a narrow last tile of M and sizes its stage-2 width to Q in steps of
+  // 16, and is 3 % faster when the pass also accumulates Psi2 (fused); the row-at-a-time kernel is 1.5 % faster on
+  // full tiles at the full stage-2 width (M a multiple of 64, 48 < Q <= 64: the headline shape).
   // bwd_pipe: 2 = that choice (default), 0 / 1 = force one of them (A/B measurements, parity tests).
   const bool fused = P2p != nullptr;
-  const bool pipe = h->bwd_pipe == 1 || (h->bwd_pipe == 2 && fused);
+  const bool full = QC == 64 && s.Q > 48 && s.M % 64 == 0;
+  const bool pipe = h->bwd_pipe == 1 || (h->bwd_pipe == 2 && (fused || !full));
   if constexpr (QC == 128) {
     if (fused) return set_error(RGP_PSI_ERR_INVALID, "fused pass is not built for Q > 64");
-  } else if (fused) {
-    if (pipe)
-      RGP_LAUNCH(h, st, "psi2_bwd_fused", (k_psi2_bwdp<QC, true>), dim3(R, G), P2_THREADS, P2CfgP<QC>::FUSED_SMEM,
-                 rows, s.Mp, s.nt, s.nblocks, s.qk, Zt, Ct, w, HP, lam, Wq, ACCp, 0, P2p);
-    else
+  }
+  if (pipe) {
+    if constexpr (QC == 16) return launch_bwdp<16, 1>(h, st, s, rows, R, G, Zt, Ct, w, HP, lam, Wq, ACCp, P2p);
+    else if constexpr (QC == 32) return launch_bwdp<32, 2>(h, st, s, rows, R, G, Zt, Ct, w, HP, lam, Wq, ACCp, P2p);
+    else if constexpr (QC == 64) {
+      if (s.Q <= 48) return launch_bwdp<64, 3>(h, st, s, rows, R, G, Zt, Ct, w, HP, lam, Wq, ACCp, P2p);
+      return launch_bwdp<64, 4>(h, st, s, rows, R, G, Zt, Ct, w, HP, lam, Wq, ACCp, P2p);
+    } else return launch_bwdp<128, 4>(h, st, s, rows, R, G, Zt, Ct, w, HP, lam, Wq, ACCp, P2p);
+  }
+  if constexpr (QC <= 64) {
+    if (fused) {
       RGP_LAUNCH(h, st, "psi2_bwd_fused", (k_psi2_bwd<QC, true>), dim3(R, G), P2_THREADS, P2Cfg<QC>::BWD_FUSED_SMEM,
                  rows, s.Mp, s.nt, s.nblocks, s.qk, Zt, Ct, w, HP, lam, Wq, ACCp, 0, P2p);
-    return 0;
+      return 0;
+    }
   }
   for (int qoff = 0; qoff < QC; qoff += P2Cfg<QC>::QS) {   // two passes for QC = 128
-    if (pipe) {
-      RGP_LAUNCH(h, st, "psi2_bwd", (k_psi2_bwdp<QC>), dim3(R, G), P2_THREADS, P2CfgP<QC>::SMEM, rows,
-                 s.Mp, s.nt, s.nblocks, s.qk, Zt, Ct, w, HP, lam, Wq, ACCp, qoff, (double*)nullptr);
+    if (false) {
     }
 #ifdef RGP_DEBUG
 #define RGP_ABL(D)                                                                                           \
