@@ -53,22 +53,38 @@ def is_current() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile rgp_b200/csrc/rgp_psi.cu -> rgp_b200/_lib/librgp_psi.so (sm_100a)."""
+    """Compile rgp_b200/csrc/rgp_psi.cu -> rgp_b200/_lib/librgp_psi.so (sm_100a).
+
+    Safe under concurrent callers (the ranks of a torchrun job importing the package at once): the build
+    runs under an exclusive file lock, writes to a temporary name and renames it into place, so no process
+    ever dlopens a half-written library."""
+    import fcntl
     os.makedirs(LIBDIR, exist_ok=True)
     if not force and is_current():
         return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, "-shared", "-o", LIB, os.path.join(CSRC, "rgp_psi.cu")]
-    if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-        print(" ".join(cmd), file=sys.stderr)
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr, file=sys.stderr)
-    with open(STAMP, "w") as f:
-        f.write(_source_hash())
+    with open(os.path.join(LIBDIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and is_current():            # another process built it while we waited
+                return LIB
+            tmp = LIB + ".tmp.%d" % os.getpid()
+            cmd = [_nvcc(), *NVCC_FLAGS, "-shared", "-o", tmp, os.path.join(CSRC, "rgp_psi.cu")]
+            if verbose:
+                cmd.insert(1, "-Xptxas")
+                cmd.insert(2, "-v")
+                print(" ".join(cmd), file=sys.stderr)
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+            if verbose:
+                print(res.stderr, file=sys.stderr)
+            os.replace(tmp, LIB)
+            with open(STAMP, "w") as f:
+                f.write(_source_hash())
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 
