@@ -202,7 +202,8 @@ k_psi2_bwdp(int64_t rc, int M, int Mp, int nt, int nblocks, int qk, const double
     // ED: interleave the epilogue of the NEXT row of a diagonal block (see below) with the k-steps.
     // niI = valid 8-row tiles of this warp in the I tile (2 unless this is the narrow last diagonal block)
     const int niI = diag ? ((tJ - 2 * wr) < 0 ? 0 : ((tJ - 2 * wr) > 2 ? 2 : tJ - 2 * wr)) : 2;
-    auto stage2I = [&](const double* __restrict__ sw, const double* __restrict__ Lr, int s, auto&& between) {
+    auto stage2I = [&](const double* __restrict__ sw, const double* __restrict__ Lr, int s, auto&& between, auto FULLT) {
+      constexpr bool FULL = decltype(FULLT)::value;
       double T[2][NJ][2];
 #pragma unroll
       for (int i = 0; i < 2; ++i)
@@ -213,18 +214,18 @@ k_psi2_bwdp(int64_t rc, int M, int Mp, int nt, int nblocks, int qk, const double
 #pragma unroll
       for (int ks = 0; ks < 16; ++ks) {
         const int k0 = 4 * ks;
-        if (k0 < kJ) {                             // (uniform) columns of L past the valid width are zero
+        if (FULL || k0 < kJ) {                     // (uniform) columns of L past the valid width are zero
           double a[2], bq[NJ];
 #pragma unroll
           for (int i = 0; i < 2; ++i)
-            if (i < niI) a[i] = pa[i * 8 * RSL + k0];
+            if (FULL || i < niI) a[i] = pa[i * 8 * RSL + k0];
 #pragma unroll
           for (int j = 0; j < NJ; ++j) bq[j] = pb[k0 * RS + 8 * j];
 #pragma unroll
           for (int i = 0; i < 2; ++i)
 #pragma unroll
             for (int j = 0; j < NJ; ++j)
-              if (i < niI) dmma(T[i][j][0], T[i][j][1], a[i], bq[j]);
+              if (FULL || i < niI) dmma(T[i][j][0], T[i][j][1], a[i], bq[j]);
         }
         between(ks);
       }
@@ -275,11 +276,13 @@ k_psi2_bwdp(int64_t rc, int M, int Mp, int nt, int nblocks, int qk, const double
         }
       const int nj = (tJ - wc + 1) >> 1;           // this warp's valid column tiles c = 2 j + wc < tJ  (0..4)
       const int niJ = (wr < tJ ? 1 : 0) + (wr + 4 < tJ ? 1 : 0);   // stage 2-J: row tiles r = wr + 4 i < tJ of the J tile
+      auto rows = [&](auto FULLT) {
+      constexpr bool FULL = decltype(FULLT)::value;
       double accN[2][4][2];                        // exponents of the next row (stage 1 output)
       double rs[2], cs[8];
       // epilogue of one (i, j) accumulator pair of the row held in accN: exp, Psi2 side sum, L, lambda partials
       auto e_pair = [&](int i, int j, double* __restrict__ Lw) {
-        if (j >= nj) return;                       // (uniform) tile past the valid width
+        if (!FULL && j >= nj) return;              // (uniform) tile past the valid width
         const double p0 = exp_tab(accN[i][j][0], sT), p1 = exp_tab(accN[i][j][1], sT);
         const int off = (16 * wr + 8 * i + g) * RSL + 16 * j + 8 * wc + 2 * t;
         if constexpr (FUSE) {
@@ -330,14 +333,14 @@ k_psi2_bwdp(int64_t rc, int M, int Mp, int nt, int nblocks, int qk, const double
           double a[2], bq[NJ];
 #pragma unroll
           for (int i = 0; i < 2; ++i)
-            if (i < niJ) a[i] = pa[k0 * RSL + 32 * i];
+            if (FULL || i < niJ) a[i] = pa[k0 * RSL + 32 * i];
 #pragma unroll
           for (int j = 0; j < NJ; ++j) bq[j] = pb[k0 * RS + 8 * j] * wq[j];
 #pragma unroll
           for (int i = 0; i < 2; ++i)
 #pragma unroll
             for (int j = 0; j < NJ; ++j)
-              if (i < niJ) dmma(accJ[i][j][0], accJ[i][j][1], a[i], bq[j]);
+              if (FULL || i < niJ) dmma(accJ[i][j][0], accJ[i][j][1], a[i], bq[j]);
           if constexpr (E) {
             // 8 accumulator pairs over k-steps 0,1, 3,4, 6,7, 9,10; the lambda reductions follow at 11,
             // so their shuffle chains still have four k-steps of DMMAs behind them
@@ -353,7 +356,7 @@ k_psi2_bwdp(int64_t rc, int M, int Mp, int nt, int nblocks, int qk, const double
       {                                            // prologue: exponents and L of the first row
         const double *sw, *vI, *vJ;
         vec(r0, sw, vI, vJ);
-        stage1x<QC>(sZI, sZJ, sw, vI, vJ, qk, wr, wc, lane, nj, accN);
+        stage1x<QC, FULL>(sZI, sZJ, sw, vI, vJ, qk, wr, wc, lane, nj, accN);
         double* Lw = sL + (int)(r0 & 1) * 64 * RSL;
         e_begin();
 #pragma unroll
@@ -383,15 +386,18 @@ k_psi2_bwdp(int64_t rc, int M, int Mp, int nt, int nblocks, int qk, const double
         if (n + 1 < r1) {
           const double *sw1, *vI1, *vJ1;
           vec(n + 1, sw1, vI1, vJ1);
-          stage1x<QC>(sZI, sZJ, sw1, vI1, vJ1, qk, wr, wc, lane, nj, accN);
-          stage2I(sw, Lr, s, nothing);
+          stage1x<QC, FULL>(sZI, sZJ, sw1, vI1, vJ1, qk, wr, wc, lane, nj, accN);
+          stage2I(sw, Lr, s, nothing, FULLT);
           stage2J(sw, Lr, Lw, s ^ 1, std::true_type{});
         } else {
-          stage2I(sw, Lr, s, nothing);
+          stage2I(sw, Lr, s, nothing, FULLT);
           stage2J(sw, Lr, Lw, s ^ 1, std::false_type{});
         }
         __syncthreads();   // L(n+1) + its lambda partials + W(n) complete; every read of L(n) done
       }
+      };
+      if (tJ == 8) rows(std::true_type{});
+      else rows(std::false_type{});
     } else {
       // ---------------------------------------------------------------- diagonal block
       int ti[5], tj[5], cnt;
@@ -403,6 +409,8 @@ k_psi2_bwdp(int64_t rc, int M, int Mp, int nt, int nblocks, int qk, const double
         creg[s5][0] = c2.x;
         creg[s5][1] = c2.y;
       }
+      auto rows = [&](auto FULLT) {
+      constexpr bool FULL = decltype(FULLT)::value;
       double accN[5][2];
       auto e_tile = [&](int s5, double* __restrict__ Lw) {
         if (s5 < cnt) {
@@ -426,7 +434,7 @@ k_psi2_bwdp(int64_t rc, int M, int Mp, int nt, int nblocks, int qk, const double
       {
         const double *sw, *vI, *vJ;
         vec(r0, sw, vI, vJ);
-        stage1x_diag<QC>(sZI, sw, vI, qk, ti, tj, cnt, lane, accN);
+        stage1x_diag<QC, FULL>(sZI, sw, vI, qk, ti, tj, cnt, lane, accN);
         double* Lw = sL + (int)(r0 & 1) * 64 * RSL;
 #pragma unroll
         for (int s5 = 0; s5 < 5; ++s5) e_tile(s5, Lw);
@@ -455,15 +463,18 @@ k_psi2_bwdp(int64_t rc, int M, int Mp, int nt, int nblocks, int qk, const double
         if (n + 1 < r1) {
           const double *sw1, *vI1, *vJ1;
           vec(n + 1, sw1, vI1, vJ1);
-          stage1x_diag<QC>(sZI, sw1, vI1, qk, ti, tj, cnt, lane, accN);
+          stage1x_diag<QC, FULL>(sZI, sw1, vI1, qk, ti, tj, cnt, lane, accN);
           stage2I(sw, Lr, s, [&](int ks) {
             if (ks % 3 == 0 && ks < 15) e_tile(ks / 3, Lw);      // 5 tiles over k-steps 0, 3, 6, 9, 12
-          });
+          }, FULLT);
         } else {
-          stage2I(sw, Lr, s, nothing);
+          stage2I(sw, Lr, s, nothing, FULLT);
         }
         __syncthreads();
       }
+          };
+      if (tJ == 8) rows(std::true_type{});
+      else rows(std::false_type{});
     }
     flush_wq(r1 - 1);
     if constexpr (FUSE) {

@@ -27,6 +27,8 @@
 // doubles makes every fragment load (rows by lane/4, cols by lane%4, or transposed)
 // hit each bank exactly twice, the minimum for 256 B.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace rgp {
@@ -176,7 +178,9 @@ RGP_DEVINL void stage1_diag(const double* __restrict__ sZ, const double* __restr
 
 // stage 1 with the three row vectors given separately (they live in different parts of a batch slot);
 // nj = number of this warp's column tiles (0..4) that are valid
-template <int QC>
+// FULL: every tile is valid (nj = 4 at compile time) - the hot path carries no predicates, so ptxas keeps
+// its software pipelining of the fragment loads and the 16-way interleaving of the exps
+template <int QC, bool FULL>
 RGP_DEVINL void stage1x(const double* __restrict__ sZI, const double* __restrict__ sZJ,
                         const double* __restrict__ sw, const double* __restrict__ hI,
                         const double* __restrict__ hJ, int qk, int wr, int wc, int lane, int nj,
@@ -205,12 +209,12 @@ RGP_DEVINL void stage1x(const double* __restrict__ sZI, const double* __restrict
     for (int i = 0; i < 2; ++i) a[i] = pa[i * 8 * RS + k0] * wv;
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-      if (j < nj) b[j] = pb[j * 16 * RS + k0];
+      if (FULL || j < nj) b[j] = pb[j * 16 * RS + k0];
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (j < nj) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        if (FULL || j < nj) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
   }
 }
 
@@ -232,10 +236,11 @@ RGP_DEVINL void diag_tiles_x(int wid, int tv, int (&ti)[5], int (&tj)[5], int& c
   }
 }
 
-template <int QC>
-RGP_DEVINL void stage1x_diag(const double* __restrict__ sZ, const double* __restrict__ sw,
-                             const double* __restrict__ hI, int qk, const int (&ti)[5], const int (&tj)[5], int cnt,
-                             int lane, double (&acc)[5][2]) {
+// CNT > 0: tile count known at compile time (full blocks: 5 or 4 per warp); CNT = 0: runtime cnt (edge block)
+template <int QC, int CNT>
+RGP_DEVINL void stage1x_diag_n(const double* __restrict__ sZ, const double* __restrict__ sw,
+                               const double* __restrict__ hI, int qk, const int (&ti)[5], const int (&tj)[5], int cnt,
+                               int lane, double (&acc)[5][2]) {
   constexpr int RS = QC + 4;
   const int g = lane >> 2, t = lane & 3;
   const double* pa[5];
@@ -255,13 +260,25 @@ RGP_DEVINL void stage1x_diag(const double* __restrict__ sZ, const double* __rest
     double a[5], b[5];
 #pragma unroll
     for (int s = 0; s < 5; ++s)
-      if (s < cnt) {
+      if (CNT ? s < CNT : s < cnt) {
         a[s] = pa[s][k0] * wv;
         b[s] = pb[s][k0];
       }
 #pragma unroll
     for (int s = 0; s < 5; ++s)
-      if (s < cnt) dmma(acc[s][0], acc[s][1], a[s], b[s]);
+      if (CNT ? s < CNT : s < cnt) dmma(acc[s][0], acc[s][1], a[s], b[s]);
+  }
+}
+
+template <int QC, bool FULL>
+RGP_DEVINL void stage1x_diag(const double* __restrict__ sZ, const double* __restrict__ sw,
+                             const double* __restrict__ hI, int qk, const int (&ti)[5], const int (&tj)[5], int cnt,
+                             int lane, double (&acc)[5][2]) {
+  if constexpr (FULL) {      // the tile count is warp-uniform; branching outside the k loop keeps it straight-line
+    if (cnt == 5) stage1x_diag_n<QC, 5>(sZ, sw, hI, qk, ti, tj, cnt, lane, acc);
+    else stage1x_diag_n<QC, 4>(sZ, sw, hI, qk, ti, tj, cnt, lane, acc);
+  } else {
+    stage1x_diag_n<QC, 0>(sZ, sw, hI, qk, ti, tj, cnt, lane, acc);
   }
 }
 
@@ -320,22 +337,27 @@ k_psi2_fwd(int64_t rc, int M, int nt, int nblocks, int qk, const double* __restr
       for (int i = 0; i < 2; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) pacc[i][j][0] = pacc[i][j][1] = 0.0;
-      for (int64_t n = r0; n < r1; ++n) {
-        const double* v = sV + (n % 3) * VB;
-        double nxt = vec_load(n + 1);             // row n+1 vectors, stored after stage 1
-        double acc[2][4][2];
-        stage1x<QC>(sZI, sZJ, v, v + QC, v + QC + 64, qk, wr, wc, lane, nj, acc);
-        if (tid < VB) sV[((n + 1) % 3) * VB + tid] = nxt;
+      auto rows = [&](auto FULLT) {
+        constexpr bool FULL = decltype(FULLT)::value;
+        for (int64_t n = r0; n < r1; ++n) {
+          const double* v = sV + (n % 3) * VB;
+          double nxt = vec_load(n + 1);             // row n+1 vectors, stored after stage 1
+          double acc[2][4][2];
+          stage1x<QC, FULL>(sZI, sZJ, v, v + QC, v + QC + 64, qk, wr, wc, lane, nj, acc);
+          if (tid < VB) sV[((n + 1) % 3) * VB + tid] = nxt;
 #pragma unroll
-        for (int i = 0; i < 2; ++i)
+          for (int i = 0; i < 2; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (j < nj) {
-              pacc[i][j][0] += exp_tab(acc[i][j][0], sT);
-              pacc[i][j][1] += exp_tab(acc[i][j][1], sT);
-            }
-        __syncthreads();                          // slot (n+1)%3 visible
-      }
+            for (int j = 0; j < 4; ++j)
+              if (FULL || j < nj) {
+                pacc[i][j][0] += exp_tab(acc[i][j][0], sT);
+                pacc[i][j][1] += exp_tab(acc[i][j][1], sT);
+              }
+          __syncthreads();                          // slot (n+1)%3 visible
+        }
+      };
+      if (tJ == 8) rows(std::true_type{});
+      else rows(std::false_type{});
 #pragma unroll
       for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -353,20 +375,25 @@ k_psi2_fwd(int64_t rc, int M, int nt, int nblocks, int qk, const double* __restr
       double pacc[5][2];
 #pragma unroll
       for (int s = 0; s < 5; ++s) pacc[s][0] = pacc[s][1] = 0.0;
-      for (int64_t n = r0; n < r1; ++n) {
-        const double* v = sV + (n % 3) * VB;
-        double nxt = vec_load(n + 1);
-        double acc[5][2];
-        stage1x_diag<QC>(sZI, v, v + QC, qk, ti, tj, cnt, lane, acc);
-        if (tid < VB) sV[((n + 1) % 3) * VB + tid] = nxt;
+      auto rows = [&](auto FULLT) {
+        constexpr bool FULL = decltype(FULLT)::value;
+        for (int64_t n = r0; n < r1; ++n) {
+          const double* v = sV + (n % 3) * VB;
+          double nxt = vec_load(n + 1);
+          double acc[5][2];
+          stage1x_diag<QC, FULL>(sZI, v, v + QC, qk, ti, tj, cnt, lane, acc);
+          if (tid < VB) sV[((n + 1) % 3) * VB + tid] = nxt;
 #pragma unroll
-        for (int s = 0; s < 5; ++s)
-          if (s < cnt) {
-            pacc[s][0] += exp_tab(acc[s][0], sT);
-            pacc[s][1] += exp_tab(acc[s][1], sT);
-          }
-        __syncthreads();
-      }
+          for (int s = 0; s < 5; ++s)
+            if (s < cnt) {
+              pacc[s][0] += exp_tab(acc[s][0], sT);
+              pacc[s][1] += exp_tab(acc[s][1], sT);
+            }
+          __syncthreads();
+        }
+      };
+      if (tJ == 8) rows(std::true_type{});
+      else rows(std::false_type{});
 #pragma unroll
       for (int s = 0; s < 5; ++s)
         if (s < cnt) {
