@@ -6,6 +6,7 @@
 #include "fast_prep.cuh"
 #include "psi2_kernels.cuh"
 #include "psi2_bwdp.cuh"
+#include "psi2_bwdw.cuh"
 
 namespace rgp {
 namespace fast {
@@ -46,6 +47,10 @@ static int init(rgp_psi_ctx*) {
   RGP_TRY((init_bwdp<64, 3>()));
   RGP_TRY((init_bwdp<64, 4>()));
   RGP_TRY((init_bwdp<128, 4>()));
+  RGP_CUDA(cudaFuncSetAttribute((k_psi2_bwdw<64, 4, false>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (P2CfgW<64, 4>::SMEM)));
+  RGP_CUDA(cudaFuncSetAttribute((k_psi2_bwdw<64, 4, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (P2CfgW<64, 4>::SMEM)));
   return 0;
 }
 
@@ -134,13 +139,25 @@ static int launch_bwd(rgp_psi_ctx* h, cudaStream_t st, const Shape& s, int64_t r
                       const double* Zt, const double* Ct, const double* w, const double* HP,
                       double* lam, double* Wq, double* ACCp, double* P2p) {
   // Two Psi2 backward kernels (profiles/SUMMARY_r02.md, "A/B").  The software-pipelined kernel (psi2_bwdp.cuh)
-  // computes only the valid 8 x 8 tiles of a narrow last tile of M and sizes its stage-2 width to Q in steps of
-  // 16, and is 3 % faster when the pass also accumulates Psi2 (fused); the row-at-a-time kernel is 1.5 % faster on
-  // full tiles at the full stage-2 width (M a multiple of 64, 48 < Q <= 64: the headline shape).
+  // computes only the valid 8 x 8 tiles of a narrow last tile of M, sizes its stage-2 width to Q in steps of 16,
+  // and is 3 % faster when the pass also accumulates Psi2 (fused); the row-at-a-time kernel is 1.5 - 7 % faster
+  // for the plain backward pass at every other shape measured (profiles/kernel_times_small_r02.jsonl).
   // bwd_pipe: 2 = that choice (default), 0 / 1 = force one of them (A/B measurements, parity tests).
   const bool fused = P2p != nullptr;
-  const bool full = QC == 64 && s.Q > 48 && s.M % 64 == 0;
-  const bool pipe = h->bwd_pipe == 1 || (h->bwd_pipe == 2 && (fused || !full));
+  if constexpr (QC == 64) {
+    // warp-specialised kernel (psi2_bwdw.cuh): full stage-2 width, enough rows per CTA to amortise its prologue
+    if ((h->bwd_pipe == 3 || (h->bwd_pipe == 2 && h->bwd_roles)) && s.Q > 48 && G == 1 && rows >= (int64_t)64 * R) {
+      if (fused)
+        RGP_LAUNCH(h, st, "psi2_bwd_fused", (k_psi2_bwdw<64, 4, true>), dim3(R, G), PW_THREADS, (P2CfgW<64, 4>::SMEM),
+                   rows, s.Mp, s.nt, s.nblocks, s.qk, Zt, Ct, w, HP, lam, Wq, ACCp, P2p);
+      else
+        RGP_LAUNCH(h, st, "psi2_bwd", (k_psi2_bwdw<64, 4, false>), dim3(R, G), PW_THREADS, (P2CfgW<64, 4>::SMEM),
+                   rows, s.Mp, s.nt, s.nblocks, s.qk, Zt, Ct, w, HP, lam, Wq, ACCp, (double*)nullptr);
+      return 0;
+    }
+  }
+  const bool narrow = QC == 64 && s.Q <= 48;      // stage-2 width 48 instead of 64: pipelined kernel 17 % faster (M=200, Q=40)
+  const bool pipe = h->bwd_pipe == 1 || (h->bwd_pipe == 2 && (fused || narrow));
   if constexpr (QC == 128) {
     if (fused) return set_error(RGP_PSI_ERR_INVALID, "fused pass is not built for Q > 64");
   }
@@ -253,7 +270,7 @@ static int forward(rgp_psi_ctx* h, cudaStream_t st, int64_t N, int M, int Q, con
     else if (QC == 32) RGP_TRY(launch_fwd<32>(h, st, s, rows, Rc, Gc, Zt, w, HP, P2p));
     else if (QC == 64) RGP_TRY(launch_fwd<64>(h, st, s, rows, Rc, Gc, Zt, w, HP, P2p));
     else RGP_TRY(launch_fwd<128>(h, st, s, rows, Rc, Gc, Zt, w, HP, P2p));
-    RGP_LAUNCH(h, st, "psi2_reduce", k_psi2_reduce, s.nblocks, 256, 0, M, s.nt, Rc, variance * variance,
+    RGP_LAUNCH(h, st, "psi2_reduce", k_psi2_reduce, dim3(s.nblocks, 16), 256, 0, M, s.nt, Rc, variance * variance,
                P2p, (chunk > 0 || h->accumulate) ? 1 : 0, psi2);
   }
   return 0;
@@ -344,7 +361,7 @@ static int backward(rgp_psi_ctx* h, cudaStream_t st, int64_t N, int M, int Q, co
     else if (QC == 64) RGP_TRY(launch_bwd<64>(h, st, s, rows, Rc, Gc, Zt, Ct, w, HP, lam, Wq, ACCp, P2p));
     else RGP_TRY(launch_bwd<128>(h, st, s, rows, Rc, Gc, Zt, Ct, w, HP, lam, Wq, ACCp, P2p));
     if (P2p)
-      RGP_LAUNCH(h, st, "psi2_reduce", k_psi2_reduce, s.nblocks, 256, 0, M, s.nt, Rc, variance * variance, P2p,
+      RGP_LAUNCH(h, st, "psi2_reduce", k_psi2_reduce, dim3(s.nblocks, 16), 256, 0, M, s.nt, Rc, variance * variance, P2p,
                  (chunk > 0 || h->accumulate) ? 1 : 0, psi2_out);
     if (Gc > 1) {
       RGP_LAUNCH(h, st, "collapse", k_collapse, ceil_div(rows * Mp, 256), 256, 0, rows * Mp, Gc, lam);

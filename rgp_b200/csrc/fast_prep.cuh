@@ -321,7 +321,9 @@ __global__ void k_final_small(int M, int Mp, int Q, int QC, const double* __rest
   }
 }
 
-// Psi2[m,m'] (+)= s2^2 * sum_r P2p[b][r][64][64], mirrored.  One CTA per block b.
+// Psi2[m,m'] (+)= s2^2 * sum_r P2p[b][r][64][64], mirrored.  grid = (blocks b, 16 slices of the 64 x 64 tile):
+// one tile element per thread, the R partials summed in fixed order (deterministic) with eight loads in flight
+// (a single dependent chain over R = 148 ... 296 partials made this the longest kernel of a small evaluation).
 __global__ void __launch_bounds__(256) k_psi2_reduce(int M, int nt, int R, double v2,
                                                     const double* __restrict__ P2p,
                                                     int accumulate, double* __restrict__ psi2) {
@@ -329,20 +331,28 @@ __global__ void __launch_bounds__(256) k_psi2_reduce(int M, int nt, int R, doubl
   int I = 0, rem = b;
   while (rem >= nt - I) { rem -= nt - I; ++I; }
   int J = I + rem;
-  for (int idx = threadIdx.x; idx < 4096; idx += blockDim.x) {
-    int r = idx >> 6, c = idx & 63;
-    int m = I * 64 + r, mp = J * 64 + c;
-    if (m >= M || mp >= M) continue;
-    double s = 0.0;
-    for (int k = 0; k < R; ++k) s += P2p[((int64_t)b * R + k) * 4096 + idx];
-    s *= v2;
-    if (accumulate) {
-      psi2[m * M + mp] += s;
-      if (I != J) psi2[mp * M + m] += s;
-    } else {
-      psi2[m * M + mp] = s;
-      if (I != J) psi2[mp * M + m] = s;
-    }
+  const int idx = blockIdx.y * 256 + threadIdx.x;
+  const int r = idx >> 6, c = idx & 63;
+  const int m = I * 64 + r, mp = J * 64 + c;
+  if (m >= M || mp >= M) return;
+  const double* p = P2p + (int64_t)b * R * 4096 + idx;
+  double s = 0.0;
+  int k = 0;
+  for (; k + 8 <= R; k += 8) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = p[(int64_t)(k + u) * 4096];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s += v[u];
+  }
+  for (; k < R; ++k) s += p[(int64_t)k * 4096];
+  s *= v2;
+  if (accumulate) {
+    psi2[m * M + mp] += s;
+    if (I != J) psi2[mp * M + m] += s;
+  } else {
+    psi2[m * M + mp] = s;
+    if (I != J) psi2[mp * M + m] = s;
   }
 }
 

@@ -23,7 +23,7 @@ ref = None
 for name in variants:
     dp = DevicePsi(0)
     peak = dp.handle.fp64_peak(reps=3)
-    dp.handle.set_option("bwd_pipe", {"pipe": 1, "rowloop": 0}.get(name, 2))
+    dp.handle.set_option("bwd_pipe", {"pipe": 1, "rowloop": 0, "roles": 3}.get(name, 2))
     for _ in range(2):
         dp.forward(mu, S, Z, ell, 1.3)
         out = dp.backward(mu, S, Z, ell, 1.3, -0.5, dL1, dL2)
