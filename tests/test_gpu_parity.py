@@ -408,7 +408,7 @@ def test_warp_specialised_backward_kernel_matches_oracle():
     dL0, dL1, dL2 = make_upstream(N, M, seed=22)
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
     dp = DevicePsi(0, impl=0)
-    dp.handle.set_option("bwd_pipe", 4)
+    dp.handle.set_option("bwd_pipe", 3)
     dp.handle.set_option("profile", 1)
     dp.handle.reset_counters()
     out = dp.backward(t(mu), t(S), t(Z), t(ell), var, t(dL0), t(dL1), t(dL2))
