@@ -23,7 +23,7 @@
 // warps compute the 36 upper-triangle tiles (balanced 5/4 per warp) and store them mirrored, the scalar warps
 // see a full symmetric tile.
 #pragma once
-#include "psi2_bwdp.cuh"
+#include "../psi2_bwdp.cuh"
 
 namespace rgp {
 namespace fast {

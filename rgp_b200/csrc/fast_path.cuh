@@ -6,7 +6,9 @@
 #include "fast_prep.cuh"
 #include "psi2_kernels.cuh"
 #include "psi2_bwdp.cuh"
-#include "psi2_bwdw.cuh"
+#ifdef RGP_DEBUG
+#include "experimental/psi2_bwdw.cuh"   // warp-specialised variant: a measured negative result, experiment builds only
+#endif
 
 namespace rgp {
 namespace fast {
@@ -47,10 +49,12 @@ static int init(rgp_psi_ctx*) {
   RGP_TRY((init_bwdp<64, 3>()));
   RGP_TRY((init_bwdp<64, 4>()));
   RGP_TRY((init_bwdp<128, 4>()));
+#ifdef RGP_DEBUG
   RGP_CUDA(cudaFuncSetAttribute((k_psi2_bwdw<64, 4, false>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (P2CfgW<64, 4>::SMEM)));
   RGP_CUDA(cudaFuncSetAttribute((k_psi2_bwdw<64, 4, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (P2CfgW<64, 4>::SMEM)));
+#endif
   return 0;
 }
 
@@ -113,7 +117,7 @@ template <int QC>
 static int launch_fwd(rgp_psi_ctx* h, cudaStream_t st, const Shape& s, int64_t rows, int R, int G,
                       const double* Zt, const double* w, const double* HP, double* P2p) {
   RGP_LAUNCH(h, st, "psi2_fwd", (k_psi2_fwd<QC>), dim3(R, G), P2_THREADS, P2Cfg<QC>::FWD_SMEM + h->fwd_smem_pad, rows,
-             s.M, s.nt, s.nblocks, s.qk, Zt, w, HP, P2p);
+             s.nt, s.nblocks, s.qk, Zt, w, HP, P2p);
   return 0;
 }
 
@@ -124,13 +128,13 @@ static int launch_bwdp(rgp_psi_ctx* h, cudaStream_t st, const Shape& s, int64_t 
   if constexpr (QC <= 64) {
     if (P2p) {     // fused forward + backward: the kernel also accumulates the Psi2 partial tiles
       RGP_LAUNCH(h, st, "psi2_bwd_fused", (k_psi2_bwdp<QC, NJ, true>), dim3(R, G), P2_THREADS,
-                 (P2CfgP<QC, NJ>::FUSED_SMEM), rows, s.M, s.Mp, s.nt, s.nblocks, s.qk, Zt, Ct, w, HP, lam, Wq, ACCp, 0, P2p);
+                 (P2CfgP<QC, NJ>::FUSED_SMEM), rows, s.Mp, s.nt, s.nblocks, s.qk, Zt, Ct, w, HP, lam, Wq, ACCp, 0, P2p);
       return 0;
     }
   }
   for (int qoff = 0; qoff < s.Q; qoff += 16 * NJ)   // two passes for 64 < Q <= 128 (one if Q <= 64)
     RGP_LAUNCH(h, st, "psi2_bwd", (k_psi2_bwdp<QC, NJ, false>), dim3(R, G), P2_THREADS, (P2CfgP<QC, NJ>::SMEM), rows,
-               s.M, s.Mp, s.nt, s.nblocks, s.qk, Zt, Ct, w, HP, lam, Wq, ACCp, qoff, (double*)nullptr);
+               s.Mp, s.nt, s.nblocks, s.qk, Zt, Ct, w, HP, lam, Wq, ACCp, qoff, (double*)nullptr);
   return 0;
 }
 
@@ -139,14 +143,14 @@ static int launch_bwd(rgp_psi_ctx* h, cudaStream_t st, const Shape& s, int64_t r
                       const double* Zt, const double* Ct, const double* w, const double* HP,
                       double* lam, double* Wq, double* ACCp, double* P2p) {
   // Two Psi2 backward kernels (profiles/SUMMARY_r02.md, "A/B").  The software-pipelined kernel (psi2_bwdp.cuh)
-  // computes only the valid 8 x 8 tiles of a narrow last tile of M, sizes its stage-2 width to Q in steps of 16,
-  // and is 3 % faster when the pass also accumulates Psi2 (fused); the row-at-a-time kernel is 1.5 - 7 % faster
-  // for the plain backward pass at every other shape measured (profiles/kernel_times_small_r02.jsonl).
+  // sizes its stage-2 width to Q in steps of 16 and is 3 % faster when the pass also accumulates Psi2 (fused);
+  // the row-at-a-time kernel is 1.5 - 7 % faster for the plain backward pass at every other shape measured.
   // bwd_pipe: 2 = that choice (default), 0 / 1 = force one of them (A/B measurements, parity tests).
   const bool fused = P2p != nullptr;
+#ifdef RGP_DEBUG
   if constexpr (QC == 64) {
-    // warp-specialised kernel (psi2_bwdw.cuh): full stage-2 width, enough rows per CTA to amortise its prologue
-    if ((h->bwd_pipe == 3 || (h->bwd_pipe == 2 && h->bwd_roles)) && s.Q > 48 && G == 1 && rows >= (int64_t)64 * R) {
+    // warp-specialised kernel (experimental/psi2_bwdw.cuh): full stage-2 width, enough rows per CTA to amortise its prologue
+    if (h->bwd_pipe == 3 && s.Q > 48 && G == 1 && rows >= (int64_t)64 * R) {
       if (fused)
         RGP_LAUNCH(h, st, "psi2_bwd_fused", (k_psi2_bwdw<64, 4, true>), dim3(R, G), PW_THREADS, (P2CfgW<64, 4>::SMEM),
                    rows, s.Mp, s.nt, s.nblocks, s.qk, Zt, Ct, w, HP, lam, Wq, ACCp, P2p);
@@ -156,6 +160,7 @@ static int launch_bwd(rgp_psi_ctx* h, cudaStream_t st, const Shape& s, int64_t r
       return 0;
     }
   }
+#endif
   const bool narrow = QC == 64 && s.Q <= 48;      // stage-2 width 48 instead of 64: pipelined kernel 17 % faster (M=200, Q=40)
   const bool pipe = h->bwd_pipe == 1 || (h->bwd_pipe == 2 && (fused || narrow));
   if constexpr (QC == 128) {

@@ -33,7 +33,8 @@ namespace rgp {
 namespace fast {
 
 // NJ = 8-wide q tiles per warp in stage 2: the stage-2 outputs cover QS = 16 NJ columns per pass (the two
-// warps of a column pair take 8 NJ each), so Q = 40 runs NJ = 3 (48 columns) instead of padding to 64.
+// warps of a column pair take 8 NJ each), so Q = 40 runs NJ = 3 (48 columns) instead of padding to 64
+// (measured 17 % faster at M = 200, Q = 40, profiles/kernel_times_small_r02.jsonl).
 template <int QC, int NJ_>
 struct P2CfgP {
   static constexpr int RS = QC + 4;
@@ -73,6 +74,82 @@ RGP_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
   } while (!ok);
 }
 
+// stage 1 with the three row vectors given separately (they live in different parts of a batch slot)
+template <int QC>
+RGP_DEVINL void stage1v(const double* __restrict__ sZI, const double* __restrict__ sZJ,
+                        const double* __restrict__ sw, const double* __restrict__ hI,
+                        const double* __restrict__ hJ, int qk, int wr, int wc, int lane,
+                        double (&acc)[2][4][2]) {
+  constexpr int RS = P2Cfg<QC>::RS;
+  const int g = lane >> 2, t = lane & 3;
+  const double* pa = sZI + (16 * wr + g) * RS + t;
+  const double* pb = sZJ + (32 * wc + g) * RS + t;
+  const double* vI = hI + 16 * wr + g;
+  const double* vJ = hJ + 32 * wc + 2 * t;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const double hi = vI[8 * i];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const double2 hj = *reinterpret_cast<const double2*>(vJ + 8 * j);
+      acc[i][j][0] = hi + hj.x;
+      acc[i][j][1] = hi + hj.y;
+    }
+  }
+#pragma unroll 2
+  for (int k0 = 0; k0 < qk; k0 += 4) {
+    const double wv = sw[k0 + t];
+    double a[2], b[4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) a[i] = pa[i * 8 * RS + k0] * wv;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = pb[j * 8 * RS + k0];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+  }
+}
+
+template <int QC, int CNT>
+RGP_DEVINL void stage1v_diag_n(const double* __restrict__ sZ, const double* __restrict__ sw,
+                               const double* __restrict__ hI, int qk, const int (&ti)[5], const int (&tj)[5],
+                               int lane, double (&acc)[5][2]) {
+  constexpr int RS = P2Cfg<QC>::RS;
+  const int g = lane >> 2, t = lane & 3;
+  const double* pa[CNT];
+  const double* pb[CNT];
+#pragma unroll
+  for (int s = 0; s < CNT; ++s) {
+    pa[s] = sZ + (8 * ti[s] + g) * RS + t;
+    pb[s] = sZ + (8 * tj[s] + g) * RS + t;
+    const double hi = hI[8 * ti[s] + g];
+    const double2 hj = *reinterpret_cast<const double2*>(hI + 8 * tj[s] + 2 * t);
+    acc[s][0] = hi + hj.x;
+    acc[s][1] = hi + hj.y;
+  }
+#pragma unroll 2
+  for (int k0 = 0; k0 < qk; k0 += 4) {
+    const double wv = sw[k0 + t];
+    double a[CNT], b[CNT];
+#pragma unroll
+    for (int s = 0; s < CNT; ++s) {
+      a[s] = pa[s][k0] * wv;
+      b[s] = pb[s][k0];
+    }
+#pragma unroll
+    for (int s = 0; s < CNT; ++s) dmma(acc[s][0], acc[s][1], a[s], b[s]);
+  }
+}
+
+template <int QC>
+RGP_DEVINL void stage1v_diag(const double* __restrict__ sZ, const double* __restrict__ sw,
+                             const double* __restrict__ hI, int qk, const int (&ti)[5], const int (&tj)[5], int cnt,
+                             int lane, double (&acc)[5][2]) {
+  if (cnt == 5) stage1v_diag_n<QC, 5>(sZ, sw, hI, qk, ti, tj, lane, acc);
+  else stage1v_diag_n<QC, 4>(sZ, sw, hI, qk, ti, tj, lane, acc);
+}
+
 // =====================================================================================
 // grid = (R row ranges, G block groups); outputs as k_psi2_bwd:
 //   lam [g][rc][Mp], Wq [g][rc][QC] (red.global.add into rows only this CTA touches),
@@ -80,7 +157,7 @@ RGP_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
 // =====================================================================================
 template <int QC, int NJ_, bool FUSE = false>
 __global__ void __launch_bounds__(P2_THREADS, 1)
-k_psi2_bwdp(int64_t rc, int M, int Mp, int nt, int nblocks, int qk, const double* __restrict__ Zt,
+k_psi2_bwdp(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __restrict__ Zt,
             const double* __restrict__ Ct, const double* __restrict__ wrow, const double* __restrict__ HP,
             double* __restrict__ lam, double* __restrict__ Wq, double* __restrict__ ACCp, int qoff,
             double* __restrict__ P2p = nullptr) {
@@ -137,12 +214,6 @@ k_psi2_bwdp(int64_t rc, int M, int Mp, int nt, int nblocks, int qk, const double
     const double* hI = HP + (size_t)I * rc * 64;
     const double* hJ = HP + (size_t)J * rc * 64;
     const double* cb = Ct + (size_t)b * 4096;
-    // valid part of the J tile (the I tile of an off-diagonal block is always full)
-    const int vJ = (M - 64 * J < 64) ? M - 64 * J : 64;
-    const int tJ = (vJ + 7) >> 3;                 // its 8-wide tiles
-    const int kJ = (vJ + 3) & ~3;                 // K bound of the products that contract over it
-    if (vJ < 64)                                  // skipped tiles of L must read as zeros
-      for (int i = tid; i < 2 * 64 * RSL; i += P2_THREADS) sL[i] = 0.0;
     // batch k of this block = rows [r0 + k VR, ...) -> slot k & 1
     auto issue = [&](int64_t k) {
       const int64_t n0 = r0 + k * VR;
@@ -200,10 +271,7 @@ k_psi2_bwdp(int64_t rc, int M, int Mp, int nt, int nblocks, int qk, const double
 
     // stage 2-I of row n (T = L Z'_J) followed by its folds: accI += ws T, W partial -> sWq slot.
     // ED: interleave the epilogue of the NEXT row of a diagonal block (see below) with the k-steps.
-    // niI = valid 8-row tiles of this warp in the I tile (2 unless this is the narrow last diagonal block)
-    const int niI = diag ? ((tJ - 2 * wr) < 0 ? 0 : ((tJ - 2 * wr) > 2 ? 2 : tJ - 2 * wr)) : 2;
-    auto stage2I = [&](const double* __restrict__ sw, const double* __restrict__ Lr, int s, auto&& between, auto FULLT) {
-      constexpr bool FULL = decltype(FULLT)::value;
+    auto stage2I = [&](const double* __restrict__ sw, const double* __restrict__ Lr, int s, auto&& between) {
       double T[2][NJ][2];
 #pragma unroll
       for (int i = 0; i < 2; ++i)
@@ -214,19 +282,15 @@ k_psi2_bwdp(int64_t rc, int M, int Mp, int nt, int nblocks, int qk, const double
 #pragma unroll
       for (int ks = 0; ks < 16; ++ks) {
         const int k0 = 4 * ks;
-        if (FULL || k0 < kJ) {                     // (uniform) columns of L past the valid width are zero
-          double a[2], bq[NJ];
+        double a[2], bq[NJ];
 #pragma unroll
-          for (int i = 0; i < 2; ++i)
-            if (FULL || i < niI) a[i] = pa[i * 8 * RSL + k0];
+        for (int i = 0; i < 2; ++i) a[i] = pa[i * 8 * RSL + k0];
 #pragma unroll
-          for (int j = 0; j < NJ; ++j) bq[j] = pb[k0 * RS + 8 * j];
+        for (int j = 0; j < NJ; ++j) bq[j] = pb[k0 * RS + 8 * j];
 #pragma unroll
-          for (int i = 0; i < 2; ++i)
+        for (int i = 0; i < 2; ++i)
 #pragma unroll
-            for (int j = 0; j < NJ; ++j)
-              if (FULL || i < niI) dmma(T[i][j][0], T[i][j][1], a[i], bq[j]);
-        }
+          for (int j = 0; j < NJ; ++j) dmma(T[i][j][0], T[i][j][1], a[i], bq[j]);
         between(ks);
       }
       double wp[2 * NJ];
@@ -270,21 +334,16 @@ k_psi2_bwdp(int64_t rc, int M, int Mp, int nt, int nblocks, int qk, const double
       for (int i = 0; i < 2; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const double2 c2 = *reinterpret_cast<const double2*>(cb + (16 * wr + 8 * i + g) * 64 + 16 * j + 8 * wc + 2 * t);
+          const double2 c2 = *reinterpret_cast<const double2*>(cb + (16 * wr + 8 * i + g) * 64 + 32 * wc + 8 * j + 2 * t);
           creg[i][j][0] = c2.x;
           creg[i][j][1] = c2.y;
         }
-      const int nj = (tJ - wc + 1) >> 1;           // this warp's valid column tiles c = 2 j + wc < tJ  (0..4)
-      const int niJ = (wr < tJ ? 1 : 0) + (wr + 4 < tJ ? 1 : 0);   // stage 2-J: row tiles r = wr + 4 i < tJ of the J tile
-      auto rows = [&](auto FULLT) {
-      constexpr bool FULL = decltype(FULLT)::value;
       double accN[2][4][2];                        // exponents of the next row (stage 1 output)
       double rs[2], cs[8];
       // epilogue of one (i, j) accumulator pair of the row held in accN: exp, Psi2 side sum, L, lambda partials
       auto e_pair = [&](int i, int j, double* __restrict__ Lw) {
-        if (!FULL && j >= nj) return;              // (uniform) tile past the valid width
         const double p0 = exp_tab(accN[i][j][0], sT), p1 = exp_tab(accN[i][j][1], sT);
-        const int off = (16 * wr + 8 * i + g) * RSL + 16 * j + 8 * wc + 2 * t;
+        const int off = (16 * wr + 8 * i + g) * RSL + 32 * wc + 8 * j + 2 * t;
         if constexpr (FUSE) {
           double2* pp = reinterpret_cast<double2*>(sP + off);
           double2 o = *pp;
@@ -315,13 +374,13 @@ k_psi2_bwdp(int64_t rc, int M, int Mp, int nt, int nblocks, int qk, const double
         }
         const double tot = reduce8_over_g(cs, lane);
         const int c = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-        sLc[s * 256 + wr * 64 + 16 * (c >> 1) + 8 * wc + 2 * t + (c & 1)] = tot;
+        sLc[s * 256 + wr * 64 + 32 * wc + 8 * (c >> 1) + 2 * t + (c & 1)] = tot;
       };
       // stage 2-J of row n: accJ += L^T (ws Z'_I); WITH_E interleaves the epilogue of row n+1
       auto stage2J = [&](const double* __restrict__ sw, const double* __restrict__ Lr, double* __restrict__ Lw,
                          int snext, auto WITH_E) {
         constexpr bool E = decltype(WITH_E)::value;
-        const double* pa = Lr + t * RSL + 8 * wr + g;              // row tile r = wr + 4 i of the J tile
+        const double* pa = Lr + t * RSL + 16 * wr + g;
         const double* pb = sZI + t * RS + qoff + qbase + g;
         double wq[NJ];
 #pragma unroll
@@ -332,15 +391,13 @@ k_psi2_bwdp(int64_t rc, int M, int Mp, int nt, int nblocks, int qk, const double
           const int k0 = 4 * ks;
           double a[2], bq[NJ];
 #pragma unroll
-          for (int i = 0; i < 2; ++i)
-            if (FULL || i < niJ) a[i] = pa[k0 * RSL + 32 * i];
+          for (int i = 0; i < 2; ++i) a[i] = pa[k0 * RSL + 8 * i];
 #pragma unroll
           for (int j = 0; j < NJ; ++j) bq[j] = pb[k0 * RS + 8 * j] * wq[j];
 #pragma unroll
           for (int i = 0; i < 2; ++i)
 #pragma unroll
-            for (int j = 0; j < NJ; ++j)
-              if (FULL || i < niJ) dmma(accJ[i][j][0], accJ[i][j][1], a[i], bq[j]);
+            for (int j = 0; j < NJ; ++j) dmma(accJ[i][j][0], accJ[i][j][1], a[i], bq[j]);
           if constexpr (E) {
             // 8 accumulator pairs over k-steps 0,1, 3,4, 6,7, 9,10; the lambda reductions follow at 11,
             // so their shuffle chains still have four k-steps of DMMAs behind them
@@ -356,7 +413,7 @@ k_psi2_bwdp(int64_t rc, int M, int Mp, int nt, int nblocks, int qk, const double
       {                                            // prologue: exponents and L of the first row
         const double *sw, *vI, *vJ;
         vec(r0, sw, vI, vJ);
-        stage1x<QC, FULL>(sZI, sZJ, sw, vI, vJ, qk, wr, wc, lane, nj, accN);
+        stage1v<QC>(sZI, sZJ, sw, vI, vJ, qk, wr, wc, lane, accN);
         double* Lw = sL + (int)(r0 & 1) * 64 * RSL;
         e_begin();
 #pragma unroll
@@ -386,22 +443,19 @@ k_psi2_bwdp(int64_t rc, int M, int Mp, int nt, int nblocks, int qk, const double
         if (n + 1 < r1) {
           const double *sw1, *vI1, *vJ1;
           vec(n + 1, sw1, vI1, vJ1);
-          stage1x<QC, FULL>(sZI, sZJ, sw1, vI1, vJ1, qk, wr, wc, lane, nj, accN);
-          stage2I(sw, Lr, s, nothing, FULLT);
+          stage1v<QC>(sZI, sZJ, sw1, vI1, vJ1, qk, wr, wc, lane, accN);
+          stage2I(sw, Lr, s, nothing);
           stage2J(sw, Lr, Lw, s ^ 1, std::true_type{});
         } else {
-          stage2I(sw, Lr, s, nothing, FULLT);
+          stage2I(sw, Lr, s, nothing);
           stage2J(sw, Lr, Lw, s ^ 1, std::false_type{});
         }
         __syncthreads();   // L(n+1) + its lambda partials + W(n) complete; every read of L(n) done
       }
-      };
-      if (tJ == 8) rows(std::true_type{});
-      else rows(std::false_type{});
     } else {
       // ---------------------------------------------------------------- diagonal block
       int ti[5], tj[5], cnt;
-      diag_tiles_x(wid, tJ, ti, tj, cnt);
+      diag_tiles(wid, ti, tj, cnt);
       double creg[5][2];
 #pragma unroll
       for (int s5 = 0; s5 < 5; ++s5) {
@@ -409,8 +463,6 @@ k_psi2_bwdp(int64_t rc, int M, int Mp, int nt, int nblocks, int qk, const double
         creg[s5][0] = c2.x;
         creg[s5][1] = c2.y;
       }
-      auto rows = [&](auto FULLT) {
-      constexpr bool FULL = decltype(FULLT)::value;
       double accN[5][2];
       auto e_tile = [&](int s5, double* __restrict__ Lw) {
         if (s5 < cnt) {
@@ -434,7 +486,7 @@ k_psi2_bwdp(int64_t rc, int M, int Mp, int nt, int nblocks, int qk, const double
       {
         const double *sw, *vI, *vJ;
         vec(r0, sw, vI, vJ);
-        stage1x_diag<QC, FULL>(sZI, sw, vI, qk, ti, tj, cnt, lane, accN);
+        stage1v_diag<QC>(sZI, sw, vI, qk, ti, tj, cnt, lane, accN);
         double* Lw = sL + (int)(r0 & 1) * 64 * RSL;
 #pragma unroll
         for (int s5 = 0; s5 < 5; ++s5) e_tile(s5, Lw);
@@ -463,18 +515,15 @@ k_psi2_bwdp(int64_t rc, int M, int Mp, int nt, int nblocks, int qk, const double
         if (n + 1 < r1) {
           const double *sw1, *vI1, *vJ1;
           vec(n + 1, sw1, vI1, vJ1);
-          stage1x_diag<QC, FULL>(sZI, sw1, vI1, qk, ti, tj, cnt, lane, accN);
+          stage1v_diag<QC>(sZI, sw1, vI1, qk, ti, tj, cnt, lane, accN);
           stage2I(sw, Lr, s, [&](int ks) {
             if (ks % 3 == 0 && ks < 15) e_tile(ks / 3, Lw);      // 5 tiles over k-steps 0, 3, 6, 9, 12
-          }, FULLT);
+          });
         } else {
-          stage2I(sw, Lr, s, nothing, FULLT);
+          stage2I(sw, Lr, s, nothing);
         }
         __syncthreads();
       }
-          };
-      if (tJ == 8) rows(std::true_type{});
-      else rows(std::false_type{});
     }
     flush_wq(r1 - 1);
     if constexpr (FUSE) {
@@ -484,14 +533,12 @@ k_psi2_bwdp(int64_t rc, int M, int Mp, int nt, int nblocks, int qk, const double
         for (int i = 0; i < 2; ++i)
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const int m = 16 * wr + 8 * i + g, mp = 16 * j + 8 * wc + 2 * t;
+            const int m = 16 * wr + 8 * i + g, mp = 32 * wc + 8 * j + 2 * t;
             *reinterpret_cast<double2*>(out + m * 64 + mp) = *reinterpret_cast<const double2*>(sP + m * RSL + mp);
           }
       } else {
-        for (int i = tid; i < 4096; i += P2_THREADS) out[i] = 0.0;   // tiles outside the valid triangle
-        __syncthreads();
         int ti[5], tj[5], cnt;
-        diag_tiles_x(wid, tJ, ti, tj, cnt);
+        diag_tiles(wid, ti, tj, cnt);
 #pragma unroll
         for (int s5 = 0; s5 < 5; ++s5)
           if (s5 < cnt) {
@@ -515,8 +562,8 @@ k_psi2_bwdp(int64_t rc, int M, int Mp, int nt, int nblocks, int qk, const double
         o.x += accI[i][j][0];
         o.y += accI[i][j][1];
         *pI = o;
-        if (!diag) {                               // stage 2-J rows: tile wr + 4 i of the J tile
-          double2* pJ = reinterpret_cast<double2*>(accp + (size_t)(J * 64 + 8 * wr + 32 * i + g) * QC + q);
+        if (!diag) {
+          double2* pJ = reinterpret_cast<double2*>(accp + (size_t)(J * 64 + 16 * wr + 8 * i + g) * QC + q);
           double2 u = *pJ;
           u.x += accJ[i][j][0];
           u.y += accJ[i][j][1];

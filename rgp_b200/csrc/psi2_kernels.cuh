@@ -27,8 +27,6 @@
 // doubles makes every fragment load (rows by lane/4, cols by lane%4, or transposed)
 // hit each bank exactly twice, the minimum for 256 B.
 #pragma once
-#include <type_traits>
-
 #include "common.cuh"
 
 namespace rgp {
@@ -170,125 +168,13 @@ RGP_DEVINL void stage1_diag(const double* __restrict__ sZ, const double* __restr
   else stage1_diag_n<QC, 4>(sZ, v, qk, ti, tj, lane, acc);
 }
 
-// Edge tiles.  M is padded to 64, but a block only computes the 8 x 8 tiles that hold valid inducing
-// points: the column tiles of an off-diagonal block are dealt to the two warps of a column pair
-// alternately (tile c = 2 j + wc), so when the last tile of M is narrow both warps lose work evenly;
-// tiles past the valid width are skipped (predicated DMMAs / exps), and the K loops of stage 2 stop at
-// the valid width.  Nothing reads the skipped part of an L tile except as zeros (cleared per block).
-
-// stage 1 with the three row vectors given separately (they live in different parts of a batch slot);
-// nj = number of this warp's column tiles (0..4) that are valid
-// FULL: every tile is valid (nj = 4 at compile time) - the hot path carries no predicates, so ptxas keeps
-// its software pipelining of the fragment loads and the 16-way interleaving of the exps
-template <int QC, bool FULL>
-RGP_DEVINL void stage1x(const double* __restrict__ sZI, const double* __restrict__ sZJ,
-                        const double* __restrict__ sw, const double* __restrict__ hI,
-                        const double* __restrict__ hJ, int qk, int wr, int wc, int lane, int nj,
-                        double (&acc)[2][4][2]) {
-  constexpr int RS = QC + 4;
-  const int g = lane >> 2, t = lane & 3;
-  const double* pa = sZI + (16 * wr + g) * RS + t;
-  const double* pb = sZJ + (8 * wc + g) * RS + t;              // column tile c = 2 j + wc: rows 8 c + g = 16 j + 8 wc + g
-  const double* vI = hI + 16 * wr + g;
-  const double* vJ = hJ + 8 * wc + 2 * t;
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const double hi = vI[8 * i];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const double2 hj = *reinterpret_cast<const double2*>(vJ + 16 * j);
-      acc[i][j][0] = hi + hj.x;
-      acc[i][j][1] = hi + hj.y;
-    }
-  }
-#pragma unroll 2
-  for (int k0 = 0; k0 < qk; k0 += 4) {
-    const double wv = sw[k0 + t];
-    double a[2], b[4];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) a[i] = pa[i * 8 * RS + k0] * wv;
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (FULL || j < nj) b[j] = pb[j * 16 * RS + k0];
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (FULL || j < nj) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-  }
-}
-
-// Diagonal blocks (I == J) are symmetric: only the upper-triangle 8 x 8 tiles of the VALID tv x tv tile
-// grid are computed and mirrored on store.  Tile idx (row-major over the triangle) goes to warp idx % 8.
-RGP_DEVINL void diag_tiles_x(int wid, int tv, int (&ti)[5], int (&tj)[5], int& cnt) {
-  const int count = tv * (tv + 1) / 2;
-  cnt = 0;
-#pragma unroll
-  for (int s = 0; s < 5; ++s) {
-    int idx = wid + 8 * s;
-    const bool ok = idx < count;
-    if (!ok) idx = 0;
-    int r = 0;
-    while (idx >= tv - r) { idx -= tv - r; ++r; }
-    ti[s] = r;
-    tj[s] = r + idx;
-    cnt += ok ? 1 : 0;
-  }
-}
-
-// CNT > 0: tile count known at compile time (full blocks: 5 or 4 per warp); CNT = 0: runtime cnt (edge block)
-template <int QC, int CNT>
-RGP_DEVINL void stage1x_diag_n(const double* __restrict__ sZ, const double* __restrict__ sw,
-                               const double* __restrict__ hI, int qk, const int (&ti)[5], const int (&tj)[5], int cnt,
-                               int lane, double (&acc)[5][2]) {
-  constexpr int RS = QC + 4;
-  const int g = lane >> 2, t = lane & 3;
-  const double* pa[5];
-  const double* pb[5];
-#pragma unroll
-  for (int s = 0; s < 5; ++s) {
-    pa[s] = sZ + (8 * ti[s] + g) * RS + t;
-    pb[s] = sZ + (8 * tj[s] + g) * RS + t;
-    const double hi = hI[8 * ti[s] + g];
-    const double2 hj = *reinterpret_cast<const double2*>(hI + 8 * tj[s] + 2 * t);
-    acc[s][0] = hi + hj.x;
-    acc[s][1] = hi + hj.y;
-  }
-#pragma unroll 2
-  for (int k0 = 0; k0 < qk; k0 += 4) {
-    const double wv = sw[k0 + t];
-    double a[5], b[5];
-#pragma unroll
-    for (int s = 0; s < 5; ++s)
-      if (CNT ? s < CNT : s < cnt) {
-        a[s] = pa[s][k0] * wv;
-        b[s] = pb[s][k0];
-      }
-#pragma unroll
-    for (int s = 0; s < 5; ++s)
-      if (CNT ? s < CNT : s < cnt) dmma(acc[s][0], acc[s][1], a[s], b[s]);
-  }
-}
-
-template <int QC, bool FULL>
-RGP_DEVINL void stage1x_diag(const double* __restrict__ sZ, const double* __restrict__ sw,
-                             const double* __restrict__ hI, int qk, const int (&ti)[5], const int (&tj)[5], int cnt,
-                             int lane, double (&acc)[5][2]) {
-  if constexpr (FULL) {      // the tile count is warp-uniform; branching outside the k loop keeps it straight-line
-    if (cnt == 5) stage1x_diag_n<QC, 5>(sZ, sw, hI, qk, ti, tj, cnt, lane, acc);
-    else stage1x_diag_n<QC, 4>(sZ, sw, hI, qk, ti, tj, cnt, lane, acc);
-  } else {
-    stage1x_diag_n<QC, 0>(sZ, sw, hI, qk, ti, tj, cnt, lane, acc);
-  }
-}
-
 // =====================================================================================
 // Forward: partial Psi2 tiles.  grid = (R row ranges, G block groups).
 //   P2p[b][r][64][64] = sum_{n in range r} exp(E_n[m,m'])                    (no s2^2 yet)
 // =====================================================================================
 template <int QC>
 __global__ void __launch_bounds__(P2_THREADS, 2)
-k_psi2_fwd(int64_t rc, int M, int nt, int nblocks, int qk, const double* __restrict__ Zt,
+k_psi2_fwd(int64_t rc, int nt, int nblocks, int qk, const double* __restrict__ Zt,
            const double* __restrict__ wrow, const double* __restrict__ HP,
            double* __restrict__ P2p) {
   using C = P2Cfg<QC>;
@@ -327,73 +213,55 @@ k_psi2_fwd(int64_t rc, int M, int nt, int nblocks, int qk, const double* __restr
     if (r0 < r1 && tid < VB) sV[(r0 % 3) * VB + tid] = vec_load(r0);
     __syncthreads();
     double* out = P2p + ((size_t)b * R + blockIdx.x) * 4096;
-    const int vJ = (M - 64 * J < 64) ? M - 64 * J : 64;      // valid part of the J tile: only its 8-wide tiles are computed
-    const int tJ = (vJ + 7) >> 3;
 
     if (!diag) {
-      const int nj = (tJ - wc + 1) >> 1;                      // column tiles c = 2 j + wc < tJ of this warp
       double pacc[2][4][2];
 #pragma unroll
       for (int i = 0; i < 2; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) pacc[i][j][0] = pacc[i][j][1] = 0.0;
-      auto rows = [&](auto FULLT) {
-        constexpr bool FULL = decltype(FULLT)::value;
-        for (int64_t n = r0; n < r1; ++n) {
-          const double* v = sV + (n % 3) * VB;
-          double nxt = vec_load(n + 1);             // row n+1 vectors, stored after stage 1
-          double acc[2][4][2];
-          stage1x<QC, FULL>(sZI, sZJ, v, v + QC, v + QC + 64, qk, wr, wc, lane, nj, acc);
-          if (tid < VB) sV[((n + 1) % 3) * VB + tid] = nxt;
+      for (int64_t n = r0; n < r1; ++n) {
+        const double* v = sV + (n % 3) * VB;
+        double nxt = vec_load(n + 1);             // row n+1 vectors, stored after stage 1
+        double acc[2][4][2];
+        stage1<QC>(sZI, sZJ, v, qk, wr, wc, lane, acc);
+        if (tid < VB) sV[((n + 1) % 3) * VB + tid] = nxt;
 #pragma unroll
-          for (int i = 0; i < 2; ++i)
+        for (int i = 0; i < 2; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (FULL || j < nj) {
-                pacc[i][j][0] += exp_tab(acc[i][j][0], sT);
-                pacc[i][j][1] += exp_tab(acc[i][j][1], sT);
-              }
-          __syncthreads();                          // slot (n+1)%3 visible
-        }
-      };
-      if (tJ == 8) rows(std::true_type{});
-      else rows(std::false_type{});
+          for (int j = 0; j < 4; ++j) {
+            pacc[i][j][0] += exp_tab(acc[i][j][0], sT);
+            pacc[i][j][1] += exp_tab(acc[i][j][1], sT);
+          }
+        __syncthreads();                          // slot (n+1)%3 visible
+      }
 #pragma unroll
       for (int i = 0; i < 2; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          int m = 16 * wr + 8 * i + g, mp = 16 * j + 8 * wc + 2 * t;
+          int m = 16 * wr + 8 * i + g, mp = 32 * wc + 8 * j + 2 * t;
           *reinterpret_cast<double2*>(out + m * 64 + mp) = make_double2(pacc[i][j][0], pacc[i][j][1]);
         }
     } else {
       int ti[5], tj[5], cnt;
-      diag_tiles_x(wid, tJ, ti, tj, cnt);
-      if (tJ < 8) {                                            // tiles outside the valid triangle
-        for (int i = tid; i < 4096; i += P2_THREADS) out[i] = 0.0;
-        __syncthreads();
-      }
+      diag_tiles(wid, ti, tj, cnt);
       double pacc[5][2];
 #pragma unroll
       for (int s = 0; s < 5; ++s) pacc[s][0] = pacc[s][1] = 0.0;
-      auto rows = [&](auto FULLT) {
-        constexpr bool FULL = decltype(FULLT)::value;
-        for (int64_t n = r0; n < r1; ++n) {
-          const double* v = sV + (n % 3) * VB;
-          double nxt = vec_load(n + 1);
-          double acc[5][2];
-          stage1x_diag<QC, FULL>(sZI, v, v + QC, qk, ti, tj, cnt, lane, acc);
-          if (tid < VB) sV[((n + 1) % 3) * VB + tid] = nxt;
+      for (int64_t n = r0; n < r1; ++n) {
+        const double* v = sV + (n % 3) * VB;
+        double nxt = vec_load(n + 1);
+        double acc[5][2];
+        stage1_diag<QC>(sZI, v, qk, ti, tj, cnt, lane, acc);
+        if (tid < VB) sV[((n + 1) % 3) * VB + tid] = nxt;
 #pragma unroll
-          for (int s = 0; s < 5; ++s)
-            if (s < cnt) {
-              pacc[s][0] += exp_tab(acc[s][0], sT);
-              pacc[s][1] += exp_tab(acc[s][1], sT);
-            }
-          __syncthreads();
-        }
-      };
-      if (tJ == 8) rows(std::true_type{});
-      else rows(std::false_type{});
+        for (int s = 0; s < 5; ++s)
+          if (s < cnt) {
+            pacc[s][0] += exp_tab(acc[s][0], sT);
+            pacc[s][1] += exp_tab(acc[s][1], sT);
+          }
+        __syncthreads();
+      }
 #pragma unroll
       for (int s = 0; s < 5; ++s)
         if (s < cnt) {

@@ -241,7 +241,11 @@ int rgp_psi_set_option(rgp_psi_handle_t h, const char* key, int64_t value) {
   } else if (!strcmp(key, "profile")) {
     h->profile = value != 0;
   } else if (!strcmp(key, "bwd_pipe")) {
-    if (value < 0 || value > 3) return set_error(RGP_PSI_ERR_INVALID, "bwd_pipe must be 0, 1, 2 or 3");
+#ifdef RGP_DEBUG
+    if (value < 0 || value > 3) return set_error(RGP_PSI_ERR_INVALID, "bwd_pipe must be 0 ... 3");
+#else
+    if (value < 0 || value > 2) return set_error(RGP_PSI_ERR_INVALID, "bwd_pipe must be 0, 1 or 2");
+#endif
     h->bwd_pipe = (int)value;
 #ifdef RGP_DEBUG
   // experiment knobs: they make kernels skip work (wrong results) or change occupancy, so the

@@ -1,4 +1,5 @@
-"""A/B timing of the Psi2 kernels on one GPU (CUDA events per launch through the handle's profile mode).
+"""A/B timing of the Psi2 kernels on one GPU ("roles" = the warp-specialised experimental kernel: needs
+RGP_PSI_LIB=rgp_b200/_lib/librgp_psi_debug.so) (CUDA events per launch through the handle's profile mode).
     python scripts/bwd_ab.py [rows] [M] [Q]
 Prints one JSON line per variant: ms per launch and the fraction of the in-run DFMA peak."""
 import json, os, sys
