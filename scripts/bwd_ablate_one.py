@@ -12,7 +12,9 @@ Z = torch.randn((M, Q), generator=g, **f64); ell = (torch.rand(Q, generator=g, *
 dL1 = torch.randn((rows, M), generator=g, **f64) / M
 dL2 = torch.randn((M, M), generator=g, **f64) / (M * M); dL2 = 0.5 * (dL2 + dL2.T)
 dp = DevicePsi(0)
-dp.handle.set_option("bwd_pipe", 0); dp.handle.set_option("debug_skip", mask)
+dp.handle.set_option("bwd_pipe", 0)
+if mask:
+    dp.handle.set_option("debug_skip", mask)
 for _ in range(3):
     dp.backward(mu, S, Z, ell, 1.3, -0.5, dL1, dL2)
 torch.cuda.synchronize()
