@@ -91,6 +91,19 @@ def build(force: bool = False, verbose: bool = False) -> str:
 DEBUG_LIB = os.path.join(LIBDIR, "librgp_psi_debug.so")
 
 
+PAD8_LIB = os.path.join(LIBDIR, "librgp_psi_pad8.so")
+
+
+def build_variant(path: str, defines) -> str:
+    """A/B build of the product sources with extra -D defines (loaded through RGP_PSI_LIB)."""
+    os.makedirs(LIBDIR, exist_ok=True)
+    cmd = [_nvcc(), *NVCC_FLAGS, *["-D" + d for d in defines], "-shared", "-o", path, os.path.join(CSRC, "rgp_psi.cu")]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    return path
+
+
 def build_debug() -> str:
     """Experiment build (-DRGP_DEBUG): the ablation / occupancy knobs of the timing probes exist only
     here (scripts/bwd_ablate.py loads it through RGP_PSI_LIB); the product library does not have them."""

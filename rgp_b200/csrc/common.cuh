@@ -7,6 +7,16 @@ namespace rgp {
 
 #define RGP_DEVINL __device__ __forceinline__
 
+// Pad (doubles) of the shared-memory operand tiles: row stride = width + pad.
+//   4: stride == 4 (mod 16): every 8-byte fragment load hits each bank exactly twice (the minimum for 256 B).
+//   8: stride == 8 (mod 16): that still holds, and a 16-byte load of two consecutive k columns is conflict free
+//      per quarter warp, so stage 1 fetches the fragments of TWO k-steps with one LDS.128 (thread t holds
+//      k = k0 + 2t and k0 + 2t + 1; the first MMA contracts over the even columns of the 8-wide step, the second
+//      over the odd ones - A and B use the same assignment, so the sum over k is unchanged).
+#ifndef RGP_TILE_PAD
+#define RGP_TILE_PAD 4
+#endif
+
 // ---------------------------------------------------------------------------------
 // exp(x) for the psi exponents (logs of quantities <= 1, so x <= ~0; positive x up to
 // ~700 also works).  Range reduction x = k ln2 + r, |r| <= ln2/2 with a single FMA

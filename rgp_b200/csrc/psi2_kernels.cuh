@@ -33,11 +33,11 @@ namespace rgp {
 namespace fast {
 
 constexpr int P2_THREADS = 256;
-constexpr int RSL = 68;
+constexpr int RSL = 64 + RGP_TILE_PAD;
 
 template <int QC>
 struct P2Cfg {
-  static constexpr int RS = QC + 4;
+  static constexpr int RS = QC + RGP_TILE_PAD;
   // stage-2 output width per pass: Q in (64, 128] runs the backward kernel twice, once per 64-wide
   // q half (stage 1 + exp are recomputed; registers cannot hold 128-wide dZ accumulators)
   static constexpr int QS = QC > 64 ? 64 : QC;
@@ -98,6 +98,29 @@ RGP_DEVINL void stage1(const double* __restrict__ sZI, const double* __restrict_
       acc[i][j][1] = hi + hj.y;
     }
   }
+#if RGP_TILE_PAD == 8
+#pragma unroll 2
+  for (int k0 = 0; k0 < qk; k0 += 8) {          // two k-steps per trip, fragments by LDS.128 (see common.cuh)
+    const double2 wv = *reinterpret_cast<const double2*>(sw + k0 + 2 * t);
+    double2 a[2], b[4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      a[i] = *reinterpret_cast<const double2*>(pa + i * 8 * RS + k0 + t);   // pa already points at column t: + t more = 2 t
+      a[i].x *= wv.x;
+      a[i].y *= wv.y;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = *reinterpret_cast<const double2*>(pb + j * 8 * RS + k0 + t);
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i].x, b[j].x);
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i].y, b[j].y);
+  }
+#else
 #pragma unroll 2
   for (int k0 = 0; k0 < qk; k0 += 4) {
     const double wv = sw[k0 + t];
@@ -111,6 +134,7 @@ RGP_DEVINL void stage1(const double* __restrict__ sZI, const double* __restrict_
 #pragma unroll
       for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
   }
+#endif
 }
 
 // Diagonal blocks (I == J) are symmetric: only the 36 upper-triangle 8x8 tiles of the 8x8
@@ -144,6 +168,24 @@ RGP_DEVINL void stage1_diag_n(const double* __restrict__ sZ, const double* __res
     acc[s][0] = hi + hj.x;
     acc[s][1] = hi + hj.y;
   }
+#if RGP_TILE_PAD == 8
+#pragma unroll 2
+  for (int k0 = 0; k0 < qk; k0 += 8) {
+    const double2 wv = *reinterpret_cast<const double2*>(v + k0 + 2 * t);
+    double2 a[CNT], b[CNT];
+#pragma unroll
+    for (int s = 0; s < CNT; ++s) {
+      a[s] = *reinterpret_cast<const double2*>(pa[s] + k0 + t);
+      a[s].x *= wv.x;
+      a[s].y *= wv.y;
+      b[s] = *reinterpret_cast<const double2*>(pb[s] + k0 + t);
+    }
+#pragma unroll
+    for (int s = 0; s < CNT; ++s) dmma(acc[s][0], acc[s][1], a[s].x, b[s].x);
+#pragma unroll
+    for (int s = 0; s < CNT; ++s) dmma(acc[s][0], acc[s][1], a[s].y, b[s].y);
+  }
+#else
 #pragma unroll 2
   for (int k0 = 0; k0 < qk; k0 += 4) {
     const double wv = v[k0 + t];
@@ -156,6 +198,7 @@ RGP_DEVINL void stage1_diag_n(const double* __restrict__ sZ, const double* __res
 #pragma unroll
     for (int s = 0; s < CNT; ++s) dmma(acc[s][0], acc[s][1], a[s], b[s]);
   }
+#endif
 }
 
 // the tile count is warp-uniform; branching outside the k loop keeps it a straight-line,
