@@ -14,7 +14,7 @@ namespace rgp {
 //      k = k0 + 2t and k0 + 2t + 1; the first MMA contracts over the even columns of the 8-wide step, the second
 //      over the odd ones - A and B use the same assignment, so the sum over k is unchanged).
 #ifndef RGP_TILE_PAD
-#define RGP_TILE_PAD 4
+#define RGP_TILE_PAD 8     // measured: forward kernel +2.3 %, backward +1.4 % at M = 512, Q = 64; -1 % on the fused pass
 #endif
 
 // ---------------------------------------------------------------------------------

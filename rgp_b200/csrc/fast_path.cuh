@@ -71,7 +71,7 @@ static Shape make_shape(const rgp_psi_ctx* h, int64_t N, int M, int Q) {
   s.nblocks = s.nt * (s.nt + 1) / 2;
   s.Q = Q;
   s.QC = qc_for(Q);
-  s.qk = (int)round_up(Q, RGP_TILE_PAD == 8 ? 8 : 4);   // stage-1 K extent (8: two k-steps per LDS.128)
+  s.qk = (int)round_up(Q, 4);
   s.RS = s.QC + RGP_TILE_PAD;
   int64_t rc = h->row_chunk > 0 ? h->row_chunk : ((int64_t)1 << 20);
   s.rc = std::min<int64_t>(N, rc);

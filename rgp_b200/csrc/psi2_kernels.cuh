@@ -33,7 +33,7 @@ namespace rgp {
 namespace fast {
 
 constexpr int P2_THREADS = 256;
-constexpr int RSL = 64 + RGP_TILE_PAD;
+constexpr int RSL = 68;     // L tiles: stride == 4 (mod 16) for their 8-byte fragment loads, whatever the Z' tiles use
 
 template <int QC>
 struct P2Cfg {
@@ -99,8 +99,9 @@ RGP_DEVINL void stage1(const double* __restrict__ sZI, const double* __restrict_
     }
   }
 #if RGP_TILE_PAD == 8
+  const int qk8 = qk & ~7;
 #pragma unroll 2
-  for (int k0 = 0; k0 < qk; k0 += 8) {          // two k-steps per trip, fragments by LDS.128 (see common.cuh)
+  for (int k0 = 0; k0 < qk8; k0 += 8) {         // two k-steps per trip, fragments by LDS.128 (see common.cuh)
     const double2 wv = *reinterpret_cast<const double2*>(sw + k0 + 2 * t);
     double2 a[2], b[4];
 #pragma unroll
@@ -119,6 +120,19 @@ RGP_DEVINL void stage1(const double* __restrict__ sZI, const double* __restrict_
     for (int i = 0; i < 2; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i].y, b[j].y);
+  }
+  if (qk & 4) {                                 // odd number of k-steps: one ordinary step at the end
+    const int k0 = qk8;
+    const double wv = sw[k0 + t];
+    double a[2], b[4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) a[i] = pa[i * 8 * RS + k0] * wv;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = pb[j * 8 * RS + k0];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
   }
 #else
 #pragma unroll 2
@@ -169,8 +183,9 @@ RGP_DEVINL void stage1_diag_n(const double* __restrict__ sZ, const double* __res
     acc[s][1] = hi + hj.y;
   }
 #if RGP_TILE_PAD == 8
+  const int qk8 = qk & ~7;
 #pragma unroll 2
-  for (int k0 = 0; k0 < qk; k0 += 8) {
+  for (int k0 = 0; k0 < qk8; k0 += 8) {
     const double2 wv = *reinterpret_cast<const double2*>(v + k0 + 2 * t);
     double2 a[CNT], b[CNT];
 #pragma unroll
@@ -184,6 +199,18 @@ RGP_DEVINL void stage1_diag_n(const double* __restrict__ sZ, const double* __res
     for (int s = 0; s < CNT; ++s) dmma(acc[s][0], acc[s][1], a[s].x, b[s].x);
 #pragma unroll
     for (int s = 0; s < CNT; ++s) dmma(acc[s][0], acc[s][1], a[s].y, b[s].y);
+  }
+  if (qk & 4) {
+    const int k0 = qk8;
+    const double wv = v[k0 + t];
+    double a[CNT], b[CNT];
+#pragma unroll
+    for (int s = 0; s < CNT; ++s) {
+      a[s] = pa[s][k0] * wv;
+      b[s] = pb[s][k0];
+    }
+#pragma unroll
+    for (int s = 0; s < CNT; ++s) dmma(acc[s][0], acc[s][1], a[s], b[s]);
   }
 #else
 #pragma unroll 2
