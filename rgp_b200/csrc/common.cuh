@@ -7,15 +7,16 @@ namespace rgp {
 
 #define RGP_DEVINL __device__ __forceinline__
 
-// Pad (doubles) of the shared-memory operand tiles: row stride = width + pad.
+// Pad (doubles) of the shared-memory Z' tiles: row stride = QC + pad.
 //   4: stride == 4 (mod 16): every 8-byte fragment load hits each bank exactly twice (the minimum for 256 B).
-//   8: stride == 8 (mod 16): that still holds, and a 16-byte load of two consecutive k columns is conflict free
-//      per quarter warp, so stage 1 fetches the fragments of TWO k-steps with one LDS.128 (thread t holds
-//      k = k0 + 2t and k0 + 2t + 1; the first MMA contracts over the even columns of the 8-wide step, the second
-//      over the odd ones - A and B use the same assignment, so the sum over k is unchanged).
-#ifndef RGP_TILE_PAD
-#define RGP_TILE_PAD 8     // measured: forward kernel +2.3 %, backward +1.4 % at M = 512, Q = 64; -1 % on the fused pass
-#endif
+//   8: stride == 8 (mod 16): the stage-2 access patterns keep that property, and a 16-byte load of two
+//      consecutive k columns is conflict free per quarter warp, so stage 1 fetches the fragments of TWO k-steps
+//      with one LDS.128 (thread t holds k = k0 + 2t and k0 + 2t + 1; the first MMA contracts over the even columns
+//      of the 8-wide step, the second over the odd ones - A and B use the same assignment, so the sum over k is
+//      unchanged; an odd number of k-steps ends with one ordinary step).
+// Measured (profiles/SUMMARY_r02.md): pad 8 gives the forward kernel +2.3 % and the backward kernel +1.4 % at
+// M = 512, Q = 64 and +1.7 % at (1024, 128); at QC <= 32 (few k-steps per row) it costs 1-2 %, so those keep pad 4.
+__host__ __device__ constexpr int tile_pad(int QC) { return QC >= 64 ? 8 : 4; }
 
 // ---------------------------------------------------------------------------------
 // exp(x) for the psi exponents (logs of quantities <= 1, so x <= ~0; positive x up to

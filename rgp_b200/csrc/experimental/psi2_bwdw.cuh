@@ -33,7 +33,7 @@ constexpr int PW_DMMA = 256;
 
 template <int QC, int NJ_>
 struct P2CfgW {
-  static constexpr int RS = QC + RGP_TILE_PAD;
+  static constexpr int RS = QC + tile_pad(QC);
   static constexpr int NJ = NJ_;
   static constexpr int QS = 16 * NJ_;
   static constexpr int VR = 8;

@@ -72,7 +72,7 @@ static Shape make_shape(const rgp_psi_ctx* h, int64_t N, int M, int Q) {
   s.Q = Q;
   s.QC = qc_for(Q);
   s.qk = (int)round_up(Q, 4);
-  s.RS = s.QC + RGP_TILE_PAD;
+  s.RS = s.QC + tile_pad(s.QC);
   int64_t rc = h->row_chunk > 0 ? h->row_chunk : ((int64_t)1 << 20);
   s.rc = std::min<int64_t>(N, rc);
   return s;

@@ -37,7 +37,7 @@ __global__ void k_center(int M, int Q, const double* __restrict__ Z, double* __r
 __global__ void k_build_Z(int M, int Mp, int Q, int QC, const double* __restrict__ Z,
                           const double* __restrict__ o, double* __restrict__ Zt,
                           double* __restrict__ ZB) {
-  const int RS = QC + RGP_TILE_PAD;
+  const int RS = QC + tile_pad(QC);
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= Mp * RS) return;
   int m = idx / RS, c = idx - m * RS;

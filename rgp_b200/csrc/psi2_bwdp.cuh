@@ -37,11 +37,11 @@ namespace fast {
 // (measured 17 % faster at M = 200, Q = 40, profiles/kernel_times_small_r02.jsonl).
 template <int QC, int NJ_>
 struct P2CfgP {
-  static constexpr int RS = QC + RGP_TILE_PAD;
+  static constexpr int RS = QC + tile_pad(QC);
   static constexpr int NJ = NJ_;
   static constexpr int QS = 16 * NJ_;
   static_assert(QS <= (QC > 64 ? 64 : QC), "stage-2 width exceeds the tile");
-  static constexpr int VR = QC > 64 ? (RGP_TILE_PAD > 4 ? 1 : 2) : 8;   // rows per TMA batch (QC = 128: shared memory is full)
+  static constexpr int VR = QC > 64 ? 1 : 8;   // rows per TMA batch (QC = 128: shared memory is full)
   static constexpr int VBB = VR * (QC + 128);                // doubles per batch slot: ws | H_I | H_J
   static constexpr int SMEM_D = 2 * 64 * RS + 2 * 64 * RSL + 2 * VBB + 2 * 4 * QS + 2 * 2 * 64 + 2 * 4 * 64 + 256 + 2;
   static constexpr int SMEM = SMEM_D * 8;
@@ -96,7 +96,7 @@ RGP_DEVINL void stage1v(const double* __restrict__ sZI, const double* __restrict
       acc[i][j][1] = hi + hj.y;
     }
   }
-#if RGP_TILE_PAD == 8
+  if constexpr (tile_pad(QC) == 8) {
   const int qk8 = qk & ~7;
 #pragma unroll 2
   for (int k0 = 0; k0 < qk8; k0 += 8) {         // two k-steps per trip, fragments by LDS.128 (see common.cuh)
@@ -132,7 +132,7 @@ RGP_DEVINL void stage1v(const double* __restrict__ sZI, const double* __restrict
 #pragma unroll
       for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
   }
-#else
+  } else {
 #pragma unroll 2
   for (int k0 = 0; k0 < qk; k0 += 4) {
     const double wv = sw[k0 + t];
@@ -146,7 +146,7 @@ RGP_DEVINL void stage1v(const double* __restrict__ sZI, const double* __restrict
 #pragma unroll
       for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
   }
-#endif
+  }
 }
 
 template <int QC, int CNT>
@@ -166,7 +166,7 @@ RGP_DEVINL void stage1v_diag_n(const double* __restrict__ sZ, const double* __re
     acc[s][0] = hi + hj.x;
     acc[s][1] = hi + hj.y;
   }
-#if RGP_TILE_PAD == 8
+  if constexpr (tile_pad(QC) == 8) {
   const int qk8 = qk & ~7;
 #pragma unroll 2
   for (int k0 = 0; k0 < qk8; k0 += 8) {
@@ -196,7 +196,7 @@ RGP_DEVINL void stage1v_diag_n(const double* __restrict__ sZ, const double* __re
 #pragma unroll
     for (int s = 0; s < CNT; ++s) dmma(acc[s][0], acc[s][1], a[s], b[s]);
   }
-#else
+  } else {
 #pragma unroll 2
   for (int k0 = 0; k0 < qk; k0 += 4) {
     const double wv = sw[k0 + t];
@@ -209,7 +209,7 @@ RGP_DEVINL void stage1v_diag_n(const double* __restrict__ sZ, const double* __re
 #pragma unroll
     for (int s = 0; s < CNT; ++s) dmma(acc[s][0], acc[s][1], a[s], b[s]);
   }
-#endif
+  }
 }
 
 template <int QC>

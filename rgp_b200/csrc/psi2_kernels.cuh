@@ -37,7 +37,7 @@ constexpr int RSL = 68;     // L tiles: stride == 4 (mod 16) for their 8-byte fr
 
 template <int QC>
 struct P2Cfg {
-  static constexpr int RS = QC + RGP_TILE_PAD;
+  static constexpr int RS = QC + tile_pad(QC);
   // stage-2 output width per pass: Q in (64, 128] runs the backward kernel twice, once per 64-wide
   // q half (stage 1 + exp are recomputed; registers cannot hold 128-wide dZ accumulators)
   static constexpr int QS = QC > 64 ? 64 : QC;
@@ -98,7 +98,7 @@ RGP_DEVINL void stage1(const double* __restrict__ sZI, const double* __restrict_
       acc[i][j][1] = hi + hj.y;
     }
   }
-#if RGP_TILE_PAD == 8
+  if constexpr (tile_pad(QC) == 8) {
   const int qk8 = qk & ~7;
 #pragma unroll 2
   for (int k0 = 0; k0 < qk8; k0 += 8) {         // two k-steps per trip, fragments by LDS.128 (see common.cuh)
@@ -134,7 +134,7 @@ RGP_DEVINL void stage1(const double* __restrict__ sZI, const double* __restrict_
 #pragma unroll
       for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
   }
-#else
+  } else {
 #pragma unroll 2
   for (int k0 = 0; k0 < qk; k0 += 4) {
     const double wv = sw[k0 + t];
@@ -148,7 +148,7 @@ RGP_DEVINL void stage1(const double* __restrict__ sZI, const double* __restrict_
 #pragma unroll
       for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
   }
-#endif
+  }
 }
 
 // Diagonal blocks (I == J) are symmetric: only the 36 upper-triangle 8x8 tiles of the 8x8
@@ -182,7 +182,7 @@ RGP_DEVINL void stage1_diag_n(const double* __restrict__ sZ, const double* __res
     acc[s][0] = hi + hj.x;
     acc[s][1] = hi + hj.y;
   }
-#if RGP_TILE_PAD == 8
+  if constexpr (tile_pad(QC) == 8) {
   const int qk8 = qk & ~7;
 #pragma unroll 2
   for (int k0 = 0; k0 < qk8; k0 += 8) {
@@ -212,7 +212,7 @@ RGP_DEVINL void stage1_diag_n(const double* __restrict__ sZ, const double* __res
 #pragma unroll
     for (int s = 0; s < CNT; ++s) dmma(acc[s][0], acc[s][1], a[s], b[s]);
   }
-#else
+  } else {
 #pragma unroll 2
   for (int k0 = 0; k0 < qk; k0 += 4) {
     const double wv = v[k0 + t];
@@ -225,7 +225,7 @@ RGP_DEVINL void stage1_diag_n(const double* __restrict__ sZ, const double* __res
 #pragma unroll
     for (int s = 0; s < CNT; ++s) dmma(acc[s][0], acc[s][1], a[s], b[s]);
   }
-#endif
+  }
 }
 
 // the tile count is warp-uniform; branching outside the k loop keeps it a straight-line,
