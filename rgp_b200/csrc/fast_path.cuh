@@ -138,6 +138,14 @@ static int launch_bwdp(rgp_psi_ctx* h, cudaStream_t st, const Shape& s, int64_t 
   return 0;
 }
 
+// Which Psi2 backward kernel serves a pass (profiles/SUMMARY_r02.md section 2): the software-pipelined kernel
+// (psi2_bwdp.cuh; pad-4 Z' tiles) for the fused pass and for 32 < Q <= 48 (48 stage-2 columns instead of 64), the
+// row-at-a-time kernel (tile_pad(QC) Z' tiles) everywhere else.  bwd_pipe 0 / 1 force one of them (A/B, tests).
+static inline bool use_pipelined(const rgp_psi_ctx* h, int QC, int Q, bool fused) {
+  const bool narrow = QC == 64 && Q <= 48;
+  return h->bwd_pipe == 1 || (h->bwd_pipe == 2 && (fused || narrow));
+}
+
 template <int QC>
 static int launch_bwd(rgp_psi_ctx* h, cudaStream_t st, const Shape& s, int64_t rows, int R, int G,
                       const double* Zt, const double* Ct, const double* w, const double* HP,
@@ -161,8 +169,7 @@ static int launch_bwd(rgp_psi_ctx* h, cudaStream_t st, const Shape& s, int64_t r
     }
   }
 #endif
-  const bool narrow = QC == 64 && s.Q <= 48;      // stage-2 width 48 instead of 64: pipelined kernel 17 % faster (M=200, Q=40)
-  const bool pipe = h->bwd_pipe == 1 || (h->bwd_pipe == 2 && (fused || narrow));
+  const bool pipe = use_pipelined(h, QC, s.Q, fused);
   if constexpr (QC == 128) {
     if (fused) return set_error(RGP_PSI_ERR_INVALID, "fused pass is not built for Q > 64");
   }
@@ -217,7 +224,7 @@ static int static_prep(rgp_psi_ctx* h, cudaStream_t st, const Shape& s, const do
                        double* Zt, double* ZB) {
   RGP_LAUNCH(h, st, "center", k_center, s.Q, 128, 0, s.M, s.Q, Z, o);
   RGP_LAUNCH(h, st, "build_Z", k_build_Z, ceil_div((int64_t)s.Mp * s.RS, 256), 256, 0, s.M, s.Mp, s.Q,
-             s.QC, Z, o, Zt, ZB);
+             s.QC, s.RS, Z, o, Zt, ZB);
   return 0;
 }
 
@@ -288,7 +295,8 @@ static int backward(rgp_psi_ctx* h, cudaStream_t st, int64_t N, int M, int Q, co
                     double* psi1_out = nullptr, double* psi2_out = nullptr) {
   // psi1_out / psi2_out (optional): fused evaluation - the statistics come out of the same pass
   // (Psi1 from one more small GEMM, Psi2 from the backward kernel itself, see k_psi2_bwd FUSE)
-  const Shape s = make_shape(h, N, M, Q);
+  Shape s = make_shape(h, N, M, Q);
+  if (use_pipelined(h, s.QC, Q, psi2_out != nullptr)) s.RS = s.QC + 4;   // the Z' tile layout follows the kernel
   int R, G;
   pick_grid(s.rc, s.nblocks, h->sm_count, &R, &G);
   const int QC = s.QC, Mp = s.Mp;

@@ -34,10 +34,9 @@ __global__ void k_center(int M, int Q, const double* __restrict__ Z, double* __r
 
 // Zt[tile][64][RS]: centred, zero padded, ready for a straight copy into shared memory.
 // ZB[Mp][2QC] = [Z' | Z'^2].
-__global__ void k_build_Z(int M, int Mp, int Q, int QC, const double* __restrict__ Z,
+__global__ void k_build_Z(int M, int Mp, int Q, int QC, int RS, const double* __restrict__ Z,
                           const double* __restrict__ o, double* __restrict__ Zt,
                           double* __restrict__ ZB) {
-  const int RS = QC + tile_pad(QC);
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= Mp * RS) return;
   int m = idx / RS, c = idx - m * RS;

@@ -37,11 +37,11 @@ namespace fast {
 // (measured 17 % faster at M = 200, Q = 40, profiles/kernel_times_small_r02.jsonl).
 template <int QC, int NJ_>
 struct P2CfgP {
-  static constexpr int RS = QC + tile_pad(QC);
+  static constexpr int RS = QC + 4;     // this kernel keeps the pad-4 Z' tiles (the LDS.128 pairing measured 1-4 % slower here)
   static constexpr int NJ = NJ_;
   static constexpr int QS = 16 * NJ_;
   static_assert(QS <= (QC > 64 ? 64 : QC), "stage-2 width exceeds the tile");
-  static constexpr int VR = QC > 64 ? 1 : 8;   // rows per TMA batch (QC = 128: shared memory is full)
+  static constexpr int VR = QC > 64 ? 2 : 8;                 // rows per TMA batch
   static constexpr int VBB = VR * (QC + 128);                // doubles per batch slot: ws | H_I | H_J
   static constexpr int SMEM_D = 2 * 64 * RS + 2 * 64 * RSL + 2 * VBB + 2 * 4 * QS + 2 * 2 * 64 + 2 * 4 * 64 + 256 + 2;
   static constexpr int SMEM = SMEM_D * 8;
@@ -80,7 +80,7 @@ RGP_DEVINL void stage1v(const double* __restrict__ sZI, const double* __restrict
                         const double* __restrict__ sw, const double* __restrict__ hI,
                         const double* __restrict__ hJ, int qk, int wr, int wc, int lane,
                         double (&acc)[2][4][2]) {
-  constexpr int RS = P2Cfg<QC>::RS;
+  constexpr int RS = QC + 4;
   const int g = lane >> 2, t = lane & 3;
   const double* pa = sZI + (16 * wr + g) * RS + t;
   const double* pb = sZJ + (32 * wc + g) * RS + t;
@@ -96,43 +96,6 @@ RGP_DEVINL void stage1v(const double* __restrict__ sZI, const double* __restrict
       acc[i][j][1] = hi + hj.y;
     }
   }
-  if constexpr (tile_pad(QC) == 8) {
-  const int qk8 = qk & ~7;
-#pragma unroll 2
-  for (int k0 = 0; k0 < qk8; k0 += 8) {         // two k-steps per trip, fragments by LDS.128 (see common.cuh)
-    const double2 wv = *reinterpret_cast<const double2*>(sw + k0 + 2 * t);
-    double2 a[2], b[4];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      a[i] = *reinterpret_cast<const double2*>(pa + i * 8 * RS + k0 + t);   // pa already points at column t: + t more = 2 t
-      a[i].x *= wv.x;
-      a[i].y *= wv.y;
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) b[j] = *reinterpret_cast<const double2*>(pb + j * 8 * RS + k0 + t);
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i].x, b[j].x);
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i].y, b[j].y);
-  }
-  if (qk & 4) {                                 // odd number of k-steps: one ordinary step at the end
-    const int k0 = qk8;
-    const double wv = sw[k0 + t];
-    double a[2], b[4];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) a[i] = pa[i * 8 * RS + k0] * wv;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) b[j] = pb[j * 8 * RS + k0];
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-  }
-  } else {
 #pragma unroll 2
   for (int k0 = 0; k0 < qk; k0 += 4) {
     const double wv = sw[k0 + t];
@@ -146,14 +109,13 @@ RGP_DEVINL void stage1v(const double* __restrict__ sZI, const double* __restrict
 #pragma unroll
       for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
   }
-  }
 }
 
 template <int QC, int CNT>
 RGP_DEVINL void stage1v_diag_n(const double* __restrict__ sZ, const double* __restrict__ sw,
                                const double* __restrict__ hI, int qk, const int (&ti)[5], const int (&tj)[5],
                                int lane, double (&acc)[5][2]) {
-  constexpr int RS = P2Cfg<QC>::RS;
+  constexpr int RS = QC + 4;
   const int g = lane >> 2, t = lane & 3;
   const double* pa[CNT];
   const double* pb[CNT];
@@ -166,37 +128,6 @@ RGP_DEVINL void stage1v_diag_n(const double* __restrict__ sZ, const double* __re
     acc[s][0] = hi + hj.x;
     acc[s][1] = hi + hj.y;
   }
-  if constexpr (tile_pad(QC) == 8) {
-  const int qk8 = qk & ~7;
-#pragma unroll 2
-  for (int k0 = 0; k0 < qk8; k0 += 8) {
-    const double2 wv = *reinterpret_cast<const double2*>(sw + k0 + 2 * t);
-    double2 a[CNT], b[CNT];
-#pragma unroll
-    for (int s = 0; s < CNT; ++s) {
-      a[s] = *reinterpret_cast<const double2*>(pa[s] + k0 + t);
-      a[s].x *= wv.x;
-      a[s].y *= wv.y;
-      b[s] = *reinterpret_cast<const double2*>(pb[s] + k0 + t);
-    }
-#pragma unroll
-    for (int s = 0; s < CNT; ++s) dmma(acc[s][0], acc[s][1], a[s].x, b[s].x);
-#pragma unroll
-    for (int s = 0; s < CNT; ++s) dmma(acc[s][0], acc[s][1], a[s].y, b[s].y);
-  }
-  if (qk & 4) {
-    const int k0 = qk8;
-    const double wv = sw[k0 + t];
-    double a[CNT], b[CNT];
-#pragma unroll
-    for (int s = 0; s < CNT; ++s) {
-      a[s] = pa[s][k0] * wv;
-      b[s] = pb[s][k0];
-    }
-#pragma unroll
-    for (int s = 0; s < CNT; ++s) dmma(acc[s][0], acc[s][1], a[s], b[s]);
-  }
-  } else {
 #pragma unroll 2
   for (int k0 = 0; k0 < qk; k0 += 4) {
     const double wv = sw[k0 + t];
@@ -208,7 +139,6 @@ RGP_DEVINL void stage1v_diag_n(const double* __restrict__ sZ, const double* __re
     }
 #pragma unroll
     for (int s = 0; s < CNT; ++s) dmma(acc[s][0], acc[s][1], a[s], b[s]);
-  }
   }
 }
 
