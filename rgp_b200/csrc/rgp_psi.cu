@@ -1,6 +1,7 @@
 // rgp_psi.cu - C ABI of librgp_psi.so (see include/rgp_psi.h for the contract and the
 // reference interfaces each entry point replaces).
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <new>
@@ -344,6 +345,15 @@ static int host_pipeline_init(rgp_psi_ctx* h) {
   }
   return 0;
 }
+// Host threads this process may use for its copies / digests: the cores divided by the ranks sharing the node
+// (torchrun exports LOCAL_WORLD_SIZE), so eight ranks do not start 8 x 32 threads on 32 cores.
+static int host_parallelism() {
+  unsigned cores = std::max(1u, std::thread::hardware_concurrency());
+  const char* lw = getenv("LOCAL_WORLD_SIZE");
+  int ranks = lw ? atoi(lw) : 1;
+  if (ranks < 1) ranks = 1;
+  return (int)std::max(1u, cores / (unsigned)ranks);
+}
 static bool is_pinned(const void* p) {
   if (!p) return true;
   cudaPointerAttributes a;
@@ -379,7 +389,7 @@ static int pin_reserve(rgp_psi_ctx* h, size_t need) {
 // keep up with the GPU).  Small copies stay on the calling thread.
 static void par_memcpy(const rgp_psi_ctx* h, void* dst, const void* src, size_t bytes) {
   if (!bytes) return;
-  int nt = h->host_threads > 0 ? h->host_threads : (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+  int nt = h->host_threads > 0 ? h->host_threads : std::min(8, std::max(1, host_parallelism() / 2));
   if (bytes < (size_t)8 << 20 || nt <= 1) {
     memcpy(dst, src, bytes);
     return;
@@ -757,7 +767,7 @@ int rgp_host_digest(const void* data, int64_t nbytes, int threads, uint64_t out[
   const size_t SL = (size_t)8 << 20;
   const size_t n = (size_t)nbytes, nsl = n ? (n + SL - 1) / SL : 1;
   std::vector<uint64_t> part(2 * nsl);
-  int nt = threads > 0 ? threads : (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
+  int nt = threads > 0 ? threads : std::min(32, rgp::host_parallelism());
   nt = (int)std::min<size_t>(nt, nsl);
   auto work = [&](int tix) {
     for (size_t sl = tix; sl < nsl; sl += nt) {
