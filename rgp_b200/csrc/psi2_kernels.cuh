@@ -43,9 +43,10 @@ struct P2Cfg {
   static constexpr int QS = QC > 64 ? 64 : QC;
   static constexpr int NJ = QS / 16;        // 8-wide q tiles per warp in stage 2
   static constexpr int VB = QC + 128;       // per-row vector slot: w[QC] | H_I[64] | H_J[64]
-  static constexpr int FWD_SMEM = (2 * 64 * RS + 3 * VB + 256) * 8;
+  static constexpr int VR = QC > 64 ? 1 : 8; // rows per TMA batch (QC = 128: shared memory is full)
+  static constexpr int FWD_SMEM = (2 * 64 * RS + 2 * VR * VB + 256 + 2) * 8;
   static constexpr int BWD_SMEM =
-      (2 * 64 * RS + 2 * 64 * RSL + 3 * VB + 2 * 4 * QS + 2 * 2 * 64 + 2 * 4 * 64 + 256) * 8;
+      (2 * 64 * RS + 2 * 64 * RSL + 2 * VR * VB + 2 * 4 * QS + 2 * 2 * 64 + 2 * 4 * 64 + 256 + 2) * 8;
   // fused variant (also accumulates the Psi2 tile of the block in shared memory): + [64][RSL]
   static constexpr int BWD_FUSED_SMEM = BWD_SMEM + 64 * RSL * 8;
 };
@@ -59,6 +60,95 @@ RGP_DEVINL void dmma(double& d0, double& d1, double a, double b) {
 RGP_DEVINL void red_add(double* addr, double v) {
   asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
 }
+
+// ---- mbarrier / bulk-copy wrappers (PTX ISA: mbarrier, cp.async.bulk) -----------------------------
+RGP_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+RGP_DEVINL void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+RGP_DEVINL void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+RGP_DEVINL void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+RGP_DEVINL void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+RGP_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
+
+// ---- TMA staging of the per-row vectors -------------------------------------------------------------
+// The vectors a row needs - ws[QC], H_I[64], H_J[64] - are three contiguous runs in HBM.  One elected thread
+// fetches them for VR consecutive rows with cp.async.bulk (UBLKCP in SASS) into a slot of a two-slot ring; an
+// mbarrier per slot carries the byte count, every thread waits on it once per batch.  Row w of a batch sits at
+// slot + w * VB in the layout the compute code reads ([ws | H_I | H_J]), so no compute thread issues a global
+// load for operands inside the row loop.
+template <int QC, int VR>
+struct RowVecStage {
+  static constexpr int VB = QC + 128;
+  double* ring;              // 2 slots of VR * VB doubles
+  uint64_t* mbar;            // 2 mbarriers
+  uint32_t phase_bits = 0;   // per thread: parity of the next completion of each slot
+  int64_t r0 = 0, r1 = 0;
+  const double* wrow = nullptr;
+  const double* hI = nullptr;
+  const double* hJ = nullptr;
+  int64_t next = 0;          // batches issued so far (meaningful on the issuing thread)
+  int64_t nb = 0;
+
+  RGP_DEVINL void init_barriers(int tid) {
+    if (tid == 0) {
+      mbar_init(&mbar[0], 1);
+      mbar_init(&mbar[1], 1);
+      mbar_fence_init();
+    }
+  }
+  // start a block: (called by all threads after the CTA barrier that ends the previous block)
+  RGP_DEVINL void begin(int64_t r0_, int64_t r1_, const double* w, const double* hi, const double* hj, int tid) {
+    r0 = r0_; r1 = r1_; wrow = w; hI = hi; hJ = hj;
+    nb = r1 > r0 ? (r1 - r0 + VR - 1) / VR : 0;
+    next = 0;
+    if (tid == 0 && nb > 0) issue();
+  }
+  RGP_DEVINL void issue() {                      // issuing thread only: batch `next` -> slot next & 1
+    const int64_t n0 = r0 + next * VR;
+    const int rows = (int)((r1 - n0 < VR) ? r1 - n0 : VR);
+    const int slot = (int)(next & 1);
+    double* dst = ring + slot * VR * VB;
+    mbar_expect_tx(&mbar[slot], (uint32_t)(rows * VB * 8));
+    for (int w = 0; w < rows; ++w) {
+      bulk_g2s(dst + w * VB, wrow + (n0 + w) * QC, QC * 8, &mbar[slot]);
+      bulk_g2s(dst + w * VB + QC, hI + (n0 + w) * 64, 512, &mbar[slot]);
+      bulk_g2s(dst + w * VB + QC + 64, hJ + (n0 + w) * 64, 512, &mbar[slot]);
+    }
+    ++next;
+  }
+  // issuing thread, at a point where every thread has finished all rows < r0 + idx: refill free slots.
+  // Batch j may overwrite the slot of batch j - 2 once all rows of batch j - 2 are done: (j - 1) VR <= idx.
+  RGP_DEVINL void refill(int64_t idx) {
+    while (next < nb && next <= idx / VR + 1 && (next - 1) * VR <= idx) issue();
+  }
+  // all threads, before the first use of row r0 + idx; returns the row's [ws | H_I | H_J]
+  RGP_DEVINL const double* row(int64_t idx) {
+    const int slot = (int)((idx / VR) & 1);
+    if (idx % VR == 0) {
+      mbar_wait(&mbar[slot], (phase_bits >> slot) & 1u);
+      phase_bits ^= 1u << slot;
+    }
+    return ring + slot * VR * VB + (idx % VR) * VB;
+  }
+};
 
 RGP_DEVINL void block_ij(int b, int nt, int& I, int& J) {
   int i = 0, rem = b;
@@ -248,12 +338,15 @@ k_psi2_fwd(int64_t rc, int nt, int nblocks, int qk, const double* __restrict__ Z
            const double* __restrict__ wrow, const double* __restrict__ HP,
            double* __restrict__ P2p) {
   using C = P2Cfg<QC>;
-  constexpr int RS = C::RS, VB = C::VB;
+  constexpr int RS = C::RS, VB = C::VB, VR = C::VR;
   extern __shared__ __align__(16) double smem[];
   double* sZI = smem;
   double* sZJ = sZI + 64 * RS;
-  double* sV = sZJ + 64 * RS;                     // 3 slots of VB
-  double* sT = sV + 3 * VB;                       // exp table, 256 entries
+  double* sV = sZJ + 64 * RS;                     // row-vector ring: 2 slots of VR rows (TMA, see RowVecStage)
+  double* sT = sV + 2 * VR * VB;                  // exp table, 256 entries
+  RowVecStage<QC, VR> rv;
+  rv.ring = sV;
+  rv.mbar = reinterpret_cast<uint64_t*>(sT + 256);
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int wr = wid >> 1, wc = wid & 1, g = lane >> 2, t = lane & 3;
@@ -261,6 +354,7 @@ k_psi2_fwd(int64_t rc, int nt, int nblocks, int qk, const double* __restrict__ Z
   const int64_t per = (rc + R - 1) / R;
   const int64_t r0 = per * blockIdx.x, r1 = (r0 + per < rc) ? r0 + per : rc;
   exp_table_init(sT, tid);
+  rv.init_barriers(tid);
 
   int curI = -1, curJ = -1;
   for (int b = blockIdx.y; b < nblocks; b += G) {
@@ -274,13 +368,7 @@ k_psi2_fwd(int64_t rc, int nt, int nblocks, int qk, const double* __restrict__ Z
     curJ = J;
     const double* hI = HP + (size_t)I * rc * 64;
     const double* hJ = HP + (size_t)J * rc * 64;
-    auto vec_load = [&](int64_t n) -> double {
-      if (tid >= VB || n >= r1) return 0.0;
-      if (tid < QC) return wrow[n * QC + tid];
-      if (tid < QC + 64) return hI[n * 64 + (tid - QC)];
-      return hJ[n * 64 + (tid - QC - 64)];
-    };
-    if (r0 < r1 && tid < VB) sV[(r0 % 3) * VB + tid] = vec_load(r0);
+    rv.begin(r0, r1, wrow, hI, hJ, tid);
     __syncthreads();
     double* out = P2p + ((size_t)b * R + blockIdx.x) * 4096;
 
@@ -291,11 +379,10 @@ k_psi2_fwd(int64_t rc, int nt, int nblocks, int qk, const double* __restrict__ Z
 #pragma unroll
         for (int j = 0; j < 4; ++j) pacc[i][j][0] = pacc[i][j][1] = 0.0;
       for (int64_t n = r0; n < r1; ++n) {
-        const double* v = sV + (n % 3) * VB;
-        double nxt = vec_load(n + 1);             // row n+1 vectors, stored after stage 1
+        if (tid == 0) rv.refill(n - r0);          // every thread is past the barrier of row n-1
+        const double* v = rv.row(n - r0);
         double acc[2][4][2];
         stage1<QC>(sZI, sZJ, v, qk, wr, wc, lane, acc);
-        if (tid < VB) sV[((n + 1) % 3) * VB + tid] = nxt;
 #pragma unroll
         for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -303,7 +390,7 @@ k_psi2_fwd(int64_t rc, int nt, int nblocks, int qk, const double* __restrict__ Z
             pacc[i][j][0] += exp_tab(acc[i][j][0], sT);
             pacc[i][j][1] += exp_tab(acc[i][j][1], sT);
           }
-        __syncthreads();                          // slot (n+1)%3 visible
+        __syncthreads();                          // all reads of row n's vectors done
       }
 #pragma unroll
       for (int i = 0; i < 2; ++i)
@@ -319,11 +406,10 @@ k_psi2_fwd(int64_t rc, int nt, int nblocks, int qk, const double* __restrict__ Z
 #pragma unroll
       for (int s = 0; s < 5; ++s) pacc[s][0] = pacc[s][1] = 0.0;
       for (int64_t n = r0; n < r1; ++n) {
-        const double* v = sV + (n % 3) * VB;
-        double nxt = vec_load(n + 1);
+        if (tid == 0) rv.refill(n - r0);
+        const double* v = rv.row(n - r0);
         double acc[5][2];
         stage1_diag<QC>(sZI, v, qk, ti, tj, cnt, lane, acc);
-        if (tid < VB) sV[((n + 1) % 3) * VB + tid] = nxt;
 #pragma unroll
         for (int s = 0; s < 5; ++s)
           if (s < cnt) {
@@ -378,12 +464,15 @@ k_psi2_bwd(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __rest
   double* sZI = smem;
   double* sZJ = sZI + 64 * RS;
   double* sL = sZJ + 64 * RS;                     // 2 slots of 64*RSL
-  double* sV = sL + 2 * 64 * RSL;                 // 3 slots of VB
-  double* sWq = sV + 3 * VB;                      // [2][4][QS]
+  double* sV = sL + 2 * 64 * RSL;                 // row-vector ring: 2 slots of VR rows (TMA, see RowVecStage)
+  double* sWq = sV + 2 * C::VR * VB;              // [2][4][QS]
   double* sLr = sWq + 2 * 4 * QS;                 // [2][2][64]  row-sum partials (per wc)
   double* sLc = sLr + 2 * 2 * 64;                 // [2][4][64]  col-sum partials (per wr)
   double* sT = sLc + 2 * 4 * 64;                  // exp table, 256 entries
-  double* sP = sT + 256;                          // FUSE: Psi2 tile of the block [64][RSL]
+  double* sP = sT + 256 + 2;                      // FUSE: Psi2 tile of the block [64][RSL]
+  RowVecStage<QC, C::VR> rv;
+  rv.ring = sV;
+  rv.mbar = reinterpret_cast<uint64_t*>(sT + 256);
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int wr = wid >> 1, wc = wid & 1, g = lane >> 2, t = lane & 3;
@@ -396,6 +485,7 @@ k_psi2_bwd(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __rest
   double* accp = ACCp + (size_t)cta * Mp * QC;
   const int qbase = wc * (QS / 2);                // this warp's q columns in stage 2 (relative to qoff)
   exp_table_init(sT, tid);
+  rv.init_barriers(tid);
 
   int curI = -1, curJ = -1;
   for (int b = blockIdx.y; b < nblocks; b += G) {
@@ -410,13 +500,7 @@ k_psi2_bwd(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __rest
     const double* hI = HP + (size_t)I * rc * 64;
     const double* hJ = HP + (size_t)J * rc * 64;
     const double* cb = Ct + (size_t)b * 4096;     // C = s2^2 sym(dL_dpsi2) on this block
-    auto vec_load = [&](int64_t n) -> double {
-      if (tid >= VB || n >= r1) return 0.0;
-      if (tid < QC) return wrow[n * QC + tid];
-      if (tid < QC + 64) return hI[n * 64 + (tid - QC)];
-      return hJ[n * 64 + (tid - QC - 64)];
-    };
-    if (r0 < r1 && tid < VB) sV[(r0 % 3) * VB + tid] = vec_load(r0);
+    rv.begin(r0, r1, wrow, hI, hJ, tid);
     if constexpr (FUSE)
       for (int i = tid; i < 64 * RSL; i += P2_THREADS) sP[i] = 0.0;
     double accI[2][NJ][2], accJ[2][NJ][2];
@@ -514,9 +598,8 @@ k_psi2_bwd(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __rest
         }
       for (int64_t n = r0; n < r1; ++n) {
         const int s = (int)(n & 1);
-        const double* v = sV + (n % 3) * VB;
+        const double* v = rv.row(n - r0);
         double* Lb = sL + s * 64 * RSL;
-        double nxt = vec_load(n + 1);
         {
           double acc[2][4][2];
           if constexpr (DBG & 128) {
@@ -525,7 +608,6 @@ k_psi2_bwd(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __rest
 #pragma unroll
               for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = v[i + j];
           } else stage1<QC>(sZI, sZJ, v, qk, wr, wc, lane, acc);
-          if (tid < VB) sV[((n + 1) % 3) * VB + tid] = nxt;
           if constexpr (DBG & 8) {                 // no epilogue: fold the exponents into one register so stage 1 stays
             double sink = 0.0;
 #pragma unroll
@@ -582,6 +664,7 @@ k_psi2_bwd(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __rest
           }
         }
         if constexpr (!(DBG & 16)) __syncthreads();   // L tile + lambda partials of row n complete; row n-1 fully finished
+        if (tid == 0) rv.refill(n - r0);              // ... so the slot of a batch that ended before row n is free
         if constexpr (DBG & 2) {
         } else if (qoff != 0) {
         } else if (tid >= 64 && tid < 128) {
@@ -642,13 +725,11 @@ k_psi2_bwd(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __rest
       }
       for (int64_t n = r0; n < r1; ++n) {
         const int s = (int)(n & 1);
-        const double* v = sV + (n % 3) * VB;
+        const double* v = rv.row(n - r0);
         double* Lb = sL + s * 64 * RSL;
-        double nxt = vec_load(n + 1);
         {
           double acc[5][2];
           stage1_diag<QC>(sZI, v, qk, ti, tj, cnt, lane, acc);
-          if (tid < VB) sV[((n + 1) % 3) * VB + tid] = nxt;
 #pragma unroll
           for (int s5 = 0; s5 < 5; ++s5)
             if (s5 < cnt) {
@@ -671,6 +752,7 @@ k_psi2_bwd(int64_t rc, int Mp, int nt, int nblocks, int qk, const double* __rest
             }
         }
         __syncthreads();
+        if (tid == 0) rv.refill(n - r0);
         if (qoff == 0 && tid >= 64 && tid < 128) { // lambda_m = full row sum of the symmetric tile
           const int m = tid - 64;
           const double2* row = reinterpret_cast<const double2*>(Lb + m * RSL);
