@@ -103,6 +103,14 @@ RGP_DEVINL double reduce8_over_g(const double (&v)[8], int lane) {
   return keep + __shfl_xor_sync(0xffffffffu, send, 4);
 }
 
+// fp64 tensor-style MMA (DMMA.8x8x4 in SASS): D[8x8] += A[8x4] B[4x8]; lane (g = lane / 4, t = lane % 4) holds
+// A[g][t], B[t][g] and D[g][2t], D[g][2t+1].  Runs on the FP64 pipe (same peak as DFMA, far fewer operand bytes).
+RGP_DEVINL void dmma(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
 RGP_DEVINL double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

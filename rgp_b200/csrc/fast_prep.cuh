@@ -111,10 +111,14 @@ __global__ void k_rowprep(int64_t N, int Q, int QC, const double* __restrict__ m
 }
 
 // ---------------------------------------------------------------------------------
-// Small tiled DGEMM: C(i,j) = sum_k A(i,k) B(j,k), 64x64 tile per CTA, 256 threads,
-// 4x4 per thread, K staged 16 at a time.  Operand element (r,k) lives at
-// ptr[r*sr + k*sk]; *_KC says whether k (true) or r (false) is the unit-stride index,
-// which only decides how the staging loads are coalesced.  blockIdx.z splits K.
+// Small tiled DGEMM on DMMA: C(i,j) = sum_k A(i,k) B(j,k), 64x64 tile per CTA, 8 warps, each a 16 x 32
+// sub-tile of 2 x 4 m8n8k4 accumulators (the tiling of the Psi2 kernels), K staged 16 at a time through
+// shared memory with the next chunk prefetched into registers.  Operand element (r,k) lives at
+// ptr[r*sr + k*sk]; *_KC says whether k (true) or r (false) is the unit-stride index, which decides how
+// the staging loads are coalesced AND the shared layout: k-major operands are kept [r][k] (stride 20),
+// r-major ones [k][r] (stride 68) - both strides == 4 (mod 16), so every fragment load hits each bank
+// exactly twice and the staging stores are contiguous.  blockIdx.z splits K.  (Round 1 used 4x4 DFMA register
+// tiles here: 42-48 % of the FP64 peak; these five GEMMs are 2.5 % of the headline step, 10 % at M = 100.)
 // ---------------------------------------------------------------------------------
 struct GemmOperand {
   const double* p;
@@ -136,86 +140,119 @@ struct GemmEpi {
   int64_t split_stride;    // EPI_PLAIN with split-K: elements between partial outputs
 };
 
+constexpr int GEMM_SK = 20;    // [r][k] layout: 16 k + 4
+constexpr int GEMM_SR = 68;    // [k][r] layout: 64 r + 4
+constexpr int GEMM_TILE = 64 * GEMM_SK;   // >= 16 * GEMM_SR
+
+// global -> registers: the 4 elements of a 64 x 16 operand chunk this thread stages
 template <bool KC>
-__device__ __forceinline__ void gemm_stage(const GemmOperand& op, int64_t r0, int64_t k0,
-                                           int64_t kend, double (*sm)[65], int tid) {
-  // fills sm[k][r] for k in [0,16), r in [0,64)
+__device__ __forceinline__ void gemm_fetch(const GemmOperand& op, int64_t r0, int64_t k0, int64_t kend, int tid,
+                                           double (&v)[4]) {
   if (KC) {
-    int kk = tid & 15, rr = tid >> 4;             // 16 k x 16 rows per pass
+    const int kk = tid & 15, rr = tid >> 4;       // 16 k x 16 rows per pass
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
-      int r = rr + 16 * p;
-      int64_t gr = r0 + r, gk = k0 + kk;
-      sm[kk][r] = (gr < op.rows && gk < kend) ? op.p[gr * op.sr + gk * op.sk] : 0.0;
+      const int64_t gr = r0 + rr + 16 * p, gk = k0 + kk;
+      v[p] = (gr < op.rows && gk < kend) ? op.p[gr * op.sr + gk * op.sk] : 0.0;
     }
   } else {
-    int rr = tid & 63, kk = tid >> 6;             // 64 rows x 4 k per pass
+    const int rr = tid & 63, kk = tid >> 6;       // 64 rows x 4 k per pass
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
-      int k = kk + 4 * p;
-      int64_t gr = r0 + rr, gk = k0 + k;
-      sm[k][rr] = (gr < op.rows && gk < kend) ? op.p[gr * op.sr + gk * op.sk] : 0.0;
+      const int64_t gr = r0 + rr, gk = k0 + kk + 4 * p;
+      v[p] = (gr < op.rows && gk < kend) ? op.p[gr * op.sr + gk * op.sk] : 0.0;
     }
   }
 }
 
+// registers -> shared, element (r, k) at sm[r * GEMM_SK + k] (KC) or sm[k * GEMM_SR + r]
+template <bool KC>
+__device__ __forceinline__ void gemm_store(double* sm, int tid, const double (&v)[4]) {
+  if (KC) {
+    const int kk = tid & 15, rr = tid >> 4;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) sm[(rr + 16 * p) * GEMM_SK + kk] = v[p];
+  } else {
+    const int rr = tid & 63, kk = tid >> 6;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) sm[(kk + 4 * p) * GEMM_SR + rr] = v[p];
+  }
+}
+
+template <bool KC>
+__device__ __forceinline__ double gemm_frag(const double* sm, int r, int k) {
+  return KC ? sm[r * GEMM_SK + k] : sm[k * GEMM_SR + r];
+}
+
 template <bool A_KC, bool B_KC>
 __global__ void __launch_bounds__(256) k_gemm(GemmOperand A, GemmOperand B, int64_t K, GemmEpi epi) {
-  __shared__ double As[16][65];
-  __shared__ double Bs[16][65];
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  __shared__ __align__(16) double As[GEMM_TILE];
+  __shared__ __align__(16) double Bs[GEMM_TILE];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int wr = wid >> 1, wc = wid & 1, g = lane >> 2, t = lane & 3;
   const int64_t i0 = (int64_t)blockIdx.x * 64, j0 = (int64_t)blockIdx.y * 64;
   int64_t kper = (K + gridDim.z - 1) / gridDim.z;
   kper = (kper + 15) / 16 * 16;
   const int64_t kbeg = kper * blockIdx.z, kend = (kbeg + kper < K) ? kbeg + kper : K;
-  double acc[4][4];
+  double acc[2][4][2];
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+  for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  double va[4], vb[4];
+  if (kbeg < kend) {
+    gemm_fetch<A_KC>(A, i0, kbeg, kend, tid, va);
+    gemm_fetch<B_KC>(B, j0, kbeg, kend, tid, vb);
+  }
   for (int64_t k0 = kbeg; k0 < kend; k0 += 16) {
-    gemm_stage<A_KC>(A, i0, k0, kend, As, tid);
-    gemm_stage<B_KC>(B, j0, k0, kend, Bs, tid);
+    __syncthreads();                              // previous chunk's fragments all read
+    gemm_store<A_KC>(As, tid, va);
+    gemm_store<B_KC>(Bs, tid, vb);
     __syncthreads();
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      double a[4], b[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        a[u] = As[k][ty + 16 * u];
-        b[u] = Bs[k][tx + 16 * u];
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-#pragma unroll
-        for (int v = 0; v < 4; ++v) acc[u][v] = fma(a[u], b[v], acc[u][v]);
+    if (k0 + 16 < kend) {                         // next chunk in flight while this one is multiplied
+      gemm_fetch<A_KC>(A, i0, k0 + 16, kend, tid, va);
+      gemm_fetch<B_KC>(B, j0, k0 + 16, kend, tid, vb);
     }
-    __syncthreads();
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      double a[2], b[4];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) a[i] = gemm_frag<A_KC>(As, 16 * wr + 8 * i + g, 4 * ks + t);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = gemm_frag<B_KC>(Bs, 32 * wc + 8 * j + g, 4 * ks + t);
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
   }
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    int64_t i = i0 + ty + 16 * u;
-    if (i >= A.rows) continue;
+  for (int i = 0; i < 2; ++i) {
+    const int64_t row = i0 + 16 * wr + 8 * i + g;
+    if (row >= A.rows) continue;
 #pragma unroll
-    for (int v = 0; v < 4; ++v) {
-      int64_t j = j0 + tx + 16 * v;
-      double val = acc[u][v];
-      if (epi.mode == EPI_HP) {
-        // HP[tile][row][64]; padded inducing points get a hugely negative exponent
-        double h = (j < epi.M) ? epi.bias[i] + val : NEG_BIG;
-        epi.out[((int64_t)blockIdx.y * epi.out_ld + i) * 64 + (tx + 16 * v)] = h;
-      } else if (epi.mode == EPI_PSI1) {
-        if (j < epi.M) epi.out[i * epi.out_ld + j] = epi.variance * exp_neg(epi.bias[i] + val);
-      } else if (epi.mode == EPI_L1) {
-        // L1[row][Mp], zero in the padding
-        double l = 0.0;
-        if (j < epi.M)
-          l = epi.scale[i * epi.scale_ld + j] * epi.variance * exp_neg(epi.bias[i] + val);
-        epi.out[i * epi.out_ld + j] = l;
-      } else {
-        if (j < B.rows) epi.out[(int64_t)blockIdx.z * epi.split_stride + i * epi.out_ld + j] = val;
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int cl = 32 * wc + 8 * j + 2 * t + e;   // column inside the 64-wide tile
+        const int64_t col = j0 + cl;
+        const double val = acc[i][j][e];
+        if (epi.mode == EPI_HP) {
+          // HP[tile][row][64]; padded inducing points get a hugely negative exponent
+          const double h = (col < epi.M) ? epi.bias[row] + val : NEG_BIG;
+          epi.out[((int64_t)blockIdx.y * epi.out_ld + row) * 64 + cl] = h;
+        } else if (epi.mode == EPI_PSI1) {
+          if (col < epi.M) epi.out[row * epi.out_ld + col] = epi.variance * exp_neg(epi.bias[row] + val);
+        } else if (epi.mode == EPI_L1) {
+          // L1[row][Mp], zero in the padding
+          double l = 0.0;
+          if (col < epi.M)
+            l = epi.scale[row * epi.scale_ld + col] * epi.variance * exp_neg(epi.bias[row] + val);
+          epi.out[row * epi.out_ld + col] = l;
+        } else {
+          if (col < B.rows) epi.out[(int64_t)blockIdx.z * epi.split_stride + row * epi.out_ld + col] = val;
+        }
       }
-    }
   }
 }
 

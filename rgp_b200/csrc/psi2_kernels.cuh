@@ -51,12 +51,6 @@ struct P2Cfg {
   static constexpr int BWD_FUSED_SMEM = BWD_SMEM + 64 * RSL * 8;
 };
 
-RGP_DEVINL void dmma(double& d0, double& d1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-               : "+d"(d0), "+d"(d1)
-               : "d"(a), "d"(b));
-}
-
 RGP_DEVINL void red_add(double* addr, double v) {
   asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
 }

@@ -252,6 +252,48 @@ def test_plugin_cache_sees_rows_permuted_in_place():
     assert relerr(kb.psi1(Z, X), r1) < 1e-14
 
 
+@pytest.mark.parametrize("pinned", [False, True, "mixed"])
+def test_host_entry_points_stream_many_chunks(pinned):
+    """The numpy plugin path over SEVERAL host chunks (ring slots reused, results of chunk c-1 drained while chunk c
+    computes, ragged last chunk): pageable caller buffers go through the pinned staging ring, page-locked ones are
+    used in place, and a mix of both must give the same answer - all against the oracle."""
+    import torch
+    from rgp_b200.psicomp import PSICOMP_RBF_B200
+    N, M, Q = 3571, 70, 12
+    var, ell, Z, mu, S = make_inputs(N, M, Q, seed=91, n_control=3)
+    dL0, dL1, dL2 = make_upstream(N, M, seed=92)
+    keep = []
+
+    def place(a, pin):
+        if not pin:
+            return a
+        t = torch.from_numpy(a.copy()).pin_memory()
+        keep.append(t)
+        return t.numpy()
+
+    pin_in = pinned is True
+    mu_p, S_p = place(mu, pin_in), place(S, pin_in or pinned == "mixed")
+    dL1_p, dL0_p = place(dL1, pin_in), place(dL0, pin_in)
+    from rgp_b200.gpy_compat import NormalPosterior
+    pc = PSICOMP_RBF_B200(cache=False)
+    kern = _kern(pc, var, ell)
+    X = NormalPosterior(mu, S)
+    X.mean, X.variance = mu_p, S_p                                          # the caller's own buffers, not copies
+    want = psi_forward(var, ell, Z, mu, S), psi_backward(dL0, dL1, dL2, var, ell, Z, mu, S)
+
+    def run():
+        return pc.psicomputations(kern, Z, X), pc.psiDerivativecomputations(kern, dL0_p, dL1_p, dL2, Z, X)
+
+    for chunk in (1000, 997):
+        pc.handle.set_option("host_chunk", chunk)                           # 4 chunks, the last one ragged
+        fwd, bwd = run()
+        _compare(fwd, bwd, want[0], want[1], TIGHT)
+    pc.handle.set_option("host_chunk", 0)
+    pc.handle.set_option("host_threads", 3)
+    fwd, bwd = run()
+    _compare(fwd, bwd, want[0], want[1], TIGHT)
+
+
 def test_device_api_scalar_dL0_and_null_outputs():
     import torch
     from rgp_b200.device import DevicePsi
