@@ -116,16 +116,19 @@ def build_debug() -> str:
 
 
 def build_microbench() -> str:
-    """Standalone hardware microbenchmarks (DFMA / DMMA peaks, smem broadcast costs)."""
+    """Standalone hardware microbenchmarks: microbench (DFMA / DMMA peaks, smem broadcast costs) and mixbench
+    (how DMMA and scalar FP64 instructions share the pipe).  Returns the path of the first."""
     os.makedirs(LIBDIR, exist_ok=True)
-    src = os.path.join(CSRC, "microbench.cu")
-    if os.path.exists(MICRO) and os.path.getmtime(MICRO) >= os.path.getmtime(src):
-        return MICRO
-    cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
-           "-std=c++17", "-o", MICRO, src]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    for name in ("microbench", "mixbench"):
+        src = os.path.join(CSRC, name + ".cu")
+        exe = os.path.join(LIBDIR, name)
+        if os.path.exists(exe) and os.path.getmtime(exe) >= os.path.getmtime(src):
+            continue
+        cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
+               "-std=c++17", "-o", exe, src]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     return MICRO
 
 
