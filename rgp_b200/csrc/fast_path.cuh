@@ -6,6 +6,7 @@
 #include "fast_prep.cuh"
 #include "psi2_kernels.cuh"
 #include "psi2_bwdp.cuh"
+#include "psi2_small.cuh"
 #ifdef RGP_DEBUG
 #include "experimental/psi2_bwdw.cuh"   // warp-specialised variant: a measured negative result, experiment builds only
 #endif
@@ -39,7 +40,25 @@ static int init_qc() {
   return 0;
 }
 
+template <int QT>
+static int init_small() {
+  RGP_CUDA(cudaFuncSetAttribute((k_psi2_small<QT, 0, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                small_smem_doubles(PS_MS_MAX, QT, false) * 8));
+  RGP_CUDA(cudaFuncSetAttribute((k_psi2_small<QT, 1, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                small_smem_doubles(PS_MS_MAX, QT, true) * 8));
+  RGP_CUDA(cudaFuncSetAttribute((k_psi2_small<QT, 1, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                small_smem_doubles(PS_MS_MAX, QT, true) * 8));
+  RGP_CUDA(cudaFuncSetAttribute((k_psi2_small<QT, 2, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                small_smem_doubles(PS_MS_MAX, QT, true) * 8));
+  RGP_CUDA(cudaFuncSetAttribute((k_psi2_small<QT, 2, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                small_smem_doubles(PS_MS_MAX, QT, true) * 8));
+  return 0;
+}
+
 static int init(rgp_psi_ctx*) {
+  RGP_TRY(init_small<1>());
+  RGP_TRY(init_small<2>());
+  RGP_TRY(init_small<3>());
   RGP_TRY(init_qc<16>());
   RGP_TRY(init_qc<32>());
   RGP_TRY(init_qc<64>());
@@ -211,6 +230,75 @@ static int launch_bwd(rgp_psi_ctx* h, cudaStream_t st, const Shape& s, int64_t r
   return 0;
 }
 
+// ---- small inducing sets (psi2_small.cuh): one CTA holds the whole pair matrix of a row -------------------
+struct SmallPlan {
+  bool ok = false;
+  int Ms = 0, Mp16 = 0, QT = 0, KS = 0, JMAX = 0;
+};
+
+// DMMAs per row of the 64 x 64 block kernels / of the small kernel (both passes), used to choose between them
+static inline double block_dmma_per_row(const Shape& s, bool pipelined) {
+  const int ks1 = s.qk / 4;
+  int qs = s.QC > 64 ? 64 : s.QC;                       // stage-2 columns per pass
+  if (pipelined && s.QC == 64 && s.Q <= 48) qs = 48;
+  const int passes = s.QC > 64 ? 2 : 1;
+  const double diag = 36.0 * ks1 + 8.0 * (qs / 8) * 16, off = 64.0 * ks1 + 2 * 8.0 * (qs / 8) * 16;
+  const double fwd = s.nt * 36.0 * ks1 + (s.nblocks - s.nt) * 64.0 * ks1;
+  return fwd + passes * (s.nt * diag + (s.nblocks - s.nt) * off);
+}
+static inline double small_dmma_per_row(int Ms, int QT, int qk) {
+  const double s1 = Ms * (Ms + 1) / 2 * 4.0 * (qk / 4);
+  return 2 * s1 + 2.0 * Ms * QT * 4 * Ms;
+}
+
+// small_m: 0 = never, 1 = whenever the shape fits, 2 (default) = when it also saves >= 15 % of the DMMAs
+static SmallPlan small_plan(const rgp_psi_ctx* h, const Shape& s) {
+  SmallPlan p;
+  if (h->small_m == 0) return p;
+  const int Ms = (s.M + 15) / 16, QT = (s.Q + 7) / 8;
+  if (Ms > PS_MS_MAX || QT > 3) return p;
+  if (h->small_m == 2 && small_dmma_per_row(Ms, QT, s.qk) > 0.85 * block_dmma_per_row(s, false)) return p;
+  p.ok = true;
+  p.Ms = Ms;
+  p.Mp16 = 16 * Ms;
+  p.QT = QT;
+  p.KS = h->small_ks > 0 ? h->small_ks : 4;
+  p.JMAX = (Ms * p.KS + PS_WARPS - 1) / PS_WARPS;
+  return p;
+}
+
+template <int QT, int MODE>
+static int launch_small_qt(rgp_psi_ctx* h, cudaStream_t st, const Shape& s, const SmallPlan& p, int64_t rows, int Rs,
+                           const double* Zt, const double* Ct, const double* w, const double* HP, double* lam,
+                           double* Wq, double* ACCp, double* P2s) {
+  const char* name = MODE == 0 ? "psi2_fwd" : (MODE == 1 ? "psi2_bwd" : "psi2_bwd_fused");
+  const int smem = small_smem_doubles(p.Ms, QT, MODE != 0) * 8;
+  if constexpr (MODE == 0) {
+    RGP_LAUNCH(h, st, name, (k_psi2_small<QT, 0, 1>), Rs, PS_THREADS, smem, rows, s.Mp, p.Ms, s.nt, s.qk, s.QC,
+               p.KS, s.RS, Zt, Ct, w, HP, lam, Wq, ACCp, P2s);
+  } else if (p.JMAX == 1) {
+    RGP_LAUNCH(h, st, name, (k_psi2_small<QT, MODE, 1>), Rs, PS_THREADS, smem, rows, s.Mp, p.Ms, s.nt, s.qk, s.QC,
+               p.KS, s.RS, Zt, Ct, w, HP, lam, Wq, ACCp, P2s);
+  } else {
+    RGP_LAUNCH(h, st, name, (k_psi2_small<QT, MODE, 2>), Rs, PS_THREADS, smem, rows, s.Mp, p.Ms, s.nt, s.qk, s.QC,
+               p.KS, s.RS, Zt, Ct, w, HP, lam, Wq, ACCp, P2s);
+  }
+  return 0;
+}
+
+template <int MODE>
+static int launch_small(rgp_psi_ctx* h, cudaStream_t st, const Shape& s, const SmallPlan& p, int64_t rows, int Rs,
+                        const double* Zt, const double* Ct, const double* w, const double* HP, double* lam,
+                        double* Wq, double* ACCp, double* P2s) {
+  if (p.QT == 1) return launch_small_qt<1, MODE>(h, st, s, p, rows, Rs, Zt, Ct, w, HP, lam, Wq, ACCp, P2s);
+  if (p.QT == 2) return launch_small_qt<2, MODE>(h, st, s, p, rows, Rs, Zt, Ct, w, HP, lam, Wq, ACCp, P2s);
+  return launch_small_qt<3, MODE>(h, st, s, p, rows, Rs, Zt, Ct, w, HP, lam, Wq, ACCp, P2s);
+}
+
+static inline int small_grid(const rgp_psi_ctx* h, int64_t rows) {
+  return (int)std::max<int64_t>(1, std::min<int64_t>(h->sm_count, rows));
+}
+
 // lam[0] += sum_{g>=1} lam[g]  (and the same for Wq); only launched when G > 1
 __global__ void k_collapse(int64_t count, int G, double* __restrict__ buf) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -244,15 +332,18 @@ static int forward(rgp_psi_ctx* h, cudaStream_t st, int64_t N, int M, int Q, con
   int R, G;
   pick_grid(s.rc, s.nblocks, 2 * h->sm_count, &R, &G);
   const int QC = s.QC;
+  const SmallPlan sp = small_plan(h, s);
+  const int Rs = small_grid(h, s.rc);
+  const size_t p2_count = sp.ok ? (size_t)Rs * sp.Mp16 * sp.Mp16 : (size_t)s.nblocks * R * 4096;
   size_t need = bump_size(Q, 8) + bump_size((size_t)s.Mp * s.RS, 8) + bump_size((size_t)s.Mp * 2 * QC, 8) +
-                bump_size((size_t)s.nblocks * R * 4096, 8) + bump_size(s.rc * QC, 8) +
+                bump_size(p2_count, 8) + bump_size(s.rc * QC, 8) +
                 bump_size(s.rc * 2 * QC, 8) * 2 + bump_size(s.rc, 8) * 2 + bump_size(s.rc * s.Mp, 8);
   RGP_TRY(arena_reserve(&h->ws, &h->ws_bytes, need));
   Bump b(h->ws, h->ws_bytes);
   double* o = b.take<double>(Q);
   double* Zt = b.take<double>((size_t)s.Mp * s.RS);
   double* ZB = b.take<double>((size_t)s.Mp * 2 * QC);
-  double* P2p = b.take<double>((size_t)s.nblocks * R * 4096);
+  double* P2p = b.take<double>(p2_count);
   double* w = b.take<double>(s.rc * QC);
   double* A2 = b.take<double>(s.rc * 2 * QC);
   double* A1 = b.take<double>(s.rc * 2 * QC);
@@ -274,6 +365,13 @@ static int forward(rgp_psi_ctx* h, cudaStream_t st, int64_t N, int M, int Q, con
     if (psi1) {
       e.mode = EPI_PSI1; e.bias = b1; e.out = psi1 + r0 * M; e.out_ld = M;
       RGP_TRY(gemm_nt(h, st, "psi1_fwd", s, rows, A1, ZB, e));
+    }
+    if (sp.ok) {
+      const int Rr = std::min(Rs, small_grid(h, rows));
+      RGP_TRY(launch_small<0>(h, st, s, sp, rows, Rr, Zt, nullptr, w, HP, nullptr, nullptr, nullptr, P2p));
+      RGP_LAUNCH(h, st, "psi2_reduce", k_psi2_reduce_small, ceil_div((int64_t)M * M, 256), 256, 0, M, sp.Mp16, Rr,
+                 variance * variance, P2p, (chunk > 0 || h->accumulate) ? 1 : 0, psi2);
+      continue;
     }
     int Rc, Gc;
     pick_grid(rows, s.nblocks, 2 * h->sm_count, &Rc, &Gc);
@@ -297,10 +395,14 @@ static int backward(rgp_psi_ctx* h, cudaStream_t st, int64_t N, int M, int Q, co
   // (Psi1 from one more small GEMM, Psi2 from the backward kernel itself, see k_psi2_bwd FUSE)
   Shape s = make_shape(h, N, M, Q);
   if (use_pipelined(h, s.QC, Q, psi2_out != nullptr)) s.RS = s.QC + 4;   // the Z' tile layout follows the kernel
+  const SmallPlan sp = small_plan(h, s);
+  const int Rs = small_grid(h, s.rc);
   int R, G;
   pick_grid(s.rc, s.nblocks, h->sm_count, &R, &G);
+  if (sp.ok) G = 1;
   const int QC = s.QC, Mp = s.Mp;
-  const int ncta = R * G;
+  const int ncta = sp.ok ? Rs * sp.KS : R * G;
+  const size_t p2_count = sp.ok ? (size_t)Rs * sp.Mp16 * sp.Mp16 : (size_t)s.nblocks * R * 4096;
   const int tn_tiles = s.nt * (2 * QC / 64 > 0 ? (2 * QC + 63) / 64 : 1);
   const int splits = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)64, (int64_t)(2 * h->sm_count / std::max(1, tn_tiles)),
                                                                  (s.rc + 255) / 256}));
@@ -311,14 +413,14 @@ static int backward(rgp_psi_ctx* h, cudaStream_t st, int64_t N, int M, int Q, co
                 bump_size((size_t)G * s.rc * Mp, 8) + bump_size((size_t)G * s.rc * QC, 8) +
                 bump_size((size_t)ncta * Mp * QC, 8) + bump_size((size_t)splits * Mp * 2 * QC, 8) * 2 +
                 bump_size((size_t)nfin * (QC + 1), 8) +
-                (psi2_out ? bump_size((size_t)s.nblocks * R * 4096, 8) : 0);
+                (psi2_out ? bump_size(p2_count, 8) : 0);
   RGP_TRY(arena_reserve(&h->ws, &h->ws_bytes, need));
   Bump b(h->ws, h->ws_bytes);
   double* o = b.take<double>(Q);
   double* Zt = b.take<double>((size_t)Mp * s.RS);
   double* ZB = b.take<double>((size_t)Mp * 2 * QC);
   double* Ct = b.take<double>((size_t)s.nblocks * 4096);
-  double* P2p = psi2_out ? b.take<double>((size_t)s.nblocks * R * 4096) : nullptr;
+  double* P2p = psi2_out ? b.take<double>(p2_count) : nullptr;
   double* w = b.take<double>(s.rc * QC);
   double* A2 = b.take<double>(s.rc * 2 * QC);
   double* A1 = b.take<double>(s.rc * 2 * QC);
@@ -350,7 +452,8 @@ static int backward(rgp_psi_ctx* h, cudaStream_t st, int64_t N, int M, int Q, co
     pick_grid(rows, s.nblocks, h->sm_count, &Rc, &Gc);
     Rc = std::min(Rc, R);
     Gc = std::min(Gc, G);
-    const int nc = Rc * Gc;
+    const int Rr = std::min(Rs, small_grid(h, rows));
+    const int nc = sp.ok ? Rr * sp.KS : Rc * Gc;
     RGP_CUDA(cudaMemsetAsync(lam, 0, sizeof(double) * (size_t)Gc * rows * Mp, st));
     RGP_CUDA(cudaMemsetAsync(Wq, 0, sizeof(double) * (size_t)Gc * rows * QC, st));
     RGP_CUDA(cudaMemsetAsync(ACCp, 0, sizeof(double) * (size_t)nc * Mp * QC, st));
@@ -369,11 +472,17 @@ static int backward(rgp_psi_ctx* h, cudaStream_t st, int64_t N, int M, int Q, co
       e.mode = EPI_L1; e.bias = b1; e.scale = dL1 + r0 * M; e.scale_ld = M; e.out = L1; e.out_ld = Mp;
       RGP_TRY(gemm_nt(h, st, "psi1_L1", s, rows, A1, ZB, e));
     }
-    if (QC == 16) RGP_TRY(launch_bwd<16>(h, st, s, rows, Rc, Gc, Zt, Ct, w, HP, lam, Wq, ACCp, P2p));
+    if (sp.ok) {
+      if (P2p) RGP_TRY(launch_small<2>(h, st, s, sp, rows, Rr, Zt, Ct, w, HP, lam, Wq, ACCp, P2p));
+      else RGP_TRY(launch_small<1>(h, st, s, sp, rows, Rr, Zt, Ct, w, HP, lam, Wq, ACCp, P2p));
+    } else if (QC == 16) RGP_TRY(launch_bwd<16>(h, st, s, rows, Rc, Gc, Zt, Ct, w, HP, lam, Wq, ACCp, P2p));
     else if (QC == 32) RGP_TRY(launch_bwd<32>(h, st, s, rows, Rc, Gc, Zt, Ct, w, HP, lam, Wq, ACCp, P2p));
     else if (QC == 64) RGP_TRY(launch_bwd<64>(h, st, s, rows, Rc, Gc, Zt, Ct, w, HP, lam, Wq, ACCp, P2p));
     else RGP_TRY(launch_bwd<128>(h, st, s, rows, Rc, Gc, Zt, Ct, w, HP, lam, Wq, ACCp, P2p));
-    if (P2p)
+    if (P2p && sp.ok)
+      RGP_LAUNCH(h, st, "psi2_reduce", k_psi2_reduce_small, ceil_div((int64_t)M * M, 256), 256, 0, M, sp.Mp16, Rr,
+                 variance * variance, P2p, (chunk > 0 || h->accumulate) ? 1 : 0, psi2_out);
+    else if (P2p)
       RGP_LAUNCH(h, st, "psi2_reduce", k_psi2_reduce, dim3(s.nblocks, 16), 256, 0, M, s.nt, Rc, variance * variance, P2p,
                  (chunk > 0 || h->accumulate) ? 1 : 0, psi2_out);
     if (Gc > 1) {

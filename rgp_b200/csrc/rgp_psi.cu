@@ -248,6 +248,13 @@ int rgp_psi_set_option(rgp_psi_handle_t h, const char* key, int64_t value) {
     if (value < 0 || value > 2) return set_error(RGP_PSI_ERR_INVALID, "bwd_pipe must be 0, 1 or 2");
 #endif
     h->bwd_pipe = (int)value;
+  } else if (!strcmp(key, "small_m")) {
+    if (value < 0 || value > 2) return set_error(RGP_PSI_ERR_INVALID, "small_m must be 0, 1 or 2");
+    h->small_m = (int)value;
+  } else if (!strcmp(key, "small_ks")) {
+    if (value != 0 && value != 1 && value != 2 && value != 4)
+      return set_error(RGP_PSI_ERR_INVALID, "small_ks must be 0, 1, 2 or 4");
+    h->small_ks = (int)value;
 #ifdef RGP_DEBUG
   // experiment knobs: they make kernels skip work (wrong results) or change occupancy, so the
   // production library does not know them

@@ -27,8 +27,12 @@ def plugins():
     from rgp_b200.psicomp import PSICOMP_RBF_B200
     pipe = PSICOMP_RBF_B200(impl="auto", cache=False)
     pipe.handle.set_option("bwd_pipe", 1)             # software-pipelined Psi2 backward kernel for the plain backward pass too
+    block = PSICOMP_RBF_B200(impl="auto", cache=False)
+    block.handle.set_option("small_m", 0)             # 64 x 64 block kernels at every shape
+    small = PSICOMP_RBF_B200(impl="auto", cache=False)
+    small.handle.set_option("small_m", 1)             # whole-pair-matrix kernels (psi2_small.cuh) wherever they fit
     return {"reference": PSICOMP_RBF_B200(impl="reference", cache=False),
-            "fast": PSICOMP_RBF_B200(impl="auto", cache=False), "pipe": pipe}
+            "fast": PSICOMP_RBF_B200(impl="auto", cache=False), "pipe": pipe, "block": block, "small": small}
 
 
 def _kern(pc, var, ell, ard=True):
@@ -72,7 +76,7 @@ SHAPES = [
 ]
 
 
-@pytest.mark.parametrize("impl", IMPLS + ["pipe"])
+@pytest.mark.parametrize("impl", IMPLS + ["pipe", "block", "small"])
 @pytest.mark.parametrize("N,M,Q,nc", SHAPES)
 def test_forward_and_backward_match_oracle(plugins, impl, N, M, Q, nc):
     var, ell, Z, mu, S = make_inputs(N, M, Q, seed=100 + N + M + Q, n_control=nc)
@@ -509,7 +513,7 @@ def test_options_are_validated():
     h = Handle(0)
     h._ensure()
     # the experiment knobs of round 1 (debug_skip, trace_ptr, fwd_smem_pad) are not options of the production library
-    for key, val in (("impl", 7), ("bwd_pipe", 3), ("row_chunk", -1), ("no_such_option", 1), ("debug_skip", 1),
+    for key, val in (("impl", 7), ("bwd_pipe", 3), ("small_m", 3), ("small_ks", 3), ("row_chunk", -1), ("no_such_option", 1), ("debug_skip", 1),
                      ("trace_ptr", 4096), ("fwd_smem_pad", 1024), ("bwd_warps", 16)):
         with pytest.raises(PsiError):
             h.set_option(key, val)
@@ -598,3 +602,79 @@ def test_fused_pass_equals_forward_then_backward(impl, N, M, Q, chunk):
         assert relerr(a.cpu().numpy(), b.cpu().numpy()) < 1e-12
     (n1, _), _ = dp.fused(t(mu), t(S), t(Z), t(ell), var, -0.5, None, t(dL2), want_psi1=False)
     assert n1 is None
+
+
+@pytest.mark.parametrize("ks", [0, 1, 2, 4])
+@pytest.mark.parametrize("N,M,Q,chunk", [
+    (5, 16, 8, 0), (37, 17, 9, 0), (300, 33, 3, 0), (611, 48, 24, 0), (1500, 50, 20, 0), (2000, 64, 16, 0),
+    (1203, 81, 7, 500), (4099, 100, 20, 0), (3001, 100, 10, 1024), (2500, 112, 24, 0), (900, 97, 17, 0)])
+def test_small_inducing_set_kernels(N, M, Q, chunk, ks):
+    """psi2_small.cuh (one CTA holds the whole pair matrix of a row; M <= 112, Q <= 24) against the 64 x 64 block
+    kernels and the oracle: every super-row count, stage-2 width and k split, fewer rows than CTAs, ragged row
+    ranges, row chunks, forward / backward / fused."""
+    import torch
+    from rgp_b200.device import DevicePsi
+    small, block = DevicePsi(0, impl=0), DevicePsi(0, impl=0)
+    small.handle.set_option("small_m", 1)
+    small.handle.set_option("small_ks", ks)
+    block.handle.set_option("small_m", 0)
+    if chunk:
+        small.handle.set_option("row_chunk", chunk)
+    var, ell, Z, mu, S = make_inputs(N, M, Q, seed=N + M + Q, n_control=min(3, Q - 1))
+    _, dL1, dL2 = make_upstream(N, M, seed=Q)
+    dL0 = np.random.default_rng(4).normal(size=N)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    np_ = lambda x: x.cpu().numpy()
+    args = (t(mu), t(S), t(Z), t(ell), var)
+    fs, fb = small.forward(*args), block.forward(*args)
+    bs, bb = small.backward(*args, t(dL0), t(dL1), t(dL2)), block.backward(*args, t(dL0), t(dL1), t(dL2))
+    assert relerr(np_(fs[1]), np_(fb[1])) < 1e-14 and relerr(np_(fs[2]), np_(fb[2])) < 1e-12
+    for name, a, b in zip(["dvar", "dl", "dZ", "dmu", "dS"], bs, bb):
+        assert relerr(np_(a), np_(b)) < 1e-11, name
+    (p1, p2), grads = small.fused(*args, t(dL0), t(dL1), t(dL2))
+    assert relerr(np_(p2), np_(fs[2])) < 1e-13 and relerr(np_(p1), np_(fs[1])) < 1e-14
+    for name, a, b in zip(["dvar", "dl", "dZ", "dmu", "dS"], grads, bs):
+        assert relerr(np_(a), np_(b)) < 1e-12, name
+    if ks == 0:
+        of = psi_forward(var, ell, Z, mu, S)
+        ob = psi_backward(dL0, dL1, dL2, var, ell, Z, mu, S)
+        assert relerr(np_(fs[2]), of[2]) < TIGHT
+        for name, a, b in zip(["dvar", "dl", "dZ", "dmu", "dS"], bs, ob):
+            assert relerr(np_(a), b) < TIGHT, name
+
+
+def test_small_inducing_set_kernels_at_launch_geometry():
+    """The full 2^20-row launch of the small kernels (148 CTAs x 7086 rows, TMA ring wrapping thousands of times)
+    plus a ragged remainder chunk, at the shape of the reference's models (M = 100, Q = 20): against the block
+    kernels on the same rows, and 8-way row additivity (testing/minibatch_tests.py:288-296)."""
+    import torch
+    from rgp_b200.device import DevicePsi
+    small, block = DevicePsi(0, impl=0), DevicePsi(0, impl=0)
+    small.handle.set_option("small_m", 1)
+    block.handle.set_option("small_m", 0)
+    N, M, Q = (1 << 20) + 37, 100, 20
+    mu, S, Z, ell, dL1, dL2 = _device_inputs(N, M, Q, seed=17)
+    var = 0.7
+    np_ = lambda x: x.cpu().numpy()
+    fs = [x.clone() if x is not None else None for x in small.forward(mu, S, Z, ell, var)]
+    bs = [x.clone() for x in small.backward(mu, S, Z, ell, var, -0.5, dL1, dL2)]
+    fb = block.forward(mu, S, Z, ell, var)
+    assert relerr(np_(fs[2]), np_(fb[2])) < 1e-12
+    bb = block.backward(mu, S, Z, ell, var, -0.5, dL1, dL2)
+    for name, a, b in zip(["dvar", "dl", "dZ", "dmu", "dS"], bs, bb):
+        assert relerr(np_(a), np_(b)) < 1e-11, name
+    (q1, q2), fo = small.fused(mu, S, Z, ell, var, -0.5, dL1, dL2)
+    assert relerr(np_(q2), np_(fs[2])) < 1e-12
+    for a, b in zip(fo, bs):
+        assert relerr(np_(a), np_(b)) < 1e-12
+    acc2 = torch.zeros_like(fs[2])
+    accs = [torch.zeros(1, device="cuda", dtype=torch.float64), torch.zeros_like(ell), torch.zeros_like(Z)]
+    cuts = np.linspace(0, N, 9).astype(np.int64)
+    for s, e in zip(cuts[:-1], cuts[1:]):
+        acc2 += small.forward(mu[s:e], S[s:e], Z, ell, var, want_psi1=False)[2]
+        b = small.backward(mu[s:e], S[s:e], Z, ell, var, -0.5, dL1[s:e], dL2)
+        for a, x in zip(accs, b[:3]):
+            a += x
+    assert relerr(np_(acc2), np_(fs[2])) < 1e-12
+    for a, x in zip(accs, bs[:3]):
+        assert relerr(np_(a), np_(x)) < 1e-11
