@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define RGP_PSI_ABI_VERSION 3   /* 2: + fused, latent-terms, MLP free-run entry points; 3: + rgp_host_digest */
+#define RGP_PSI_ABI_VERSION 4   /* 2: + fused, latent-terms, MLP free-run entry points; 3: + rgp_host_digest; 4: + rgp_psi_small_schedule */
 
 typedef struct rgp_psi_ctx* rgp_psi_handle_t;
 
@@ -77,7 +77,10 @@ int rgp_psi_destroy(rgp_psi_handle_t h);
  * (threads of the pageable <-> pinned copies, 0 = min(8, cores / 2)),
  * "bwd_pipe" (Psi2 backward kernel: 0 = row-at-a-time, 1 = software-pipelined with TMA row-vector
  * staging, 2 (default) = row-at-a-time for the plain backward pass and pipelined for the fused pass,
- * the measured faster choice for each), "profile" (1 = record a CUDA-event pair around every kernel
+ * the measured faster choice for each), "small_m" (kernels for small inducing sets, M <= 112 and Q <= 24,
+ * where one CTA holds the whole pair matrix of a row: 0 = never, 1 = whenever the shape fits, 2 (default) =
+ * when they also save work against the 64 x 64 block kernels), "small_ks" (their stage-2 k split: 0 =
+ * default, or 1 / 2 / 4), "profile" (1 = record a CUDA-event pair around every kernel
  * launch).  Experiment knobs that change results or occupancy ("debug_skip", "fwd_smem_pad") exist only
  * in libraries compiled with -DRGP_DEBUG. */
 int rgp_psi_set_option(rgp_psi_handle_t h, const char* key, int64_t value);
@@ -111,6 +114,16 @@ int rgp_psi_backward_dev(rgp_psi_handle_t h, void* stream, int64_t N, int M, int
  * rows in a new order in testing/minibatch_tests.py:281-296).  out[0..1] = 128-bit order-sensitive
  * digest of data[0..nbytes); threads = 0 picks min(32, cores).  Pure host code, no device needed. */
 int rgp_host_digest(const void* data, int64_t nbytes, int threads, uint64_t out[2]);
+
+/* Work table of the small-inducing-set kernels (pure host code; introspection for tests and DESIGN.md).
+ * For shape (M, Q), stage-2 k split `ks` (0 = default) and pass (`backward` 0 / 1) writes, as signed bytes,
+ *   [0..15]  supertiles per warp        [16..47]  their indices, 2 per warp (row-major upper triangle of the
+ *   16 x 16 supertile grid)             [48..63]  jobs per warp          [64..95]  their job indices, 2 per warp
+ *   [96] number of jobs  [97] k slots   [98..129] strip of job j         [130..161] first k-step   [162..193] end
+ *   k-step   [194..225] accumulator slot
+ * and returns the number of bytes (226), or -1 (message set) when the small kernels do not serve the shape
+ * or `out_bytes` is too small. */
+int rgp_psi_small_schedule(int M, int Q, int ks, int backward, signed char* out, int out_bytes);
 
 /* ---- host-buffer wrappers (the numpy-in / numpy-out plugin path) -------------------
  * Rows are streamed through double-buffered device mirrors on three streams (copy-in, compute,

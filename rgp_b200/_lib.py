@@ -57,6 +57,7 @@ SIGNATURES = {
     "rgp_psi_reset_counters": (C.c_int, [C.c_void_p]),
     "rgp_psi_kernel_times": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), c_double_p,
                                        C.POINTER(C.c_int64)]),
+    "rgp_psi_small_schedule": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int]),
     "rgp_psi_fp64_peak": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, c_double_p]),
     "rgp_psi_workspace_bytes": (C.c_int64, [C.c_void_p]),
 }
@@ -98,7 +99,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.rgp_psi_abi_version() != 3:
+    if lib.rgp_psi_abi_version() != 4:
         raise OSError("librgp_psi ABI version mismatch")
     _lib = lib
     return lib

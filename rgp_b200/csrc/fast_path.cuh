@@ -1,6 +1,7 @@
 // fast_path.cuh - host-side driver of the tiled kernels: workspace plan and launch order.
 #pragma once
 #include <algorithm>
+#include <vector>
 
 #include "context.cuh"
 #include "fast_prep.cuh"
@@ -233,7 +234,8 @@ static int launch_bwd(rgp_psi_ctx* h, cudaStream_t st, const Shape& s, int64_t r
 // ---- small inducing sets (psi2_small.cuh): one CTA holds the whole pair matrix of a row -------------------
 struct SmallPlan {
   bool ok = false;
-  int Ms = 0, Mp16 = 0, QT = 0, KS = 0, JMAX = 0;
+  int Ms = 0, Mp16 = 0, QT = 0, KS = 0, JMAX = 1;
+  SmallSched fwd, bwd;     // which warp computes which supertiles (forward only) / supertiles and jobs (backward)
 };
 
 // DMMAs per row of the 64 x 64 block kernels / of the small kernel (both passes), used to choose between them
@@ -246,9 +248,75 @@ static inline double block_dmma_per_row(const Shape& s, bool pipelined) {
   const double fwd = s.nt * 36.0 * ks1 + (s.nblocks - s.nt) * 64.0 * ks1;
   return fwd + passes * (s.nt * diag + (s.nblocks - s.nt) * off);
 }
-static inline double small_dmma_per_row(int Ms, int QT, int qk) {
-  const double s1 = Ms * (Ms + 1) / 2 * 4.0 * (qk / 4);
-  return 2 * s1 + 2.0 * Ms * QT * 4 * Ms;
+static inline int small_valid_tiles(int si, int sj, int M8) {
+  const int vi = 16 * si + 8 < M8 ? 2 : 1, vj = 16 * sj + 8 < M8 ? 2 : 1;
+  return si == sj ? (vi == 2 ? 4 : 1) : vi * vj;     // 8x8 tiles the kernel computes on this supertile
+}
+static inline double small_dmma_per_row(int M, int Ms, int QT, int qk) {
+  const int M8 = (M + 7) & ~7;
+  double s1 = 0, s2 = 0;
+  for (int i = 0; i < Ms; ++i)
+    for (int j = i; j < Ms; ++j) s1 += small_valid_tiles(i, j, M8) * (qk / 4);
+  for (int sp = 0; sp < Ms; ++sp) s2 += (16 * sp + 8 < M8 ? 2 : 1) * QT * ((M + 3) / 4);
+  return 2 * s1 + s2;
+}
+
+// The work table of the small kernels.  Items: the supertiles of the upper triangle (stage 1 + exp) and, for the
+// backward pass, jobs = (16-row strip, 1 / KS of the k-steps).  Warp w issues on SM sub-partition w % 4, so the
+// items are dealt greedily (largest first) to the least loaded sub-partition, then to its least loaded warp with
+// a free slot.  Costs are FP64-pipe cycles: 16 per DMMA plus the scalar epilogue / fold work.
+static void small_schedule(int M, int Ms, int QT, int qk, int KS, int JMAX, bool bwd, SmallSched* sc) {
+  memset(sc, 0, sizeof(*sc));
+  const int M8 = (M + 7) & ~7, ksteps = (M + 3) / 4;
+  struct Item { double cost; int kind, a, b, c, d; };   // kind 0: supertile index a; kind 1: job (sp a, kb b, ke c, slot d)
+  std::vector<Item> items;
+  int u = 0;
+  for (int i = 0; i < Ms; ++i)
+    for (int j = i; j < Ms; ++j, ++u) {
+      const int tiles = small_valid_tiles(i, j, M8);
+      items.push_back({tiles * ((qk / 4) * 16.0 + 45.0) + 30.0, 0, u, 0, 0, 0});
+    }
+  int kslots = 1;
+  if (bwd)
+    for (int sp = 0; sp < Ms; ++sp) {
+      const int last = std::min(ksteps, 4 * Ms);
+      int slot = 0;
+      for (int i = 0; i < KS; ++i) {
+        const int kb = last * i / KS, ke = last * (i + 1) / KS;
+        if (ke <= kb) continue;
+        const int rowsets = 16 * sp + 8 < M8 ? 2 : 1;
+        items.push_back({(ke - kb) * (rowsets * QT * 16.0 + 6.0) + 90.0 + 14.0 * QT, 1, sp, kb, ke, slot});
+        ++slot;
+      }
+      kslots = std::max(kslots, slot);
+    }
+  std::stable_sort(items.begin(), items.end(), [](const Item& x, const Item& y) { return x.cost > y.cost; });
+  double wload[PS_WARPS] = {0}, pload[4] = {0};
+  int njobs = 0;
+  for (const Item& it : items) {
+    int best = -1;
+    for (int w = 0; w < PS_WARPS; ++w) {
+      if (it.kind == 0 ? sc->ns[w] >= PS_S1 : sc->nj[w] >= JMAX) continue;
+      if (best < 0 || pload[w & 3] < pload[best & 3] - 1e-9 ||
+          (pload[w & 3] < pload[best & 3] + 1e-9 && wload[w] < wload[best] - 1e-9))
+        best = w;
+    }
+    if (best < 0) best = 0;     // cannot happen: 16 * PS_S1 >= 28 supertiles, 16 * JMAX >= jobs (checked by the caller)
+    wload[best] += it.cost;
+    pload[best & 3] += it.cost;
+    if (it.kind == 0) {
+      sc->su[best][sc->ns[best]++] = (signed char)it.a;
+    } else {
+      sc->jsp[njobs] = (signed char)it.a;
+      sc->jkb[njobs] = (signed char)it.b;
+      sc->jke[njobs] = (signed char)it.c;
+      sc->jslot[njobs] = (signed char)it.d;
+      sc->jw[best][sc->nj[best]++] = (signed char)njobs;
+      ++njobs;
+    }
+  }
+  sc->njobs = (signed char)njobs;
+  sc->kslots = (signed char)kslots;
 }
 
 // small_m: 0 = never, 1 = whenever the shape fits, 2 (default) = when it also saves >= 15 % of the DMMAs
@@ -257,13 +325,15 @@ static SmallPlan small_plan(const rgp_psi_ctx* h, const Shape& s) {
   if (h->small_m == 0) return p;
   const int Ms = (s.M + 15) / 16, QT = (s.Q + 7) / 8;
   if (Ms > PS_MS_MAX || QT > 3) return p;
-  if (h->small_m == 2 && small_dmma_per_row(Ms, QT, s.qk) > 0.85 * block_dmma_per_row(s, false)) return p;
+  if (h->small_m == 2 && small_dmma_per_row(s.M, Ms, QT, s.qk) > 0.85 * block_dmma_per_row(s, false)) return p;
   p.ok = true;
   p.Ms = Ms;
   p.Mp16 = 16 * Ms;
   p.QT = QT;
-  p.KS = h->small_ks > 0 ? h->small_ks : 4;
+  p.KS = h->small_ks > 0 ? h->small_ks : 2;
   p.JMAX = (Ms * p.KS + PS_WARPS - 1) / PS_WARPS;
+  small_schedule(s.M, Ms, QT, s.qk, p.KS, p.JMAX, false, &p.fwd);
+  small_schedule(s.M, Ms, QT, s.qk, p.KS, p.JMAX, true, &p.bwd);
   return p;
 }
 
@@ -274,14 +344,14 @@ static int launch_small_qt(rgp_psi_ctx* h, cudaStream_t st, const Shape& s, cons
   const char* name = MODE == 0 ? "psi2_fwd" : (MODE == 1 ? "psi2_bwd" : "psi2_bwd_fused");
   const int smem = small_smem_doubles(p.Ms, QT, MODE != 0) * 8;
   if constexpr (MODE == 0) {
-    RGP_LAUNCH(h, st, name, (k_psi2_small<QT, 0, 1>), Rs, PS_THREADS, smem, rows, s.Mp, p.Ms, s.nt, s.qk, s.QC,
-               p.KS, s.RS, Zt, Ct, w, HP, lam, Wq, ACCp, P2s);
+    RGP_LAUNCH(h, st, name, (k_psi2_small<QT, 0, 1>), Rs, PS_THREADS, smem, rows, s.M, s.Mp, p.Ms, s.nt, s.qk, s.QC,
+               s.RS, p.fwd, Zt, Ct, w, HP, lam, Wq, ACCp, P2s);
   } else if (p.JMAX == 1) {
-    RGP_LAUNCH(h, st, name, (k_psi2_small<QT, MODE, 1>), Rs, PS_THREADS, smem, rows, s.Mp, p.Ms, s.nt, s.qk, s.QC,
-               p.KS, s.RS, Zt, Ct, w, HP, lam, Wq, ACCp, P2s);
+    RGP_LAUNCH(h, st, name, (k_psi2_small<QT, MODE, 1>), Rs, PS_THREADS, smem, rows, s.M, s.Mp, p.Ms, s.nt, s.qk,
+               s.QC, s.RS, p.bwd, Zt, Ct, w, HP, lam, Wq, ACCp, P2s);
   } else {
-    RGP_LAUNCH(h, st, name, (k_psi2_small<QT, MODE, 2>), Rs, PS_THREADS, smem, rows, s.Mp, p.Ms, s.nt, s.qk, s.QC,
-               p.KS, s.RS, Zt, Ct, w, HP, lam, Wq, ACCp, P2s);
+    RGP_LAUNCH(h, st, name, (k_psi2_small<QT, MODE, 2>), Rs, PS_THREADS, smem, rows, s.M, s.Mp, p.Ms, s.nt, s.qk,
+               s.QC, s.RS, p.bwd, Zt, Ct, w, HP, lam, Wq, ACCp, P2s);
   }
   return 0;
 }
@@ -401,7 +471,7 @@ static int backward(rgp_psi_ctx* h, cudaStream_t st, int64_t N, int M, int Q, co
   pick_grid(s.rc, s.nblocks, h->sm_count, &R, &G);
   if (sp.ok) G = 1;
   const int QC = s.QC, Mp = s.Mp;
-  const int ncta = sp.ok ? Rs * sp.KS : R * G;
+  const int ncta = sp.ok ? Rs * sp.bwd.kslots : R * G;
   const size_t p2_count = sp.ok ? (size_t)Rs * sp.Mp16 * sp.Mp16 : (size_t)s.nblocks * R * 4096;
   const int tn_tiles = s.nt * (2 * QC / 64 > 0 ? (2 * QC + 63) / 64 : 1);
   const int splits = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)64, (int64_t)(2 * h->sm_count / std::max(1, tn_tiles)),
@@ -453,7 +523,7 @@ static int backward(rgp_psi_ctx* h, cudaStream_t st, int64_t N, int M, int Q, co
     Rc = std::min(Rc, R);
     Gc = std::min(Gc, G);
     const int Rr = std::min(Rs, small_grid(h, rows));
-    const int nc = sp.ok ? Rr * sp.KS : Rc * Gc;
+    const int nc = sp.ok ? Rr * sp.bwd.kslots : Rc * Gc;
     RGP_CUDA(cudaMemsetAsync(lam, 0, sizeof(double) * (size_t)Gc * rows * Mp, st));
     RGP_CUDA(cudaMemsetAsync(Wq, 0, sizeof(double) * (size_t)Gc * rows * QC, st));
     RGP_CUDA(cudaMemsetAsync(ACCp, 0, sizeof(double) * (size_t)nc * Mp * QC, st));

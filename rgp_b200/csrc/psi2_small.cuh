@@ -7,19 +7,21 @@
 // red.global.add, and 8 warps (2 per scheduler) cannot hide the DMMA issue latency of the short k loops.  Here ONE
 // CTA of 16 warps holds the whole problem of a row:
 //
-//   Z' [Mp16][Qp + 4] and the FULL symmetric L_n [Mp16][Mp16 + 4] in shared memory (Mp16 = M rounded up to 16,
-//   Qp = Q rounded up to 8);
-//   stage 1   E = H_m + H_m' + sum_q (ws_q Z'_mq) Z'_m'q on the 16 x 16 supertiles of the upper triangle only
-//             (Ms (Ms + 1) / 2 supertiles dealt round-robin to the warps), p = exp(E), Psi2 += p (registers),
-//             L = C p stored with its mirror image;
-//   stage 2   T = L Z' as (16 rows x Qp columns x 1/KS of the k range) jobs dealt round-robin to the warps:
-//             acc[m,q] += ws_q T[m,q], W_q += sum_m Z'_mq T[m,q], lambda_m += row sums of the L fragments;
-//   per row   lambda_n and W_n are complete inside the CTA: written once with plain stores (no atomics, no
-//             block passes), in a fixed order (deterministic).
+//   Z' [Mp16][Qp + 4] in shared memory (Mp16 = M rounded up to 16, Qp = Q rounded up to 8) and the UPPER TRIANGLE
+//   of the symmetric L_n as packed 16 x 16 supertiles (row stride 20), double-buffered by row parity;
+//   stage 1   E = H_m + H_m' + sum_q (ws_q Z'_mq) Z'_m'q on the supertiles of the upper triangle (8x8 tiles that lie
+//             entirely in the padding are skipped), p = exp(E), Psi2 += p (registers), L = C p -> shared;
+//   stage 2   T = L Z' as jobs (16-row strip x Qp columns x a range of k-steps); a job reads L[strip][k] from the
+//             supertile (strip, k) directly or from (k, strip) transposed - both fragment patterns are conflict
+//             free at stride 20 - and folds  acc[m,q] += ws_q T[m,q],  W_q += sum_m Z'_mq T[m,q],
+//             lambda_m += row sums of its L fragments;
+//   per row   ONE CTA barrier (L_n complete); the partials of row n are combined after the barrier of row n + 1 and
+//             lambda_n, W_n are written once with plain stores, in a fixed order (deterministic, no atomics).
 //
-// DMMAs per row at M = 100, Q = 20: 560 + 1092 against 680 + 2048 in the block kernels.  The per-row vectors
-// (ws[Qp], H[Mp16]) arrive by TMA bulk copies into a two-slot ring (SmallRowStage), as in the block kernels.
-// Two CTA barriers per row (L complete / L consumed): L is single-buffered, 16 warps overlap the phases' tails.
+// Which warp computes which supertiles and jobs is a small table made on the host (SmallSched, fast_path.cuh): it
+// balances the FP64-pipe load per SM sub-partition (warp w runs on sub-partition w % 4).
+// The per-row vectors (ws[Qp], H[Mp16]) arrive by TMA bulk copies into a two-slot ring (SmallRowStage), as in the
+// block kernels.  The forward-only kernel needs a barrier only when a ring slot is recycled (every PS_VR rows).
 #pragma once
 #include "psi2_kernels.cuh"
 
@@ -29,15 +31,26 @@ namespace fast {
 constexpr int PS_THREADS = 512;
 constexpr int PS_WARPS = PS_THREADS / 32;
 constexpr int PS_MS_MAX = 7;      // 16-row super rows: M <= 112
-constexpr int PS_S1 = 2;          // supertiles per warp: 7 * 8 / 2 = 28 <= 2 * 16
+constexpr int PS_S1 = 2;          // supertile slots per warp (28 supertiles <= 2 * 16)
 constexpr int PS_VR = 4;          // rows per TMA batch
+constexpr int PS_JOBS = 32;       // job list length
+constexpr int PS_ST = 320;        // doubles per packed supertile: 16 rows x stride 20
 constexpr int PS_QT_MAX = 6;
 
-// shared-memory size in bytes (host + device agree through this one function)
+struct SmallSched {
+  signed char ns[PS_WARPS];            // supertiles of warp w ...
+  signed char su[PS_WARPS][PS_S1];     // ... and their indices in the row-major enumeration of the upper triangle
+  signed char nj[PS_WARPS];            // jobs of warp w ...
+  signed char jw[PS_WARPS][2];         // ... and their indices into the job list
+  signed char njobs, kslots;           // job list length; ACCp slots per CTA (largest number of k ranges of a strip)
+  signed char jsp[PS_JOBS], jkb[PS_JOBS], jke[PS_JOBS], jslot[PS_JOBS];   // strip, k-step range [kb, ke), ACCp slot
+};
+
+// shared-memory size in doubles (host and device agree through this one function)
 __host__ __device__ constexpr int small_smem_doubles(int Ms, int QT, bool bwd) {
   const int Mp16 = 16 * Ms, Qp = 8 * QT;
   int d = Mp16 * (Qp + 4) + 2 * PS_VR * (Qp + Mp16) + 258;
-  if (bwd) d += 32 * Qp + 4 * Mp16 + Mp16 * (Mp16 + 4);
+  if (bwd) d += 2 * PS_JOBS * Qp + 2 * PS_JOBS * 16 + 2 * (Ms * (Ms + 1) / 2) * PS_ST;
   return d;
 }
 
@@ -93,27 +106,31 @@ struct SmallRowStage {
   }
 };
 
+// index of supertile (lo, hi), lo <= hi, in the row-major enumeration of the upper triangle
+RGP_DEVINL int st_index(int lo, int hi, int Ms) { return lo * Ms - lo * (lo - 1) / 2 + (hi - lo); }
+
 // MODE 0: forward only (Psi2 partials), 1: backward only, 2: backward + Psi2 partials (fused SVI pass).
 // Outputs (strides of the block path, so the small GEMMs and combiners downstream are shared):
-//   lam [rc][Mp]   Wq [rc][QC]            complete per row, plain stores
-//   ACCp[cta * KS + kr][Mp][QC]           sum_n ws (L_n Z') over this CTA's rows and the k range kr (plain stores)
-//   P2s [cta][Mp16][Mp16]                 sum_n p over this CTA's rows (MODE 0 / 2), full symmetric
+//   lam [rc][Mp]   Wq [rc][QC]                 complete per row, plain stores
+//   ACCp[cta * kslots + slot][Mp][QC]          sum_n ws (L_n Z') over this CTA's rows and one k range (plain stores
+//                                              where a job exists; the buffer is zeroed before the launch)
+//   P2s [cta][Mp16][Mp16]                      sum_n p over this CTA's rows (MODE 0 / 2), full symmetric
 template <int QT, int MODE, int JMAX>
 __global__ void __launch_bounds__(PS_THREADS, 1)
-k_psi2_small(int64_t rc, int Mp, int Ms, int nt, int qk, int QC, int KS, int RSz,
+k_psi2_small(int64_t rc, int M, int Mp, int Ms, int nt, int qk, int QC, int RSz, const __grid_constant__ SmallSched sc,
              const double* __restrict__ Zt, const double* __restrict__ Ct, const double* __restrict__ wrow,
              const double* __restrict__ HP, double* __restrict__ lam, double* __restrict__ Wq,
              double* __restrict__ ACCp, double* __restrict__ P2s) {
   constexpr int Qp = 8 * QT, RS = Qp + 4;
   constexpr bool BWD = MODE != 0, FWD = MODE != 1;
-  const int Mp16 = 16 * Ms, RSL = Mp16 + 4, VB = Qp + Mp16;
+  const int Mp16 = 16 * Ms, VB = Qp + Mp16, M8 = (M + 7) & ~7, NS = Ms * (Ms + 1) / 2;
   extern __shared__ __align__(16) double smem[];
   double* sZ = smem;                         // [Mp16][RS]
   double* sV = sZ + Mp16 * RS;               // row-vector ring: 2 slots x PS_VR rows x VB
   double* sT = sV + 2 * PS_VR * VB;          // exp table (256) + 2 mbarriers
-  double* sW = sT + 258;                     // [jobs <= 32][Qp]   W partials of the row
-  double* sLam = sW + 32 * Qp;               // [KS <= 4][Mp16]    lambda partials of the row
-  double* sL = sLam + 4 * Mp16;              // [Mp16][RSL]        L_n, full symmetric
+  double* sW = sT + 258;                     // [2][PS_JOBS][Qp]   W partials per job, by row parity
+  double* sLam = sW + 2 * PS_JOBS * Qp;      // [2][PS_JOBS][16]   lambda partials per job
+  double* sL = sLam + 2 * PS_JOBS * 16;      // [2][NS][PS_ST]     packed supertiles of L_n, by row parity
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, t = lane & 3;
   const int R = gridDim.x;
@@ -134,21 +151,16 @@ k_psi2_small(int64_t rc, int Mp, int Ms, int nt, int qk, int QC, int KS, int RSz
     sZ[m * RS + c] = Zt[(size_t)m * RSz + c];
   }
 
-  // this warp's supertiles of the upper triangle
-  const int NS = Ms * (Ms + 1) / 2;
-  int si[PS_S1], sj[PS_S1];
-  int ns = 0;
+  // this warp's supertiles
+  const int ns = sc.ns[wid];
+  int su[PS_S1], si[PS_S1], sj[PS_S1];
 #pragma unroll
   for (int s = 0; s < PS_S1; ++s) {
-    const int u = wid + PS_WARPS * s;
-    si[s] = sj[s] = 0;
-    if (u < NS) {
-      int i = 0, rem = u;
-      while (rem >= Ms - i) { rem -= Ms - i; ++i; }
-      si[s] = i;
-      sj[s] = i + rem;
-      ns = s + 1;
-    }
+    su[s] = s < ns ? sc.su[wid][s] : 0;
+    int i = 0, rem = su[s];
+    while (rem >= Ms - i) { rem -= Ms - i; ++i; }
+    si[s] = i;
+    sj[s] = i + rem;
   }
   double creg[PS_S1][2][2][2], pacc[PS_S1][2][2][2];
 #pragma unroll
@@ -168,8 +180,8 @@ k_psi2_small(int64_t rc, int Mp, int Ms, int nt, int qk, int QC, int KS, int RSz
           creg[s][i][j][1] = c2.y;
         }
       }
-  // stage-2 jobs: job jb = (k range kr, 16-row strip sp)
-  const int njobs = Ms * KS, kper = 4 * Ms / KS;       // k-steps per job
+  // this warp's stage-2 jobs
+  const int nj = BWD ? sc.nj[wid] : 0;
   double accZ[JMAX][2][QT][2];
 #pragma unroll
   for (int jj = 0; jj < JMAX; ++jj)
@@ -178,19 +190,41 @@ k_psi2_small(int64_t rc, int Mp, int Ms, int nt, int qk, int QC, int KS, int RSz
 #pragma unroll
       for (int j = 0; j < QT; ++j) accZ[jj][i][j][0] = accZ[jj][i][j][1] = 0.0;
 
+  // lambda_n, W_n of a finished row: fixed-order sums of the per-job partials
+  auto flush_row = [&](int64_t n) {
+    const int par = (int)(n & 1);
+    const int njobs = sc.njobs;
+    if (tid < Qp) {
+      const double* p = sW + par * PS_JOBS * Qp + tid;
+      double s = 0.0;
+      for (int jb = 0; jb < njobs; ++jb) s += p[jb * Qp];
+      Wq[n * QC + tid] = s;
+    } else if (tid >= 64 && tid < 64 + Mp16) {
+      const int m = tid - 64, strip = m >> 4;
+      const double* p = sLam + par * PS_JOBS * 16 + (m & 15);
+      double s = 0.0;
+      for (int jb = 0; jb < njobs; ++jb)
+        if (sc.jsp[jb] == strip) s += p[jb * 16];
+      lam[n * Mp + m] = s;
+    }
+  };
+
   rv.begin(r0, r1, tid);
+  if constexpr (!BWD)
+    if (tid == 0) rv.refill(0);                       // forward only: both slots in flight from the start
   __syncthreads();
 
   for (int64_t n = r0; n < r1; ++n) {
-    if (tid == 0) rv.refill(n - r0);                 // every thread is past the last barrier of row n - 1
     const double* v = rv.row(n - r0);
     const double* H = v + Qp;
+    double* Lb = sL + (n & 1) * NS * PS_ST;
     // ------------------------------------------------------------------ stage 1 + exp (+ L)
 #pragma unroll
     for (int s = 0; s < PS_S1; ++s) {
       if (s < ns) {
         double acc[2][2][2];
         const int mi = 16 * si[s] + g, mj = 16 * sj[s] + 2 * t;
+        const bool vi1 = 16 * si[s] + 8 < M8, vj1 = 16 * sj[s] + 8 < M8;     // second tile row / column not all padding
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           const double hi = H[mi + 8 * i];
@@ -203,67 +237,91 @@ k_psi2_small(int64_t rc, int Mp, int Ms, int nt, int qk, int QC, int KS, int RSz
         }
         const double* pa = sZ + (16 * si[s] + g) * RS + t;
         const double* pb = sZ + (16 * sj[s] + g) * RS + t;
+        if (vi1 && vj1) {
 #pragma unroll 2
-        for (int k0 = 0; k0 < qk; k0 += 4) {
-          const double wv = v[k0 + t];
-          const double a0 = pa[k0] * wv, a1 = pa[8 * RS + k0] * wv;
-          const double b0 = pb[k0], b1 = pb[8 * RS + k0];
-          dmma(acc[0][0][0], acc[0][0][1], a0, b0);
-          dmma(acc[0][1][0], acc[0][1][1], a0, b1);
-          dmma(acc[1][0][0], acc[1][0][1], a1, b0);
-          dmma(acc[1][1][0], acc[1][1][1], a1, b1);
+          for (int k0 = 0; k0 < qk; k0 += 4) {
+            const double wv = v[k0 + t];
+            const double a0 = pa[k0] * wv, a1 = pa[8 * RS + k0] * wv;
+            const double b0 = pb[k0], b1 = pb[8 * RS + k0];
+            dmma(acc[0][0][0], acc[0][0][1], a0, b0);
+            dmma(acc[0][1][0], acc[0][1][1], a0, b1);
+            dmma(acc[1][0][0], acc[1][0][1], a1, b0);
+            dmma(acc[1][1][0], acc[1][1][1], a1, b1);
+          }
+        } else {
+          for (int k0 = 0; k0 < qk; k0 += 4) {
+            const double wv = v[k0 + t];
+            const double a0 = pa[k0] * wv, a1 = pa[8 * RS + k0] * wv;
+            const double b0 = pb[k0], b1 = pb[8 * RS + k0];
+            dmma(acc[0][0][0], acc[0][0][1], a0, b0);
+            if (vj1) dmma(acc[0][1][0], acc[0][1][1], a0, b1);
+            if (vi1) dmma(acc[1][0][0], acc[1][0][1], a1, b0);
+          }
         }
-        const bool offd = si[s] != sj[s];
 #pragma unroll
         for (int i = 0; i < 2; ++i)
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
-            const double p0 = exp_tab(acc[i][j][0], sT), p1 = exp_tab(acc[i][j][1], sT);
-            if constexpr (FWD) {
-              pacc[s][i][j][0] += p0;
-              pacc[s][i][j][1] += p1;
-            }
-            if constexpr (BWD) {
-              const double l0 = creg[s][i][j][0] * p0, l1 = creg[s][i][j][1] * p1;
-              const int m = mi + 8 * i, mp = mj + 8 * j;
-              *reinterpret_cast<double2*>(sL + m * RSL + mp) = make_double2(l0, l1);
-              if (offd) {
-                sL[mp * RSL + m] = l0;
-                sL[(mp + 1) * RSL + m] = l1;
+            if ((i == 0 || vi1) && (j == 0 || vj1)) {
+              const double p0 = exp_tab(acc[i][j][0], sT), p1 = exp_tab(acc[i][j][1], sT);
+              if constexpr (FWD) {
+                pacc[s][i][j][0] += p0;
+                pacc[s][i][j][1] += p1;
               }
+              if constexpr (BWD)
+                *reinterpret_cast<double2*>(Lb + su[s] * PS_ST + (8 * i + g) * 20 + 8 * j + 2 * t) =
+                    make_double2(creg[s][i][j][0] * p0, creg[s][i][j][1] * p1);
             }
           }
       }
     }
-    __syncthreads();                                  // BWD: L_n complete.  forward only: row n's vectors consumed
-    if constexpr (BWD) {
+    if constexpr (!BWD) {
+      // the ring slot of this batch is recycled once every thread has consumed its last row
+      const int64_t idx = n - r0;
+      if (idx % PS_VR == PS_VR - 1 && n + 1 < r1) {
+        __syncthreads();
+        if (tid == 0) rv.refill(idx + 1);
+      }
+    } else {
+      __syncthreads();                                // L_n complete; every thread has finished row n - 1
+      if (tid == 0) rv.refill(n - r0);
+      if (n > r0) flush_row(n - 1);
       // ---------------------------------------------------------------- stage 2: T = L Z' by jobs
+      const int par = (int)(n & 1);
 #pragma unroll
       for (int jj = 0; jj < JMAX; ++jj) {
-        const int jb = wid + PS_WARPS * jj;
-        if (jb < njobs) {
-          const int kr = jb / Ms, sp = jb - kr * Ms;
+        if (jj < nj) {
+          const int jb = sc.jw[wid][jj];
+          const int sp = sc.jsp[jb], kb = sc.jkb[jb], ke = sc.jke[jb];
+          const bool two = 16 * sp + 8 < M8;          // the strip's second 8 rows are not all padding
           double T[2][QT][2];
 #pragma unroll
           for (int i = 0; i < 2; ++i)
 #pragma unroll
             for (int j = 0; j < QT; ++j) T[i][j][0] = T[i][j][1] = 0.0;
           double ls0 = 0.0, ls1 = 0.0;
-          const double* pa = sL + (16 * sp + g) * RSL + t;
-          const double* pb = sZ + t * RS + g;
-          const int kb = 4 * kr * kper, ke = kb + 4 * kper;
-#pragma unroll 2
-          for (int k0 = kb; k0 < ke; k0 += 4) {
-            const double a0 = pa[k0], a1 = pa[8 * RSL + k0];
-            double bq[QT];
+          const double* pbz = sZ + t * RS + g;
+          for (int sk = kb >> 2; 4 * sk < ke; ++sk) {
+            // L[strip sp][k in supertile column sk]: from supertile (sp, sk) as stored, or from (sk, sp) transposed
+            const bool tr = sk < sp;
+            const double* pa = Lb + (tr ? st_index(sk, sp, Ms) : st_index(sp, sk, Ms)) * PS_ST + (tr ? t * 20 + g : g * 20 + t);
+            const int kst = tr ? 80 : 4, ioff = tr ? 8 : 160;
+            const int k0 = kb > 4 * sk ? kb : 4 * sk, k1 = ke < 4 * sk + 4 ? ke : 4 * sk + 4;
+            for (int ks = k0; ks < k1; ++ks) {
+              const int kk = ks - 4 * sk;
+              const double a0 = pa[kk * kst];
+              const double a1 = two ? pa[kk * kst + ioff] : 0.0;
+              double bq[QT];
 #pragma unroll
-            for (int j = 0; j < QT; ++j) bq[j] = pb[k0 * RS + 8 * j];
-            ls0 += a0;
-            ls1 += a1;
+              for (int j = 0; j < QT; ++j) bq[j] = pbz[ks * 4 * RS + 8 * j];
+              ls0 += a0;
+              ls1 += a1;
 #pragma unroll
-            for (int j = 0; j < QT; ++j) {
-              dmma(T[0][j][0], T[0][j][1], a0, bq[j]);
-              dmma(T[1][j][0], T[1][j][1], a1, bq[j]);
+              for (int j = 0; j < QT; ++j) dmma(T[0][j][0], T[0][j][1], a0, bq[j]);
+              if (two) {
+#pragma unroll
+                for (int j = 0; j < QT; ++j) dmma(T[1][j][0], T[1][j][1], a1, bq[j]);
+              }
             }
           }
           // folds: acc += ws T ; W partial = sum over this strip's rows of Z' T
@@ -284,6 +342,7 @@ k_psi2_small(int64_t rc, int Mp, int Ms, int nt, int qk, int QC, int KS, int RSz
             wp[2 * j] = w0;
             wp[2 * j + 1] = w1;
           }
+          double* myW = sW + (par * PS_JOBS + jb) * Qp;
 #pragma unroll
           for (int c0 = 0; c0 < 2 * QT; c0 += 8) {
             double v8[8];
@@ -291,39 +350,30 @@ k_psi2_small(int64_t rc, int Mp, int Ms, int nt, int qk, int QC, int KS, int RSz
             for (int c = 0; c < 8; ++c) v8[c] = (c0 + c < 2 * QT) ? wp[(c0 + c < 2 * QT) ? c0 + c : 0] : 0.0;
             const double tot = reduce8_over_g(v8, lane);
             const int cc = c0 + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-            if (cc < 2 * QT) sW[jb * Qp + 8 * (cc >> 1) + 2 * t + (cc & 1)] = tot;
+            if (cc < 2 * QT) myW[8 * (cc >> 1) + 2 * t + (cc & 1)] = tot;
           }
           ls0 += __shfl_xor_sync(0xffffffffu, ls0, 1);
           ls0 += __shfl_xor_sync(0xffffffffu, ls0, 2);
           ls1 += __shfl_xor_sync(0xffffffffu, ls1, 1);
           ls1 += __shfl_xor_sync(0xffffffffu, ls1, 2);
           if (t == 0) {
-            sLam[kr * Mp16 + 16 * sp + g] = ls0;
-            sLam[kr * Mp16 + 16 * sp + 8 + g] = ls1;
+            sLam[(par * PS_JOBS + jb) * 16 + g] = ls0;
+            sLam[(par * PS_JOBS + jb) * 16 + 8 + g] = ls1;
           }
         }
-      }
-      __syncthreads();                                // L_n consumed; partials of row n complete
-      if (tid < Qp) {
-        double s = 0.0;
-        for (int jb = 0; jb < njobs; ++jb) s += sW[jb * Qp + tid];
-        Wq[n * QC + tid] = s;
-      } else if (tid >= 64 && tid < 64 + Mp16) {
-        const int m = tid - 64;
-        double s = 0.0;
-        for (int kr = 0; kr < KS; ++kr) s += sLam[kr * Mp16 + m];
-        lam[n * Mp + m] = s;
       }
     }
   }
 
   if constexpr (BWD) {
+    __syncthreads();                                  // partials of the last row complete
+    if (r1 > r0) flush_row(r1 - 1);
 #pragma unroll
     for (int jj = 0; jj < JMAX; ++jj) {
-      const int jb = wid + PS_WARPS * jj;
-      if (jb < njobs) {
-        const int kr = jb / Ms, sp = jb - kr * Ms;
-        double* out = ACCp + (size_t)(blockIdx.x * KS + kr) * Mp * QC;
+      if (jj < nj) {
+        const int jb = sc.jw[wid][jj];
+        const int sp = sc.jsp[jb];
+        double* out = ACCp + (size_t)(blockIdx.x * sc.kslots + sc.jslot[jb]) * Mp * QC;
 #pragma unroll
         for (int i = 0; i < 2; ++i)
 #pragma unroll

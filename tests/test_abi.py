@@ -31,7 +31,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), "missing export " + n
     assert sorted(_lib.SIGNATURES) == names           # the ctypes table covers the header exactly
-    assert lib.rgp_psi_abi_version() == 3
+    assert lib.rgp_psi_abi_version() == 4
 
 
 def test_shared_object_contains_sm100a_code_only():

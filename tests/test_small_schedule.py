@@ -1,0 +1,152 @@
+"""CPU tests of the small-inducing-set kernels' work table (rgp_psi_small_schedule, pure host code in the C-ABI
+library) and of the data flow it drives.
+
+`emulate` is a numpy model of psi2_small.cuh at the level of warps and k-steps: supertiles of the upper triangle
+packed as the kernel stores them (16 x 16, row stride 20), stage-2 jobs reading L[strip][k] either from supertile
+(strip, k) directly or from (k, strip) transposed, tiles that lie in the padding skipped, k-steps trimmed to
+ceil(M / 4), per-job lambda / W partials combined in job order, accumulators written to (k slot, strip) slices.
+It is test infrastructure (it documents and guards the index algebra); the product never runs it."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from rgp_b200._lib import load
+
+
+def schedule(M, Q, ks=0, backward=1):
+    buf = C.create_string_buffer(226)
+    n = load().rgp_psi_small_schedule(M, Q, ks, backward, buf, 226)
+    if n < 0:
+        return None
+    a = np.frombuffer(buf.raw, dtype=np.int8).astype(int)
+    return dict(ns=a[0:16], su=a[16:48].reshape(16, 2), nj=a[48:64], jw=a[64:96].reshape(16, 2), njobs=a[96],
+                kslots=a[97], jsp=a[98:130], jkb=a[130:162], jke=a[162:194], jslot=a[194:226])
+
+
+SHAPES = [(1, 1), (7, 3), (16, 8), (17, 9), (33, 3), (48, 24), (50, 20), (64, 16), (81, 7), (97, 17), (100, 10),
+          (100, 20), (104, 24), (112, 24)]
+
+
+@pytest.mark.parametrize("ks", [0, 1, 2, 4])
+@pytest.mark.parametrize("M,Q", SHAPES)
+def test_schedule_covers_every_supertile_and_k_step_once(M, Q, ks):
+    Ms = (M + 15) // 16
+    NS = Ms * (Ms + 1) // 2
+    for backward in (0, 1):
+        sc = schedule(M, Q, ks, backward)
+        assert sc is not None
+        tiles = sorted(int(sc["su"][w, s]) for w in range(16) for s in range(sc["ns"][w]))
+        assert tiles == list(range(NS))                       # every supertile exactly once
+        assert sc["ns"].max() <= 2
+        if not backward:
+            assert sc["njobs"] == 0 and sc["nj"].sum() == 0
+            continue
+        jobs = sorted(int(sc["jw"][w, j]) for w in range(16) for j in range(sc["nj"][w]))
+        assert jobs == list(range(sc["njobs"]))               # every job on exactly one warp
+        ksteps = (M + 3) // 4
+        for sp in range(Ms):
+            cover = np.zeros(ksteps, int)
+            slots = []
+            for j in range(sc["njobs"]):
+                if sc["jsp"][j] == sp:
+                    cover[sc["jkb"][j]:sc["jke"][j]] += 1
+                    slots.append(int(sc["jslot"][j]))
+            assert (cover == 1).all(), (sp, cover)             # the strip's k-steps exactly once
+            assert sorted(slots) == list(range(len(slots))) and len(slots) <= sc["kslots"]
+        # FP64-pipe load per SM sub-partition (warp w issues on w % 4): DMMAs within 25 % of the mean
+        M8 = (M + 7) // 8 * 8
+        load4 = np.zeros(4)
+        for w in range(16):
+            for s in range(sc["ns"][w]):
+                u = int(sc["su"][w, s]); i = 0
+                while u >= Ms - i:
+                    u -= Ms - i; i += 1
+                j = i + u
+                vi, vj = (2 if 16 * i + 8 < M8 else 1), (2 if 16 * j + 8 < M8 else 1)
+                load4[w % 4] += ((4 if vi == 2 else 1) if i == j else vi * vj) * ((Q + 3) // 4)
+            for jj in range(sc["nj"][w]):
+                j = sc["jw"][w, jj]
+                load4[w % 4] += (sc["jke"][j] - sc["jkb"][j]) * (2 if 16 * sc["jsp"][j] + 8 < M8 else 1) * ((Q + 7) // 8)
+        if Ms >= 4:
+            assert load4.max() <= 1.25 * load4.mean(), load4
+
+
+def test_large_shapes_are_left_to_the_block_kernels():
+    assert schedule(113, 20) is None and schedule(100, 25) is None and schedule(512, 64) is None
+    assert b"block kernels" in load().rgp_psi_last_error()
+
+
+def emulate(M, Q, ks, N, seed=0):
+    rng = np.random.default_rng(seed)
+    sc = schedule(M, Q, ks, 1)
+    Ms = (M + 15) // 16; Mp16 = 16 * Ms; Qp = (Q + 7) // 8 * 8; qk = (Q + 3) // 4 * 4; M8 = (M + 7) // 8 * 8
+    Z = np.zeros((Mp16, Qp)); Z[:M, :Q] = rng.normal(size=(M, Q))
+    Cm = np.zeros((Mp16, Mp16)); c = rng.normal(size=(M, M)); Cm[:M, :M] = (c + c.T) / 2
+    H = np.full((N, Mp16), -1e300); H[:, :M] = -rng.random((N, M))
+    ws = np.zeros((N, Qp)); ws[:, :Q] = rng.random((N, Q)) * 0.1
+    ref = dict(lam=np.zeros((N, M)), W=np.zeros((N, Q)), acc=np.zeros((M, Q)), P=np.zeros((M, M)))
+    for n in range(N):
+        E = H[n][:, None] + H[n][None, :] + (Z * ws[n]) @ Z.T
+        P = np.exp(E); L = Cm * P; T = L @ Z
+        ref["P"] += P[:M, :M]; ref["lam"][n] = L.sum(1)[:M]; ref["W"][n] = (Z * T).sum(0)[:Q]; ref["acc"] += (ws[n] * T)[:M, :Q]
+
+    def st(u):
+        i = 0
+        while u >= Ms - i:
+            u -= Ms - i; i += 1
+        return i, i + u
+    idx = lambda lo, hi: lo * Ms - lo * (lo - 1) // 2 + (hi - lo)
+    NS = Ms * (Ms + 1) // 2
+    lam = np.zeros((N, Mp16)); W = np.zeros((N, Qp))
+    ACC = np.zeros((sc["kslots"], Mp16, Qp)); P2 = np.zeros((Mp16, Mp16))
+    for n in range(N):
+        Lb = np.full((NS, 16, 20), np.nan)                  # packed supertiles; NaN = never written
+        for w in range(16):
+            for s in range(sc["ns"][w]):
+                u = int(sc["su"][w, s]); si, sj = st(u)
+                vi1, vj1 = 16 * si + 8 < M8, 16 * sj + 8 < M8
+                for i in range(2):
+                    for j in range(2):
+                        if (i and not vi1) or (j and not vj1):
+                            continue
+                        r = slice(16 * si + 8 * i, 16 * si + 8 * i + 8); cc = slice(16 * sj + 8 * j, 16 * sj + 8 * j + 8)
+                        E = H[n, r][:, None] + H[n, cc][None, :] + (Z[r, :qk] * ws[n, :qk]) @ Z[cc, :qk].T
+                        p = np.exp(E)
+                        P2[r, cc] += p
+                        if si != sj:
+                            P2[cc, r] += p.T
+                        Lb[u, 8 * i:8 * i + 8, 8 * j:8 * j + 8] = Cm[r, cc] * p
+        sW = np.zeros((sc["njobs"], Qp)); sLam = np.zeros((sc["njobs"], 16))
+        for w in range(16):
+            for jj in range(sc["nj"][w]):
+                jb = int(sc["jw"][w, jj]); sp, kb, ke = int(sc["jsp"][jb]), int(sc["jkb"][jb]), int(sc["jke"][jb])
+                two = 16 * sp + 8 < M8
+                T = np.zeros((16, Qp)); ls = np.zeros(16)
+                for k in range(kb, ke):                      # k-step: 4 columns of L
+                    sk, kk = k // 4, (k % 4) * 4
+                    if sk < sp:
+                        A = Lb[idx(sk, sp), kk:kk + 4, :16].T        # transposed read of supertile (sk, sp)
+                    else:
+                        A = Lb[idx(sp, sk), :16, kk:kk + 4]
+                    A = A.copy()
+                    if not two:
+                        A[8:] = 0.0
+                    assert not np.isnan(A).any(), (M, sp, k)        # only tiles that stage 1 wrote are read
+                    T += A @ Z[4 * k:4 * k + 4]; ls += A.sum(1)
+                ACC[sc["jslot"][jb], 16 * sp:16 * sp + 16] += ws[n] * T
+                sW[jb] = (Z[16 * sp:16 * sp + 16] * T).sum(0); sLam[jb] = ls
+        W[n] = sW.sum(0)
+        for m in range(Mp16):
+            lam[n, m] = sum(sLam[j, m & 15] for j in range(sc["njobs"]) if sc["jsp"][j] == m >> 4)
+    err = lambda a, b: np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+    return (err(lam[:, :M], ref["lam"]), err(W[:, :Q], ref["W"]), err(ACC.sum(0)[:M, :Q], ref["acc"]),
+            err(P2[:M, :M], ref["P"]), np.abs(lam[:, M:]).max() if Mp16 > M else 0.0)
+
+
+@pytest.mark.parametrize("M,Q,ks", [(1, 1, 0), (17, 9, 2), (33, 3, 1), (50, 20, 4), (97, 17, 0), (100, 20, 0),
+                                    (100, 20, 4), (104, 24, 1), (112, 24, 2)])
+def test_emulated_data_flow_matches_the_definitions(M, Q, ks):
+    e = emulate(M, Q, ks, N=2, seed=M + Q)
+    assert max(e[:4]) < 1e-13, e
+    assert e[4] == 0.0                                       # lambda of padded inducing points is exactly zero
