@@ -252,23 +252,27 @@ static inline int small_valid_tiles(int si, int sj, int M8) {
   const int vi = 16 * si + 8 < M8 ? 2 : 1, vj = 16 * sj + 8 < M8 ? 2 : 1;
   return si == sj ? (vi == 2 ? 4 : 1) : vi * vj;     // 8x8 tiles the kernel computes on this supertile
 }
+static inline int small_col_ksteps(int sk, int M8) { return 16 * sk + 8 < M8 ? 4 : 2; }   // k-steps of a supertile column
 static inline double small_dmma_per_row(int M, int Ms, int QT, int qk) {
   const int M8 = (M + 7) & ~7;
   double s1 = 0, s2 = 0;
+  int ksteps = 0;
+  for (int sk = 0; sk < Ms; ++sk) ksteps += small_col_ksteps(sk, M8);
   for (int i = 0; i < Ms; ++i)
     for (int j = i; j < Ms; ++j) s1 += small_valid_tiles(i, j, M8) * (qk / 4);
-  for (int sp = 0; sp < Ms; ++sp) s2 += (16 * sp + 8 < M8 ? 2 : 1) * QT * ((M + 3) / 4);
+  for (int sp = 0; sp < Ms; ++sp) s2 += (16 * sp + 8 < M8 ? 2 : 1) * QT * ksteps;
   return 2 * s1 + s2;
 }
 
 // The work table of the small kernels.  Items: the supertiles of the upper triangle (stage 1 + exp) and, for the
-// backward pass, jobs = (16-row strip, 1 / KS of the k-steps).  Warp w issues on SM sub-partition w % 4, so the
-// items are dealt greedily (largest first) to the least loaded sub-partition, then to its least loaded warp with
-// a free slot.  Costs are FP64-pipe cycles: 16 per DMMA plus the scalar epilogue / fold work.
+// backward pass, jobs = (16-row strip, a contiguous group of supertile columns holding ~1 / KS of the k-steps).
+// Warp w issues on SM sub-partition w % 4, so the items are dealt greedily (largest first) to the least loaded
+// sub-partition, then to its least loaded warp with a free slot.  Costs are FP64-pipe cycles: 16 per DMMA plus
+// the scalar epilogue / fold work.
 static void small_schedule(int M, int Ms, int QT, int qk, int KS, int JMAX, bool bwd, SmallSched* sc) {
   memset(sc, 0, sizeof(*sc));
-  const int M8 = (M + 7) & ~7, ksteps = (M + 3) / 4;
-  struct Item { double cost; int kind, a, b, c, d; };   // kind 0: supertile index a; kind 1: job (sp a, kb b, ke c, slot d)
+  const int M8 = (M + 7) & ~7;
+  struct Item { double cost; int kind, a, b, c, d; };   // kind 0: supertile index a; kind 1: job (strip a, columns [b, c), slot d)
   std::vector<Item> items;
   int u = 0;
   for (int i = 0; i < Ms; ++i)
@@ -277,19 +281,31 @@ static void small_schedule(int M, int Ms, int QT, int qk, int KS, int JMAX, bool
       items.push_back({tiles * ((qk / 4) * 16.0 + 45.0) + 30.0, 0, u, 0, 0, 0});
     }
   int kslots = 1;
-  if (bwd)
+  if (bwd) {
+    // column groups: cut where the running k-step count is nearest to i / KS of the total
+    int cum[PS_MS_MAX + 1] = {0};
+    for (int sk = 0; sk < Ms; ++sk) cum[sk + 1] = cum[sk] + small_col_ksteps(sk, M8);
+    int cut[5] = {0, Ms, Ms, Ms, Ms};
+    for (int i = 1; i < KS; ++i) {
+      int best = cut[i - 1];
+      for (int c = cut[i - 1]; c <= Ms; ++c)
+        if (std::abs(cum[c] * KS - cum[Ms] * i) < std::abs(cum[best] * KS - cum[Ms] * i)) best = c;
+      cut[i] = best;
+    }
+    cut[KS] = Ms;
     for (int sp = 0; sp < Ms; ++sp) {
-      const int last = std::min(ksteps, 4 * Ms);
       int slot = 0;
       for (int i = 0; i < KS; ++i) {
-        const int kb = last * i / KS, ke = last * (i + 1) / KS;
+        const int kb = cut[i], ke = cut[i + 1];
         if (ke <= kb) continue;
         const int rowsets = 16 * sp + 8 < M8 ? 2 : 1;
-        items.push_back({(ke - kb) * (rowsets * QT * 16.0 + 6.0) + 90.0 + 14.0 * QT, 1, sp, kb, ke, slot});
+        items.push_back({(cum[ke] - cum[kb]) * (rowsets * QT * 16.0 + 4.0) + (ke - kb) * 12.0 + 80.0 + 14.0 * QT, 1, sp, kb,
+                         ke, slot});
         ++slot;
       }
       kslots = std::max(kslots, slot);
     }
+  }
   std::stable_sort(items.begin(), items.end(), [](const Item& x, const Item& y) { return x.cost > y.cost; });
   double wload[PS_WARPS] = {0}, pload[4] = {0};
   int njobs = 0;
@@ -301,7 +317,7 @@ static void small_schedule(int M, int Ms, int QT, int qk, int KS, int JMAX, bool
           (pload[w & 3] < pload[best & 3] + 1e-9 && wload[w] < wload[best] - 1e-9))
         best = w;
     }
-    if (best < 0) best = 0;     // cannot happen: 16 * PS_S1 >= 28 supertiles, 16 * JMAX >= jobs (checked by the caller)
+    if (best < 0) best = 0;     // cannot happen: 16 * PS_S1 >= 28 supertiles, 16 * JMAX >= jobs
     wload[best] += it.cost;
     pload[best & 3] += it.cost;
     if (it.kind == 0) {
@@ -323,7 +339,7 @@ static void small_schedule(int M, int Ms, int QT, int qk, int KS, int JMAX, bool
 static SmallPlan small_plan(const rgp_psi_ctx* h, const Shape& s) {
   SmallPlan p;
   if (h->small_m == 0) return p;
-  const int Ms = (s.M + 15) / 16, QT = (s.Q + 7) / 8;
+  const int Ms = (s.M + 15) / 16, QT = s.Q / 8 + 1;     // stage-2 columns: Q and the ones column, in tiles of 8
   if (Ms > PS_MS_MAX || QT > 3) return p;
   if (h->small_m == 2 && small_dmma_per_row(s.M, Ms, QT, s.qk) > 0.85 * block_dmma_per_row(s, false)) return p;
   p.ok = true;
@@ -344,14 +360,14 @@ static int launch_small_qt(rgp_psi_ctx* h, cudaStream_t st, const Shape& s, cons
   const char* name = MODE == 0 ? "psi2_fwd" : (MODE == 1 ? "psi2_bwd" : "psi2_bwd_fused");
   const int smem = small_smem_doubles(p.Ms, QT, MODE != 0) * 8;
   if constexpr (MODE == 0) {
-    RGP_LAUNCH(h, st, name, (k_psi2_small<QT, 0, 1>), Rs, PS_THREADS, smem, rows, s.M, s.Mp, p.Ms, s.nt, s.qk, s.QC,
-               s.RS, p.fwd, Zt, Ct, w, HP, lam, Wq, ACCp, P2s);
+    RGP_LAUNCH(h, st, name, (k_psi2_small<QT, 0, 1>), Rs, PS_THREADS, smem, rows, s.M, s.Q, s.Mp, p.Ms, s.nt, s.qk,
+               s.QC, s.RS, p.fwd, Zt, Ct, w, HP, lam, Wq, ACCp, P2s);
   } else if (p.JMAX == 1) {
-    RGP_LAUNCH(h, st, name, (k_psi2_small<QT, MODE, 1>), Rs, PS_THREADS, smem, rows, s.M, s.Mp, p.Ms, s.nt, s.qk,
-               s.QC, s.RS, p.bwd, Zt, Ct, w, HP, lam, Wq, ACCp, P2s);
+    RGP_LAUNCH(h, st, name, (k_psi2_small<QT, MODE, 1>), Rs, PS_THREADS, smem, rows, s.M, s.Q, s.Mp, p.Ms, s.nt,
+               s.qk, s.QC, s.RS, p.bwd, Zt, Ct, w, HP, lam, Wq, ACCp, P2s);
   } else {
-    RGP_LAUNCH(h, st, name, (k_psi2_small<QT, MODE, 2>), Rs, PS_THREADS, smem, rows, s.M, s.Mp, p.Ms, s.nt, s.qk,
-               s.QC, s.RS, p.bwd, Zt, Ct, w, HP, lam, Wq, ACCp, P2s);
+    RGP_LAUNCH(h, st, name, (k_psi2_small<QT, MODE, 2>), Rs, PS_THREADS, smem, rows, s.M, s.Q, s.Mp, p.Ms, s.nt,
+               s.qk, s.QC, s.RS, p.bwd, Zt, Ct, w, HP, lam, Wq, ACCp, P2s);
   }
   return 0;
 }

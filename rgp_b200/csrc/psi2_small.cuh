@@ -7,14 +7,15 @@
 // red.global.add, and 8 warps (2 per scheduler) cannot hide the DMMA issue latency of the short k loops.  Here ONE
 // CTA of 16 warps holds the whole problem of a row:
 //
-//   Z' [Mp16][Qp + 4] in shared memory (Mp16 = M rounded up to 16, Qp = Q rounded up to 8) and the UPPER TRIANGLE
-//   of the symmetric L_n as packed 16 x 16 supertiles (row stride 20), double-buffered by row parity;
+//   Z' [Mp16][Qp + 4] in shared memory (Mp16 = M rounded up to 16, Qp = 8 (Q / 8 + 1): at least one spare column,
+//   column Q holds ONES so that T[:, Q] = L 1 = lambda comes out of the stage-2 MMAs for free) and the UPPER
+//   TRIANGLE of the symmetric L_n as packed 16 x 16 supertiles (row stride 20), double-buffered by row parity;
 //   stage 1   E = H_m + H_m' + sum_q (ws_q Z'_mq) Z'_m'q on the supertiles of the upper triangle (8x8 tiles that lie
 //             entirely in the padding are skipped), p = exp(E), Psi2 += p (registers), L = C p -> shared;
-//   stage 2   T = L Z' as jobs (16-row strip x Qp columns x a range of k-steps); a job reads L[strip][k] from the
-//             supertile (strip, k) directly or from (k, strip) transposed - both fragment patterns are conflict
-//             free at stride 20 - and folds  acc[m,q] += ws_q T[m,q],  W_q += sum_m Z'_mq T[m,q],
-//             lambda_m += row sums of its L fragments;
+//   stage 2   T = L Z' as jobs (16-row strip x Qp columns x a range of supertile columns); a job reads L[strip][k]
+//             from the supertile (strip, k) directly or from (k, strip) transposed - both fragment patterns are
+//             conflict free at stride 20, the four k-steps of a supertile column are unrolled with immediate
+//             offsets - and folds  acc[m,q] += ws_q T[m,q],  W_q += sum_m Z'_mq T[m,q],  lambda_m = T[m, Q];
 //   per row   ONE CTA barrier (L_n complete); the partials of row n are combined after the barrier of row n + 1 and
 //             lambda_n, W_n are written once with plain stores, in a fixed order (deterministic, no atomics).
 //
@@ -36,6 +37,7 @@ constexpr int PS_VR = 4;          // rows per TMA batch
 constexpr int PS_JOBS = 32;       // job list length
 constexpr int PS_ST = 320;        // doubles per packed supertile: 16 rows x stride 20
 constexpr int PS_QT_MAX = 6;
+constexpr int PS_LAM = 16 * PS_MS_MAX;   // lambda partials: [parity][k slot <= 4][PS_LAM]
 
 struct SmallSched {
   signed char ns[PS_WARPS];            // supertiles of warp w ...
@@ -43,14 +45,14 @@ struct SmallSched {
   signed char nj[PS_WARPS];            // jobs of warp w ...
   signed char jw[PS_WARPS][2];         // ... and their indices into the job list
   signed char njobs, kslots;           // job list length; ACCp slots per CTA (largest number of k ranges of a strip)
-  signed char jsp[PS_JOBS], jkb[PS_JOBS], jke[PS_JOBS], jslot[PS_JOBS];   // strip, k-step range [kb, ke), ACCp slot
+  signed char jsp[PS_JOBS], jkb[PS_JOBS], jke[PS_JOBS], jslot[PS_JOBS];   // strip, supertile columns [kb, ke), k slot
 };
 
 // shared-memory size in doubles (host and device agree through this one function)
 __host__ __device__ constexpr int small_smem_doubles(int Ms, int QT, bool bwd) {
   const int Mp16 = 16 * Ms, Qp = 8 * QT;
   int d = Mp16 * (Qp + 4) + 2 * PS_VR * (Qp + Mp16) + 258;
-  if (bwd) d += 2 * PS_JOBS * Qp + 2 * PS_JOBS * 16 + 2 * (Ms * (Ms + 1) / 2) * PS_ST;
+  if (bwd) d += 2 * PS_JOBS * Qp + 2 * 4 * PS_LAM + 2 * (Ms * (Ms + 1) / 2) * PS_ST;
   return d;
 }
 
@@ -63,7 +65,7 @@ struct SmallRowStage {
   const double* wrow = nullptr;
   const double* hp = nullptr;
   int64_t htile = 0;          // doubles between two 64-wide tiles of HP
-  int QC = 0, Qp = 0, Mp16 = 0, VB = 0;
+  int QC = 0, Qp = 0, Mp16 = 0, VB = 0;   // the ring slot of a row is [ws (Qp) | H (Mp16)]; min(Qp, QC) of ws are copied
 
   RGP_DEVINL void init_barriers(int tid) {
     if (tid == 0) {
@@ -83,10 +85,10 @@ struct SmallRowStage {
     const int rows = (int)((r1 - n0 < PS_VR) ? r1 - n0 : PS_VR);
     const int slot = (int)(next & 1);
     double* dst = ring + slot * PS_VR * VB;
-    const int h0 = Mp16 < 64 ? Mp16 : 64;
-    mbar_expect_tx(&mbar[slot], (uint32_t)(rows * VB * 8));
+    const int h0 = Mp16 < 64 ? Mp16 : 64, qc = Qp < QC ? Qp : QC;
+    mbar_expect_tx(&mbar[slot], (uint32_t)(rows * (qc + Mp16) * 8));
     for (int w = 0; w < rows; ++w) {
-      bulk_g2s(dst + w * VB, wrow + (n0 + w) * QC, Qp * 8, &mbar[slot]);
+      bulk_g2s(dst + w * VB, wrow + (n0 + w) * QC, qc * 8, &mbar[slot]);
       bulk_g2s(dst + w * VB + Qp, hp + (n0 + w) * 64, h0 * 8, &mbar[slot]);
       if (Mp16 > 64) bulk_g2s(dst + w * VB + Qp + 64, hp + htile + (n0 + w) * 64, (Mp16 - 64) * 8, &mbar[slot]);
     }
@@ -109,6 +111,32 @@ struct SmallRowStage {
 // index of supertile (lo, hi), lo <= hi, in the row-major enumeration of the upper triangle
 RGP_DEVINL int st_index(int lo, int hi, int Ms) { return lo * Ms - lo * (lo - 1) / 2 + (hi - lo); }
 
+// Stage 2 on one supertile column (16 k values = 4 k-steps, or 2 when the column's second half is padding):
+// T[i][j] += L[strip rows 8 i + g][k] Z'[k][8 j ...].  KST / IOFF are the fragment strides of the packed supertile:
+// (4, 160) when it is read as stored, (80, 8) when it is read transposed.  TWO: the strip's second 8 rows exist.
+template <int QT, int KST, int IOFF, bool TWO>
+RGP_DEVINL void small_s2_column(const double* __restrict__ pa, const double* __restrict__ pb, bool four,
+                                double (&T)[2][QT][2]) {
+  constexpr int RS = 8 * QT + 4;
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    if (kk < 2 || four) {
+      const double a0 = pa[kk * KST];
+      double a1 = 0.0;
+      if constexpr (TWO) a1 = pa[kk * KST + IOFF];
+      double bq[QT];
+#pragma unroll
+      for (int j = 0; j < QT; ++j) bq[j] = pb[kk * 4 * RS + 8 * j];
+#pragma unroll
+      for (int j = 0; j < QT; ++j) dmma(T[0][j][0], T[0][j][1], a0, bq[j]);
+      if constexpr (TWO) {
+#pragma unroll
+        for (int j = 0; j < QT; ++j) dmma(T[1][j][0], T[1][j][1], a1, bq[j]);
+      }
+    }
+  }
+}
+
 // MODE 0: forward only (Psi2 partials), 1: backward only, 2: backward + Psi2 partials (fused SVI pass).
 // Outputs (strides of the block path, so the small GEMMs and combiners downstream are shared):
 //   lam [rc][Mp]   Wq [rc][QC]                 complete per row, plain stores
@@ -117,7 +145,8 @@ RGP_DEVINL int st_index(int lo, int hi, int Ms) { return lo * Ms - lo * (lo - 1)
 //   P2s [cta][Mp16][Mp16]                      sum_n p over this CTA's rows (MODE 0 / 2), full symmetric
 template <int QT, int MODE, int JMAX>
 __global__ void __launch_bounds__(PS_THREADS, 1)
-k_psi2_small(int64_t rc, int M, int Mp, int Ms, int nt, int qk, int QC, int RSz, const __grid_constant__ SmallSched sc,
+k_psi2_small(int64_t rc, int M, int Q, int Mp, int Ms, int nt, int qk, int QC, int RSz,
+             const __grid_constant__ SmallSched sc,
              const double* __restrict__ Zt, const double* __restrict__ Ct, const double* __restrict__ wrow,
              const double* __restrict__ HP, double* __restrict__ lam, double* __restrict__ Wq,
              double* __restrict__ ACCp, double* __restrict__ P2s) {
@@ -129,8 +158,8 @@ k_psi2_small(int64_t rc, int M, int Mp, int Ms, int nt, int qk, int QC, int RSz,
   double* sV = sZ + Mp16 * RS;               // row-vector ring: 2 slots x PS_VR rows x VB
   double* sT = sV + 2 * PS_VR * VB;          // exp table (256) + 2 mbarriers
   double* sW = sT + 258;                     // [2][PS_JOBS][Qp]   W partials per job, by row parity
-  double* sLam = sW + 2 * PS_JOBS * Qp;      // [2][PS_JOBS][16]   lambda partials per job
-  double* sL = sLam + 2 * PS_JOBS * 16;      // [2][NS][PS_ST]     packed supertiles of L_n, by row parity
+  double* sLam = sW + 2 * PS_JOBS * Qp;      // [2][4][PS_LAM]     lambda partials per k slot
+  double* sL = sLam + 2 * 4 * PS_LAM;        // [2][NS][PS_ST]     packed supertiles of L_n, by row parity
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, t = lane & 3;
   const int R = gridDim.x;
@@ -148,8 +177,10 @@ k_psi2_small(int64_t rc, int M, int Mp, int Ms, int nt, int qk, int QC, int RSz,
   rv.init_barriers(tid);
   for (int idx = tid; idx < Mp16 * Qp; idx += PS_THREADS) {
     const int m = idx / Qp, c = idx - m * Qp;
-    sZ[m * RS + c] = Zt[(size_t)m * RSz + c];
+    sZ[m * RS + c] = c < Q ? Zt[(size_t)m * RSz + c] : ((c == Q && m < M) ? 1.0 : 0.0);   // column Q: ones (lambda)
   }
+  if constexpr (BWD)
+    for (int idx = tid; idx < 2 * 4 * PS_LAM; idx += PS_THREADS) sLam[idx] = 0.0;   // (slot, strip) pairs without a job stay 0
 
   // this warp's supertiles
   const int ns = sc.ns[wid];
@@ -190,21 +221,22 @@ k_psi2_small(int64_t rc, int M, int Mp, int Ms, int nt, int qk, int QC, int RSz,
 #pragma unroll
       for (int j = 0; j < QT; ++j) accZ[jj][i][j][0] = accZ[jj][i][j][1] = 0.0;
 
-  // lambda_n, W_n of a finished row: fixed-order sums of the per-job partials
+  // lambda_n, W_n of a finished row: fixed-order sums of the partials
+  const int njobs = sc.njobs, kslots = sc.kslots;
   auto flush_row = [&](int64_t n) {
     const int par = (int)(n & 1);
-    const int njobs = sc.njobs;
     if (tid < Qp) {
-      const double* p = sW + par * PS_JOBS * Qp + tid;
-      double s = 0.0;
-      for (int jb = 0; jb < njobs; ++jb) s += p[jb * Qp];
-      Wq[n * QC + tid] = s;
+      if (tid < QC) {
+        const double* p = sW + par * PS_JOBS * Qp + tid;
+        double s = 0.0;
+        for (int jb = 0; jb < njobs; ++jb) s += p[jb * Qp];
+        Wq[n * QC + tid] = s;
+      }
     } else if (tid >= 64 && tid < 64 + Mp16) {
-      const int m = tid - 64, strip = m >> 4;
-      const double* p = sLam + par * PS_JOBS * 16 + (m & 15);
-      double s = 0.0;
-      for (int jb = 0; jb < njobs; ++jb)
-        if (sc.jsp[jb] == strip) s += p[jb * 16];
+      const int m = tid - 64;
+      const double* p = sLam + par * 4 * PS_LAM + m;
+      double s = p[0];
+      for (int k = 1; k < kslots; ++k) s += p[k * PS_LAM];
       lam[n * Mp + m] = s;
     }
   };
@@ -292,36 +324,26 @@ k_psi2_small(int64_t rc, int M, int Mp, int Ms, int nt, int qk, int QC, int RSz,
       for (int jj = 0; jj < JMAX; ++jj) {
         if (jj < nj) {
           const int jb = sc.jw[wid][jj];
-          const int sp = sc.jsp[jb], kb = sc.jkb[jb], ke = sc.jke[jb];
+          const int sp = sc.jsp[jb], skb = sc.jkb[jb], ske = sc.jke[jb];
           const bool two = 16 * sp + 8 < M8;          // the strip's second 8 rows are not all padding
           double T[2][QT][2];
 #pragma unroll
           for (int i = 0; i < 2; ++i)
 #pragma unroll
             for (int j = 0; j < QT; ++j) T[i][j][0] = T[i][j][1] = 0.0;
-          double ls0 = 0.0, ls1 = 0.0;
           const double* pbz = sZ + t * RS + g;
-          for (int sk = kb >> 2; 4 * sk < ke; ++sk) {
+          for (int sk = skb; sk < ske; ++sk) {
             // L[strip sp][k in supertile column sk]: from supertile (sp, sk) as stored, or from (sk, sp) transposed
             const bool tr = sk < sp;
             const double* pa = Lb + (tr ? st_index(sk, sp, Ms) : st_index(sp, sk, Ms)) * PS_ST + (tr ? t * 20 + g : g * 20 + t);
-            const int kst = tr ? 80 : 4, ioff = tr ? 8 : 160;
-            const int k0 = kb > 4 * sk ? kb : 4 * sk, k1 = ke < 4 * sk + 4 ? ke : 4 * sk + 4;
-            for (int ks = k0; ks < k1; ++ks) {
-              const int kk = ks - 4 * sk;
-              const double a0 = pa[kk * kst];
-              const double a1 = two ? pa[kk * kst + ioff] : 0.0;
-              double bq[QT];
-#pragma unroll
-              for (int j = 0; j < QT; ++j) bq[j] = pbz[ks * 4 * RS + 8 * j];
-              ls0 += a0;
-              ls1 += a1;
-#pragma unroll
-              for (int j = 0; j < QT; ++j) dmma(T[0][j][0], T[0][j][1], a0, bq[j]);
-              if (two) {
-#pragma unroll
-                for (int j = 0; j < QT; ++j) dmma(T[1][j][0], T[1][j][1], a1, bq[j]);
-              }
+            const double* pb = pbz + sk * 16 * RS;
+            const bool four = 16 * sk + 8 < M8;       // the column's second 8 k values are not all padding
+            if (tr) {
+              if (two) small_s2_column<QT, 80, 8, true>(pa, pb, four, T);
+              else small_s2_column<QT, 80, 8, false>(pa, pb, four, T);
+            } else {
+              if (two) small_s2_column<QT, 4, 160, true>(pa, pb, four, T);
+              else small_s2_column<QT, 4, 160, false>(pa, pb, four, T);
             }
           }
           // folds: acc += ws T ; W partial = sum over this strip's rows of Z' T
@@ -352,13 +374,18 @@ k_psi2_small(int64_t rc, int M, int Mp, int Ms, int nt, int qk, int QC, int RSz,
             const int cc = c0 + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
             if (cc < 2 * QT) myW[8 * (cc >> 1) + 2 * t + (cc & 1)] = tot;
           }
-          ls0 += __shfl_xor_sync(0xffffffffu, ls0, 1);
-          ls0 += __shfl_xor_sync(0xffffffffu, ls0, 2);
-          ls1 += __shfl_xor_sync(0xffffffffu, ls1, 1);
-          ls1 += __shfl_xor_sync(0xffffffffu, ls1, 2);
-          if (t == 0) {
-            sLam[(par * PS_JOBS + jb) * 16 + g] = ls0;
-            sLam[(par * PS_JOBS + jb) * 16 + 8 + g] = ls1;
+          // lambda of the strip's rows over this job's k range = column Q of T (the ones column of Z')
+          if (t == ((Q & 7) >> 1)) {
+            double l0 = 0.0, l1 = 0.0;
+#pragma unroll
+            for (int j = 0; j < QT; ++j)
+              if (j == (Q >> 3)) {
+                l0 = (Q & 1) ? T[0][j][1] : T[0][j][0];
+                l1 = (Q & 1) ? T[1][j][1] : T[1][j][0];
+              }
+            double* pl = sLam + (par * 4 + sc.jslot[jb]) * PS_LAM + 16 * sp + g;
+            pl[0] = l0;
+            pl[8] = l1;
           }
         }
       }
@@ -378,8 +405,9 @@ k_psi2_small(int64_t rc, int M, int Mp, int Ms, int nt, int qk, int QC, int RSz,
         for (int i = 0; i < 2; ++i)
 #pragma unroll
           for (int j = 0; j < QT; ++j)
-            *reinterpret_cast<double2*>(out + (size_t)(16 * sp + 8 * i + g) * QC + 8 * j + 2 * t) =
-                make_double2(accZ[jj][i][j][0], accZ[jj][i][j][1]);
+            if (8 * j + 2 * t < QC)
+              *reinterpret_cast<double2*>(out + (size_t)(16 * sp + 8 * i + g) * QC + 8 * j + 2 * t) =
+                  make_double2(accZ[jj][i][j][0], accZ[jj][i][j][1]);
       }
     }
   }

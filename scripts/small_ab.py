@@ -7,7 +7,7 @@ from rgp_b200.device import DevicePsi
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 18
 dev = torch.device("cuda", 0)
 f64 = dict(dtype=torch.float64, device=dev)
-shapes = [(100, 20), (100, 10), (50, 20), (64, 16), (112, 24), (100, 8), (33, 20)]
+shapes = [(100, 20), (100, 10), (50, 20), (64, 16), (112, 23), (100, 7), (33, 20)]
 for M, Q in shapes:
     g = torch.Generator(device=dev).manual_seed(1)
     mu = torch.randn((N, Q), generator=g, **f64); S = torch.rand((N, Q), generator=g, **f64) * 0.49 + 0.01
