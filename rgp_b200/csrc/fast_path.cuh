@@ -265,7 +265,7 @@ static inline double small_dmma_per_row(int M, int Ms, int QT, int qk) {
 }
 
 // The work table of the small kernels.  Items: the supertiles of the upper triangle (stage 1 + exp) and, for the
-// backward pass, jobs = (16-row strip, a contiguous group of supertile columns holding ~1 / KS of the k-steps).
+// backward pass, jobs = (16-row strip, 1 / KS of the k-steps).
 // Warp w issues on SM sub-partition w % 4, so the items are dealt greedily (largest first) to the least loaded
 // sub-partition, then to its least loaded warp with a free slot.  Costs are FP64-pipe cycles: 16 per DMMA plus
 // the scalar epilogue / fold work.
@@ -282,25 +282,21 @@ static void small_schedule(int M, int Ms, int QT, int qk, int KS, int JMAX, bool
     }
   int kslots = 1;
   if (bwd) {
-    // column groups: cut where the running k-step count is nearest to i / KS of the total
-    int cum[PS_MS_MAX + 1] = {0};
-    for (int sk = 0; sk < Ms; ++sk) cum[sk + 1] = cum[sk] + small_col_ksteps(sk, M8);
-    int cut[5] = {0, Ms, Ms, Ms, Ms};
-    for (int i = 1; i < KS; ++i) {
-      int best = cut[i - 1];
-      for (int c = cut[i - 1]; c <= Ms; ++c)
-        if (std::abs(cum[c] * KS - cum[Ms] * i) < std::abs(cum[best] * KS - cum[Ms] * i)) best = c;
-      cut[i] = best;
-    }
-    cut[KS] = Ms;
+    // k-steps are numbered 4 * (supertile column) + (0..3); a column whose second half is padding has only 2, so the
+    // valid ones are listed first and each strip's list is cut into KS contiguous ranges of equal length
+    int ks_list[4 * PS_MS_MAX], nks = 0;
+    for (int sk = 0; sk < Ms; ++sk)
+      for (int kk = 0; kk < small_col_ksteps(sk, M8); ++kk) ks_list[nks++] = 4 * sk + kk;
     for (int sp = 0; sp < Ms; ++sp) {
       int slot = 0;
-      for (int i = 0; i < KS; ++i) {
-        const int kb = cut[i], ke = cut[i + 1];
-        if (ke <= kb) continue;
-        const int rowsets = 16 * sp + 8 < M8 ? 2 : 1;
-        items.push_back({(cum[ke] - cum[kb]) * (rowsets * QT * 16.0 + 4.0) + (ke - kb) * 12.0 + 80.0 + 14.0 * QT, 1, sp, kb,
-                         ke, slot});
+      const int rowsets = 16 * sp + 8 < M8 ? 2 : 1;
+      const int ksp = rowsets == 2 ? KS : (KS + 1) / 2;      // a half strip (8 valid rows) is half the work per k-step
+      for (int i = 0; i < ksp; ++i) {
+        const int a = nks * i / ksp, b = nks * (i + 1) / ksp;
+        if (b <= a) continue;
+        const int kb = ks_list[a], ke = ks_list[b - 1] + 1;
+        items.push_back({(b - a) * (rowsets * QT * 16.0 + 4.0) + ((ke + 3) / 4 - kb / 4) * 12.0 + 80.0 + 14.0 * QT, 1, sp,
+                         kb, ke, slot});
         ++slot;
       }
       kslots = std::max(kslots, slot);
@@ -335,13 +331,15 @@ static void small_schedule(int M, int Ms, int QT, int qk, int KS, int JMAX, bool
   sc->kslots = (signed char)kslots;
 }
 
-// small_m: 0 = never, 1 = whenever the shape fits, 2 (default) = when it also saves >= 15 % of the DMMAs
+// small_m: 0 = never, 1 = whenever the shape fits, 2 (default) = when it also saves >= 35 % of the DMMAs
 static SmallPlan small_plan(const rgp_psi_ctx* h, const Shape& s) {
   SmallPlan p;
   if (h->small_m == 0) return p;
   const int Ms = (s.M + 15) / 16, QT = s.Q / 8 + 1;     // stage-2 columns: Q and the ones column, in tiles of 8
   if (Ms > PS_MS_MAX || QT > 3) return p;
-  if (h->small_m == 2 && small_dmma_per_row(s.M, Ms, QT, s.qk) > 0.85 * block_dmma_per_row(s, false)) return p;
+  // measured (profiles/small_ab_r02.jsonl): the small kernels win where they compute <= ~0.65 of the block kernels' DMMAs
+  // (M = 100 / 112, M = 33); at M = 50 (0.69) and M = 64 (1.3) the block kernels are as fast or faster
+  if (h->small_m == 2 && small_dmma_per_row(s.M, Ms, QT, s.qk) > 0.65 * block_dmma_per_row(s, false)) return p;
   p.ok = true;
   p.Ms = Ms;
   p.Mp16 = 16 * Ms;

@@ -12,7 +12,7 @@
 //   TRIANGLE of the symmetric L_n as packed 16 x 16 supertiles (row stride 20), double-buffered by row parity;
 //   stage 1   E = H_m + H_m' + sum_q (ws_q Z'_mq) Z'_m'q on the supertiles of the upper triangle (8x8 tiles that lie
 //             entirely in the padding are skipped), p = exp(E), Psi2 += p (registers), L = C p -> shared;
-//   stage 2   T = L Z' as jobs (16-row strip x Qp columns x a range of supertile columns); a job reads L[strip][k]
+//   stage 2   T = L Z' as jobs (16-row strip x Qp columns x a range of k-steps); a job reads L[strip][k]
 //             from the supertile (strip, k) directly or from (k, strip) transposed - both fragment patterns are
 //             conflict free at stride 20, the four k-steps of a supertile column are unrolled with immediate
 //             offsets - and folds  acc[m,q] += ws_q T[m,q],  W_q += sum_m Z'_mq T[m,q],  lambda_m = T[m, Q];
@@ -45,7 +45,7 @@ struct SmallSched {
   signed char nj[PS_WARPS];            // jobs of warp w ...
   signed char jw[PS_WARPS][2];         // ... and their indices into the job list
   signed char njobs, kslots;           // job list length; ACCp slots per CTA (largest number of k ranges of a strip)
-  signed char jsp[PS_JOBS], jkb[PS_JOBS], jke[PS_JOBS], jslot[PS_JOBS];   // strip, supertile columns [kb, ke), k slot
+  signed char jsp[PS_JOBS], jkb[PS_JOBS], jke[PS_JOBS], jslot[PS_JOBS];   // strip, k-steps [kb, ke), k slot
 };
 
 // shared-memory size in doubles (host and device agree through this one function)
@@ -111,16 +111,16 @@ struct SmallRowStage {
 // index of supertile (lo, hi), lo <= hi, in the row-major enumeration of the upper triangle
 RGP_DEVINL int st_index(int lo, int hi, int Ms) { return lo * Ms - lo * (lo - 1) / 2 + (hi - lo); }
 
-// Stage 2 on one supertile column (16 k values = 4 k-steps, or 2 when the column's second half is padding):
+// Stage 2 on one supertile column (16 k values = 4 k-steps), k-steps [klo, khi) of it:
 // T[i][j] += L[strip rows 8 i + g][k] Z'[k][8 j ...].  KST / IOFF are the fragment strides of the packed supertile:
 // (4, 160) when it is read as stored, (80, 8) when it is read transposed.  TWO: the strip's second 8 rows exist.
 template <int QT, int KST, int IOFF, bool TWO>
-RGP_DEVINL void small_s2_column(const double* __restrict__ pa, const double* __restrict__ pb, bool four,
+RGP_DEVINL void small_s2_column(const double* __restrict__ pa, const double* __restrict__ pb, int klo, int khi,
                                 double (&T)[2][QT][2]) {
   constexpr int RS = 8 * QT + 4;
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) {
-    if (kk < 2 || four) {
+    if (kk >= klo && kk < khi) {
       const double a0 = pa[kk * KST];
       double a1 = 0.0;
       if constexpr (TWO) a1 = pa[kk * KST + IOFF];
@@ -324,7 +324,7 @@ k_psi2_small(int64_t rc, int M, int Q, int Mp, int Ms, int nt, int qk, int QC, i
       for (int jj = 0; jj < JMAX; ++jj) {
         if (jj < nj) {
           const int jb = sc.jw[wid][jj];
-          const int sp = sc.jsp[jb], skb = sc.jkb[jb], ske = sc.jke[jb];
+          const int sp = sc.jsp[jb], kb = sc.jkb[jb], ke = sc.jke[jb];   // k-steps [kb, ke): k-step 4 sk + kk = columns 16 sk + 4 kk ...
           const bool two = 16 * sp + 8 < M8;          // the strip's second 8 rows are not all padding
           double T[2][QT][2];
 #pragma unroll
@@ -332,18 +332,18 @@ k_psi2_small(int64_t rc, int M, int Q, int Mp, int Ms, int nt, int qk, int QC, i
 #pragma unroll
             for (int j = 0; j < QT; ++j) T[i][j][0] = T[i][j][1] = 0.0;
           const double* pbz = sZ + t * RS + g;
-          for (int sk = skb; sk < ske; ++sk) {
+          for (int sk = kb >> 2; 4 * sk < ke; ++sk) {
             // L[strip sp][k in supertile column sk]: from supertile (sp, sk) as stored, or from (sk, sp) transposed
             const bool tr = sk < sp;
             const double* pa = Lb + (tr ? st_index(sk, sp, Ms) : st_index(sp, sk, Ms)) * PS_ST + (tr ? t * 20 + g : g * 20 + t);
             const double* pb = pbz + sk * 16 * RS;
-            const bool four = 16 * sk + 8 < M8;       // the column's second 8 k values are not all padding
+            const int klo = kb - 4 * sk, khi = ke - 4 * sk;     // (k-steps of padding columns are not in any job)
             if (tr) {
-              if (two) small_s2_column<QT, 80, 8, true>(pa, pb, four, T);
-              else small_s2_column<QT, 80, 8, false>(pa, pb, four, T);
+              if (two) small_s2_column<QT, 80, 8, true>(pa, pb, klo, khi, T);
+              else small_s2_column<QT, 80, 8, false>(pa, pb, klo, khi, T);
             } else {
-              if (two) small_s2_column<QT, 4, 160, true>(pa, pb, four, T);
-              else small_s2_column<QT, 4, 160, false>(pa, pb, four, T);
+              if (two) small_s2_column<QT, 4, 160, true>(pa, pb, klo, khi, T);
+              else small_s2_column<QT, 4, 160, false>(pa, pb, klo, khi, T);
             }
           }
           // folds: acc += ws T ; W partial = sum over this strip's rows of Z' T

@@ -4,7 +4,7 @@ library) and of the data flow it drives.
 `emulate` is a numpy model of psi2_small.cuh at the level of warps and k-steps: supertiles of the upper triangle
 packed as the kernel stores them (16 x 16, row stride 20), stage-2 jobs reading L[strip][k] either from supertile
 (strip, k) directly or from (k, strip) transposed, tiles that lie in the padding skipped (a supertile column whose
-second half is padding has 2 k-steps instead of 4), lambda taken from the ones column of Z' (column Q), per-job
+second half is padding contributes 2 k-steps instead of 4), lambda taken from the ones column of Z' (column Q), per-job
 W partials combined in job order, lambda / accumulator partials written to (k slot, strip) slices.
 It is test infrastructure (it documents and guards the index algebra); the product never runs it."""
 import ctypes as C
@@ -45,14 +45,16 @@ def test_schedule_covers_every_supertile_and_k_step_once(M, Q, ks):
             continue
         jobs = sorted(int(sc["jw"][w, j]) for w in range(16) for j in range(sc["nj"][w]))
         assert jobs == list(range(sc["njobs"]))               # every job on exactly one warp
+        M8_ = (M + 7) // 8 * 8
+        valid = [4 * c + k for c in range(Ms) for k in range(4 if 16 * c + 8 < M8_ else 2)]   # k-step 4 c + k = columns 16 c + 4 k ...
         for sp in range(Ms):
-            cover = np.zeros(Ms, int)
+            cover = np.zeros(4 * Ms, int)
             slots = []
             for j in range(sc["njobs"]):
                 if sc["jsp"][j] == sp:
                     cover[sc["jkb"][j]:sc["jke"][j]] += 1
                     slots.append(int(sc["jslot"][j]))
-            assert (cover == 1).all(), (sp, cover)             # the strip's supertile columns exactly once
+            assert sorted(np.nonzero(cover)[0]) == valid and cover.max() == 1, (sp, cover)   # every valid k-step once, no padding
             assert sorted(slots) == list(range(len(slots))) and len(slots) <= sc["kslots"] <= 4
         # FP64-pipe load per SM sub-partition (warp w issues on w % 4): DMMAs within 25 % of the mean
         M8 = (M + 7) // 8 * 8
@@ -67,8 +69,7 @@ def test_schedule_covers_every_supertile_and_k_step_once(M, Q, ks):
                 load4[w % 4] += ((4 if vi == 2 else 1) if i == j else vi * vj) * ((Q + 3) // 4)
             for jj in range(sc["nj"][w]):
                 j = sc["jw"][w, jj]
-                ks_ = sum(4 if 16 * c + 8 < M8 else 2 for c in range(sc["jkb"][j], sc["jke"][j]))
-                load4[w % 4] += ks_ * (2 if 16 * sc["jsp"][j] + 8 < M8 else 1) * (Q // 8 + 1)
+                load4[w % 4] += (sc["jke"][j] - sc["jkb"][j]) * (2 if 16 * sc["jsp"][j] + 8 < M8 else 1) * (Q // 8 + 1)
         if Ms >= 4:
             assert load4.max() <= 1.25 * load4.mean(), load4
 
@@ -123,21 +124,20 @@ def emulate(M, Q, ks, N, seed=0):
         sW = np.zeros((sc["njobs"], Qp)); sLam = np.zeros((sc["kslots"], Mp16))
         for w in range(16):
             for jj in range(sc["nj"][w]):
-                jb = int(sc["jw"][w, jj]); sp, skb, ske = int(sc["jsp"][jb]), int(sc["jkb"][jb]), int(sc["jke"][jb])
+                jb = int(sc["jw"][w, jj]); sp, kb, ke = int(sc["jsp"][jb]), int(sc["jkb"][jb]), int(sc["jke"][jb])
                 two = 16 * sp + 8 < M8
                 T = np.zeros((16, Qp))
-                for sk in range(skb, ske):
-                    for kk4 in range(4 if 16 * sk + 8 < M8 else 2):     # k-steps of this supertile column
-                        kk = 4 * kk4
-                        if sk < sp:
-                            A = Lb[idx(sk, sp), kk:kk + 4, :16].T        # transposed read of supertile (sk, sp)
-                        else:
-                            A = Lb[idx(sp, sk), :16, kk:kk + 4]
-                        A = A.copy()
-                        if not two:
-                            A[8:] = 0.0
-                        assert not np.isnan(A).any(), (M, sp, sk, kk)    # only tiles that stage 1 wrote are read
-                        T += A @ Z1[16 * sk + kk:16 * sk + kk + 4]
+                for ks_ in range(kb, ke):                               # k-step: 4 columns of L
+                    sk, kk = ks_ // 4, (ks_ % 4) * 4
+                    if sk < sp:
+                        A = Lb[idx(sk, sp), kk:kk + 4, :16].T            # transposed read of supertile (sk, sp)
+                    else:
+                        A = Lb[idx(sp, sk), :16, kk:kk + 4]
+                    A = A.copy()
+                    if not two:
+                        A[8:] = 0.0
+                    assert not np.isnan(A).any(), (M, sp, sk, kk)        # only tiles that stage 1 wrote are read
+                    T += A @ Z1[4 * ks_:4 * ks_ + 4]
                 ACC[sc["jslot"][jb], 16 * sp:16 * sp + 16] += wsp[n] * T
                 sW[jb] = (Z1[16 * sp:16 * sp + 16] * T).sum(0)
                 sLam[sc["jslot"][jb], 16 * sp:16 * sp + 16] = T[:, Q]
