@@ -8,14 +8,14 @@
 // CTA of 16 warps holds the whole problem of a row:
 //
 //   Z' [Mp16][Qp + 4] in shared memory (Mp16 = M rounded up to 16, Qp = 8 (Q / 8 + 1): at least one spare column,
-//   column Q holds ONES so that T[:, Q] = L 1 = lambda comes out of the stage-2 MMAs for free) and the UPPER
+//   the last one holds ONES so that T[:, Qp - 1] = L 1 = lambda comes out of the stage-2 MMAs for free) and the UPPER
 //   TRIANGLE of the symmetric L_n as packed 16 x 16 supertiles (row stride 20), double-buffered by row parity;
 //   stage 1   E = H_m + H_m' + sum_q (ws_q Z'_mq) Z'_m'q on the supertiles of the upper triangle (8x8 tiles that lie
 //             entirely in the padding are skipped), p = exp(E), Psi2 += p (registers), L = C p -> shared;
 //   stage 2   T = L Z' as jobs (16-row strip x Qp columns x a range of k-steps); a job reads L[strip][k]
 //             from the supertile (strip, k) directly or from (k, strip) transposed - both fragment patterns are
 //             conflict free at stride 20, the four k-steps of a supertile column are unrolled with immediate
-//             offsets - and folds  acc[m,q] += ws_q T[m,q],  W_q += sum_m Z'_mq T[m,q],  lambda_m = T[m, Q];
+//             offsets - and folds  acc[m,q] += ws_q T[m,q],  W_q += sum_m Z'_mq T[m,q],  lambda_m = T[m, Qp - 1];
 //   per row   ONE CTA barrier (L_n complete); the partials of row n are combined after the barrier of row n + 1 and
 //             lambda_n, W_n are written once with plain stores, in a fixed order (deterministic, no atomics).
 //
@@ -24,6 +24,8 @@
 // The per-row vectors (ws[Qp], H[Mp16]) arrive by TMA bulk copies into a two-slot ring (SmallRowStage), as in the
 // block kernels.  The forward-only kernel needs a barrier only when a ring slot is recycled (every PS_VR rows).
 #pragma once
+#include <type_traits>
+
 #include "psi2_kernels.cuh"
 
 namespace rgp {
@@ -111,32 +113,6 @@ struct SmallRowStage {
 // index of supertile (lo, hi), lo <= hi, in the row-major enumeration of the upper triangle
 RGP_DEVINL int st_index(int lo, int hi, int Ms) { return lo * Ms - lo * (lo - 1) / 2 + (hi - lo); }
 
-// Stage 2 on one supertile column (16 k values = 4 k-steps), k-steps [klo, khi) of it:
-// T[i][j] += L[strip rows 8 i + g][k] Z'[k][8 j ...].  KST / IOFF are the fragment strides of the packed supertile:
-// (4, 160) when it is read as stored, (80, 8) when it is read transposed.  TWO: the strip's second 8 rows exist.
-template <int QT, int KST, int IOFF, bool TWO>
-RGP_DEVINL void small_s2_column(const double* __restrict__ pa, const double* __restrict__ pb, int klo, int khi,
-                                double (&T)[2][QT][2]) {
-  constexpr int RS = 8 * QT + 4;
-#pragma unroll
-  for (int kk = 0; kk < 4; ++kk) {
-    if (kk >= klo && kk < khi) {
-      const double a0 = pa[kk * KST];
-      double a1 = 0.0;
-      if constexpr (TWO) a1 = pa[kk * KST + IOFF];
-      double bq[QT];
-#pragma unroll
-      for (int j = 0; j < QT; ++j) bq[j] = pb[kk * 4 * RS + 8 * j];
-#pragma unroll
-      for (int j = 0; j < QT; ++j) dmma(T[0][j][0], T[0][j][1], a0, bq[j]);
-      if constexpr (TWO) {
-#pragma unroll
-        for (int j = 0; j < QT; ++j) dmma(T[1][j][0], T[1][j][1], a1, bq[j]);
-      }
-    }
-  }
-}
-
 // MODE 0: forward only (Psi2 partials), 1: backward only, 2: backward + Psi2 partials (fused SVI pass).
 // Outputs (strides of the block path, so the small GEMMs and combiners downstream are shared):
 //   lam [rc][Mp]   Wq [rc][QC]                 complete per row, plain stores
@@ -177,7 +153,7 @@ k_psi2_small(int64_t rc, int M, int Q, int Mp, int Ms, int nt, int qk, int QC, i
   rv.init_barriers(tid);
   for (int idx = tid; idx < Mp16 * Qp; idx += PS_THREADS) {
     const int m = idx / Qp, c = idx - m * Qp;
-    sZ[m * RS + c] = c < Q ? Zt[(size_t)m * RSz + c] : ((c == Q && m < M) ? 1.0 : 0.0);   // column Q: ones (lambda)
+    sZ[m * RS + c] = c < Q ? Zt[(size_t)m * RSz + c] : ((c == Qp - 1 && m < M) ? 1.0 : 0.0);   // last column: ones (lambda)
   }
   if constexpr (BWD)
     for (int idx = tid; idx < 2 * 4 * PS_LAM; idx += PS_THREADS) sLam[idx] = 0.0;   // (slot, strip) pairs without a job stay 0
@@ -332,6 +308,34 @@ k_psi2_small(int64_t rc, int M, int Q, int Mp, int Ms, int nt, int qk, int QC, i
 #pragma unroll
             for (int j = 0; j < QT; ++j) T[i][j][0] = T[i][j][1] = 0.0;
           const double* pbz = sZ + t * RS + g;
+          // one supertile column (4 k-steps, [klo, khi) of them): T[i][j] += L[strip rows 8 i + g][k] Z'[k][8 j ...].
+          // KST / IOFF: fragment strides of the packed supertile - (4, 160) read as stored, (80, 8) read transposed;
+          // TWO: the strip's second 8 rows exist.  (A generic lambda, so T stays in registers.)
+          auto column = [&](auto kst_c, auto ioff_c, auto two_c, const double* pa, const double* pb, int klo, int khi) {
+            constexpr int KST = decltype(kst_c)::value, IOFF = decltype(ioff_c)::value;
+            constexpr bool TWO = decltype(two_c)::value;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              if (kk >= klo && kk < khi) {
+                const double a0 = pa[kk * KST];
+                double a1 = 0.0;
+                if constexpr (TWO) a1 = pa[kk * KST + IOFF];
+                double bq[QT];
+#pragma unroll
+                for (int j = 0; j < QT; ++j) bq[j] = pb[kk * 4 * RS + 8 * j];
+#pragma unroll
+                for (int j = 0; j < QT; ++j) dmma(T[0][j][0], T[0][j][1], a0, bq[j]);
+                if constexpr (TWO) {
+#pragma unroll
+                  for (int j = 0; j < QT; ++j) dmma(T[1][j][0], T[1][j][1], a1, bq[j]);
+                }
+              }
+            }
+          };
+          using I4 = std::integral_constant<int, 4>;
+          using I8 = std::integral_constant<int, 8>;
+          using I80 = std::integral_constant<int, 80>;
+          using I160 = std::integral_constant<int, 160>;
           for (int sk = kb >> 2; 4 * sk < ke; ++sk) {
             // L[strip sp][k in supertile column sk]: from supertile (sp, sk) as stored, or from (sk, sp) transposed
             const bool tr = sk < sp;
@@ -339,11 +343,11 @@ k_psi2_small(int64_t rc, int M, int Q, int Mp, int Ms, int nt, int qk, int QC, i
             const double* pb = pbz + sk * 16 * RS;
             const int klo = kb - 4 * sk, khi = ke - 4 * sk;     // (k-steps of padding columns are not in any job)
             if (tr) {
-              if (two) small_s2_column<QT, 80, 8, true>(pa, pb, klo, khi, T);
-              else small_s2_column<QT, 80, 8, false>(pa, pb, klo, khi, T);
+              if (two) column(I80{}, I8{}, std::true_type{}, pa, pb, klo, khi);
+              else column(I80{}, I8{}, std::false_type{}, pa, pb, klo, khi);
             } else {
-              if (two) small_s2_column<QT, 4, 160, true>(pa, pb, klo, khi, T);
-              else small_s2_column<QT, 4, 160, false>(pa, pb, klo, khi, T);
+              if (two) column(I4{}, I160{}, std::true_type{}, pa, pb, klo, khi);
+              else column(I4{}, I160{}, std::false_type{}, pa, pb, klo, khi);
             }
           }
           // folds: acc += ws T ; W partial = sum over this strip's rows of Z' T
@@ -374,15 +378,9 @@ k_psi2_small(int64_t rc, int M, int Q, int Mp, int Ms, int nt, int qk, int QC, i
             const int cc = c0 + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
             if (cc < 2 * QT) myW[8 * (cc >> 1) + 2 * t + (cc & 1)] = tot;
           }
-          // lambda of the strip's rows over this job's k range = column Q of T (the ones column of Z')
-          if (t == ((Q & 7) >> 1)) {
-            double l0 = 0.0, l1 = 0.0;
-#pragma unroll
-            for (int j = 0; j < QT; ++j)
-              if (j == (Q >> 3)) {
-                l0 = (Q & 1) ? T[0][j][1] : T[0][j][0];
-                l1 = (Q & 1) ? T[1][j][1] : T[1][j][0];
-              }
+          // lambda of the strip's rows over this job's k range = the last column of T (the ones column of Z')
+          if (t == 3) {
+            const double l0 = T[0][QT - 1][1], l1 = T[1][QT - 1][1];
             double* pl = sLam + (par * 4 + sc.jslot[jb]) * PS_LAM + 16 * sp + g;
             pl[0] = l0;
             pl[8] = l1;

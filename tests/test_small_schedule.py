@@ -4,7 +4,7 @@ library) and of the data flow it drives.
 `emulate` is a numpy model of psi2_small.cuh at the level of warps and k-steps: supertiles of the upper triangle
 packed as the kernel stores them (16 x 16, row stride 20), stage-2 jobs reading L[strip][k] either from supertile
 (strip, k) directly or from (k, strip) transposed, tiles that lie in the padding skipped (a supertile column whose
-second half is padding contributes 2 k-steps instead of 4), lambda taken from the ones column of Z' (column Q), per-job
+second half is padding contributes 2 k-steps instead of 4), lambda taken from the ones column of Z' (its last column), per-job
 W partials combined in job order, lambda / accumulator partials written to (k slot, strip) slices.
 It is test infrastructure (it documents and guards the index algebra); the product never runs it."""
 import ctypes as C
@@ -84,7 +84,7 @@ def emulate(M, Q, ks, N, seed=0):
     sc = schedule(M, Q, ks, 1)
     Ms = (M + 15) // 16; Mp16 = 16 * Ms; Qp = (Q // 8 + 1) * 8; qk = (Q + 3) // 4 * 4; M8 = (M + 7) // 8 * 8
     Z = np.zeros((Mp16, Qp)); Z[:M, :Q] = rng.normal(size=(M, Q))
-    Z1 = Z.copy(); Z1[:M, Q] = 1.0                        # the kernel's shared-memory tile: ones in column Q
+    Z1 = Z.copy(); Z1[:M, Qp - 1] = 1.0                   # the kernel's shared-memory tile: ones in its last column
     Cm = np.zeros((Mp16, Mp16)); c = rng.normal(size=(M, M)); Cm[:M, :M] = (c + c.T) / 2
     H = np.full((N, Mp16), -1e300); H[:, :M] = -rng.random((N, M))
     ws = np.zeros((N, Qp)); ws[:, :Q] = rng.random((N, Q)) * 0.1
@@ -140,7 +140,7 @@ def emulate(M, Q, ks, N, seed=0):
                     T += A @ Z1[4 * ks_:4 * ks_ + 4]
                 ACC[sc["jslot"][jb], 16 * sp:16 * sp + 16] += wsp[n] * T
                 sW[jb] = (Z1[16 * sp:16 * sp + 16] * T).sum(0)
-                sLam[sc["jslot"][jb], 16 * sp:16 * sp + 16] = T[:, Q]
+                sLam[sc["jslot"][jb], 16 * sp:16 * sp + 16] = T[:, Qp - 1]
         W[n] = sW.sum(0)
         lam[n] = sLam.sum(0)
     err = lambda a, b: np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
