@@ -77,7 +77,7 @@ int rgp_psi_destroy(rgp_psi_handle_t h);
  * (threads of the pageable <-> pinned copies, 0 = min(8, cores / 2)),
  * "bwd_pipe" (Psi2 backward kernel: 0 = row-at-a-time, 1 = software-pipelined with TMA row-vector
  * staging, 2 (default) = row-at-a-time for the plain backward pass and pipelined for the fused pass,
- * the measured faster choice for each), "small_m" (kernels for small inducing sets, M <= 112 and Q <= 23,
+ * the measured faster choice for each), "small_m" (kernels for small inducing sets, M <= 112 and Q <= 47,
  * where one CTA holds the whole pair matrix of a row: 0 = never, 1 = whenever the shape fits, 2 (default) =
  * when they also save work against the 64 x 64 block kernels), "small_ks" (their stage-2 k split: 0 =
  * default, or 1 / 2 / 4), "profile" (1 = record a CUDA-event pair around every kernel

@@ -42,6 +42,17 @@ static int init_qc() {
 }
 
 template <int QT>
+static int init_small_wide() {      // Q > 23: one job per warp
+  RGP_CUDA(cudaFuncSetAttribute((k_psi2_small<QT, 0, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                small_smem_doubles(PS_MS_MAX, QT, false) * 8));
+  RGP_CUDA(cudaFuncSetAttribute((k_psi2_small<QT, 1, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                small_smem_doubles(PS_MS_MAX, QT, true) * 8));
+  RGP_CUDA(cudaFuncSetAttribute((k_psi2_small<QT, 2, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                small_smem_doubles(PS_MS_MAX, QT, true) * 8));
+  return 0;
+}
+
+template <int QT>
 static int init_small() {
   RGP_CUDA(cudaFuncSetAttribute((k_psi2_small<QT, 0, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 small_smem_doubles(PS_MS_MAX, QT, false) * 8));
@@ -60,6 +71,8 @@ static int init(rgp_psi_ctx*) {
   RGP_TRY(init_small<1>());
   RGP_TRY(init_small<2>());
   RGP_TRY(init_small<3>());
+  RGP_TRY(init_small_wide<4>());
+  RGP_TRY(init_small_wide<6>());
   RGP_TRY(init_qc<16>());
   RGP_TRY(init_qc<32>());
   RGP_TRY(init_qc<64>());
@@ -335,16 +348,20 @@ static void small_schedule(int M, int Ms, int QT, int qk, int KS, int JMAX, bool
 static SmallPlan small_plan(const rgp_psi_ctx* h, const Shape& s) {
   SmallPlan p;
   if (h->small_m == 0) return p;
-  const int Ms = (s.M + 15) / 16, QT = s.Q / 8 + 1;     // stage-2 columns: Q and the ones column, in tiles of 8
-  if (Ms > PS_MS_MAX || QT > 3) return p;
+  const int Ms = (s.M + 15) / 16;
+  int QT = s.Q / 8 + 1;                                 // stage-2 columns: Q and the ones column, in tiles of 8
+  if (QT == 5) QT = 6;                                  // Q > 23: two column passes of QT / 2 tiles (4 or 6 tiles)
+  if (Ms > PS_MS_MAX || QT > 6) return p;
   // measured (profiles/small_ab_r02.jsonl): the small kernels win where they compute <= ~0.65 of the block kernels' DMMAs
   // (M = 100 / 112, M = 33); at M = 50 (0.69) and M = 64 (1.3) the block kernels are as fast or faster
-  if (h->small_m == 2 && small_dmma_per_row(s.M, Ms, QT, s.qk) > 0.65 * block_dmma_per_row(s, false)) return p;
+  if (h->small_m == 2 && small_dmma_per_row(s.M, Ms, QT, s.qk) > 0.65 * block_dmma_per_row(s, s.QC == 64 && s.Q <= 48))
+    return p;
   p.ok = true;
   p.Ms = Ms;
   p.Mp16 = 16 * Ms;
   p.QT = QT;
-  p.KS = h->small_ks > 0 ? h->small_ks : 2;
+  p.KS = h->small_ks > 0 ? h->small_ks : (Ms >= 5 ? 2 : 4);   // ~13 ... 16 jobs (measured: profiles/small_ab_r02.jsonl)
+  if (QT > 3) p.KS = std::min(p.KS, PS_WARPS / Ms >= 4 ? 4 : (PS_WARPS / Ms >= 2 ? 2 : 1));   // wide Q: one job per warp
   p.JMAX = (Ms * p.KS + PS_WARPS - 1) / PS_WARPS;
   small_schedule(s.M, Ms, QT, s.qk, p.KS, p.JMAX, false, &p.fwd);
   small_schedule(s.M, Ms, QT, s.qk, p.KS, p.JMAX, true, &p.bwd);
@@ -360,10 +377,10 @@ static int launch_small_qt(rgp_psi_ctx* h, cudaStream_t st, const Shape& s, cons
   if constexpr (MODE == 0) {
     RGP_LAUNCH(h, st, name, (k_psi2_small<QT, 0, 1>), Rs, PS_THREADS, smem, rows, s.M, s.Q, s.Mp, p.Ms, s.nt, s.qk,
                s.QC, s.RS, p.fwd, Zt, Ct, w, HP, lam, Wq, ACCp, P2s);
-  } else if (p.JMAX == 1) {
+  } else if (p.JMAX == 1 || QT > 3) {
     RGP_LAUNCH(h, st, name, (k_psi2_small<QT, MODE, 1>), Rs, PS_THREADS, smem, rows, s.M, s.Q, s.Mp, p.Ms, s.nt,
                s.qk, s.QC, s.RS, p.bwd, Zt, Ct, w, HP, lam, Wq, ACCp, P2s);
-  } else {
+  } else if constexpr (QT <= 3) {
     RGP_LAUNCH(h, st, name, (k_psi2_small<QT, MODE, 2>), Rs, PS_THREADS, smem, rows, s.M, s.Q, s.Mp, p.Ms, s.nt,
                s.qk, s.QC, s.RS, p.bwd, Zt, Ct, w, HP, lam, Wq, ACCp, P2s);
   }
@@ -376,7 +393,9 @@ static int launch_small(rgp_psi_ctx* h, cudaStream_t st, const Shape& s, const S
                         double* Wq, double* ACCp, double* P2s) {
   if (p.QT == 1) return launch_small_qt<1, MODE>(h, st, s, p, rows, Rs, Zt, Ct, w, HP, lam, Wq, ACCp, P2s);
   if (p.QT == 2) return launch_small_qt<2, MODE>(h, st, s, p, rows, Rs, Zt, Ct, w, HP, lam, Wq, ACCp, P2s);
-  return launch_small_qt<3, MODE>(h, st, s, p, rows, Rs, Zt, Ct, w, HP, lam, Wq, ACCp, P2s);
+  if (p.QT == 3) return launch_small_qt<3, MODE>(h, st, s, p, rows, Rs, Zt, Ct, w, HP, lam, Wq, ACCp, P2s);
+  if (p.QT == 4) return launch_small_qt<4, MODE>(h, st, s, p, rows, Rs, Zt, Ct, w, HP, lam, Wq, ACCp, P2s);
+  return launch_small_qt<6, MODE>(h, st, s, p, rows, Rs, Zt, Ct, w, HP, lam, Wq, ACCp, P2s);
 }
 
 static inline int small_grid(const rgp_psi_ctx* h, int64_t rows) {

@@ -1,4 +1,4 @@
-// psi2_small.cuh - Psi2 forward / backward for SMALL inducing sets (M <= 112, Q <= 48): the shapes of the
+// psi2_small.cuh - Psi2 forward / backward for SMALL inducing sets (M <= 112, Q <= 47): the shapes of the
 // reference's own models (M = 50 ... 100, Q = 10 ... 40; autoreg/benchmark/tasks.py:141-177,
 // examples/walk_run_2_alex.py:364-393, svi_experiments/rgp_experiments.py).
 //
@@ -37,6 +37,7 @@ constexpr int PS_MS_MAX = 7;      // 16-row super rows: M <= 112
 constexpr int PS_S1 = 2;          // supertile slots per warp (28 supertiles <= 2 * 16)
 constexpr int PS_VR = 4;          // rows per TMA batch
 constexpr int PS_JOBS = 32;       // job list length
+__host__ __device__ constexpr int PS_JOBS_OF(int QT) { return QT > 3 ? 16 : 32; }   // jobs per row (wide Q: one per warp)
 constexpr int PS_ST = 320;        // doubles per packed supertile: 16 rows x stride 20
 constexpr int PS_QT_MAX = 6;
 constexpr int PS_LAM = 16 * PS_MS_MAX;   // lambda partials: [parity][k slot <= 4][PS_LAM]
@@ -54,7 +55,7 @@ struct SmallSched {
 __host__ __device__ constexpr int small_smem_doubles(int Ms, int QT, bool bwd) {
   const int Mp16 = 16 * Ms, Qp = 8 * QT;
   int d = Mp16 * (Qp + 4) + 2 * PS_VR * (Qp + Mp16) + 258;
-  if (bwd) d += 2 * PS_JOBS * Qp + 2 * 4 * PS_LAM + 2 * (Ms * (Ms + 1) / 2) * PS_ST;
+  if (bwd) d += 2 * PS_JOBS_OF(QT) * Qp + 2 * 4 * PS_LAM + 2 * (Ms * (Ms + 1) / 2) * PS_ST;
   return d;
 }
 
@@ -127,14 +128,16 @@ k_psi2_small(int64_t rc, int M, int Q, int Mp, int Ms, int nt, int qk, int QC, i
              const double* __restrict__ HP, double* __restrict__ lam, double* __restrict__ Wq,
              double* __restrict__ ACCp, double* __restrict__ P2s) {
   constexpr int Qp = 8 * QT, RS = Qp + 4;
+  constexpr int NH = QT > 3 ? 2 : 1, QH = QT / NH;     // stage-2 column passes and 8-wide tiles per pass
+  static_assert(QT % NH == 0 && 2 * QH <= 8, "stage-2 halves");
   constexpr bool BWD = MODE != 0, FWD = MODE != 1;
   const int Mp16 = 16 * Ms, VB = Qp + Mp16, M8 = (M + 7) & ~7, NS = Ms * (Ms + 1) / 2;
   extern __shared__ __align__(16) double smem[];
   double* sZ = smem;                         // [Mp16][RS]
   double* sV = sZ + Mp16 * RS;               // row-vector ring: 2 slots x PS_VR rows x VB
   double* sT = sV + 2 * PS_VR * VB;          // exp table (256) + 2 mbarriers
-  double* sW = sT + 258;                     // [2][PS_JOBS][Qp]   W partials per job, by row parity
-  double* sLam = sW + 2 * PS_JOBS * Qp;      // [2][4][PS_LAM]     lambda partials per k slot
+  double* sW = sT + 258;                     // [2][jobs][Qp]      W partials per job, by row parity
+  double* sLam = sW + 2 * PS_JOBS_OF(QT) * Qp;   // [2][4][PS_LAM]  lambda partials per k slot
   double* sL = sLam + 2 * 4 * PS_LAM;        // [2][NS][PS_ST]     packed supertiles of L_n, by row parity
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, t = lane & 3;
@@ -203,7 +206,7 @@ k_psi2_small(int64_t rc, int M, int Q, int Mp, int Ms, int nt, int qk, int QC, i
     const int par = (int)(n & 1);
     if (tid < Qp) {
       if (tid < QC) {
-        const double* p = sW + par * PS_JOBS * Qp + tid;
+        const double* p = sW + par * PS_JOBS_OF(QT) * Qp + tid;
         double s = 0.0;
         for (int jb = 0; jb < njobs; ++jb) s += p[jb * Qp];
         Wq[n * QC + tid] = s;
@@ -302,12 +305,16 @@ k_psi2_small(int64_t rc, int M, int Q, int Mp, int Ms, int nt, int qk, int QC, i
           const int jb = sc.jw[wid][jj];
           const int sp = sc.jsp[jb], kb = sc.jkb[jb], ke = sc.jke[jb];   // k-steps [kb, ke): k-step 4 sk + kk = columns 16 sk + 4 kk ...
           const bool two = 16 * sp + 8 < M8;          // the strip's second 8 rows are not all padding
-          double T[2][QT][2];
+          double* myW = sW + (par * PS_JOBS_OF(QT) + jb) * Qp;
+          // Q > 23: the stage-2 columns go in two halves of QH tiles (registers hold one half of T at a time)
+#pragma unroll
+          for (int h = 0; h < NH; ++h) {
+          double T[2][QH][2];
 #pragma unroll
           for (int i = 0; i < 2; ++i)
 #pragma unroll
-            for (int j = 0; j < QT; ++j) T[i][j][0] = T[i][j][1] = 0.0;
-          const double* pbz = sZ + t * RS + g;
+            for (int j = 0; j < QH; ++j) T[i][j][0] = T[i][j][1] = 0.0;
+          const double* pbz = sZ + t * RS + 8 * QH * h + g;
           // one supertile column (4 k-steps, [klo, khi) of them): T[i][j] += L[strip rows 8 i + g][k] Z'[k][8 j ...].
           // KST / IOFF: fragment strides of the packed supertile - (4, 160) read as stored, (80, 8) read transposed;
           // TWO: the strip's second 8 rows exist.  (A generic lambda, so T stays in registers.)
@@ -320,14 +327,14 @@ k_psi2_small(int64_t rc, int M, int Q, int Mp, int Ms, int nt, int qk, int QC, i
                 const double a0 = pa[kk * KST];
                 double a1 = 0.0;
                 if constexpr (TWO) a1 = pa[kk * KST + IOFF];
-                double bq[QT];
+                double bq[QH];
 #pragma unroll
-                for (int j = 0; j < QT; ++j) bq[j] = pb[kk * 4 * RS + 8 * j];
+                for (int j = 0; j < QH; ++j) bq[j] = pb[kk * 4 * RS + 8 * j];
 #pragma unroll
-                for (int j = 0; j < QT; ++j) dmma(T[0][j][0], T[0][j][1], a0, bq[j]);
+                for (int j = 0; j < QH; ++j) dmma(T[0][j][0], T[0][j][1], a0, bq[j]);
                 if constexpr (TWO) {
 #pragma unroll
-                  for (int j = 0; j < QT; ++j) dmma(T[1][j][0], T[1][j][1], a1, bq[j]);
+                  for (int j = 0; j < QH; ++j) dmma(T[1][j][0], T[1][j][1], a1, bq[j]);
                 }
               }
             }
@@ -351,39 +358,38 @@ k_psi2_small(int64_t rc, int M, int Q, int Mp, int Ms, int nt, int qk, int QC, i
             }
           }
           // folds: acc += ws T ; W partial = sum over this strip's rows of Z' T
-          double wp[2 * QT];
+          double wp[2 * QH];
 #pragma unroll
-          for (int j = 0; j < QT; ++j) {
-            const int q = 8 * j + 2 * t;
+          for (int j = 0; j < QH; ++j) {
+            const int q = 8 * (QH * h + j) + 2 * t;
             const double2 wq = *reinterpret_cast<const double2*>(v + q);
             double w0 = 0.0, w1 = 0.0;
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
               const double2 z = *reinterpret_cast<const double2*>(sZ + (16 * sp + 8 * i + g) * RS + q);
-              accZ[jj][i][j][0] = fma(wq.x, T[i][j][0], accZ[jj][i][j][0]);
-              accZ[jj][i][j][1] = fma(wq.y, T[i][j][1], accZ[jj][i][j][1]);
+              accZ[jj][i][QH * h + j][0] = fma(wq.x, T[i][j][0], accZ[jj][i][QH * h + j][0]);
+              accZ[jj][i][QH * h + j][1] = fma(wq.y, T[i][j][1], accZ[jj][i][QH * h + j][1]);
               w0 = fma(z.x, T[i][j][0], w0);
               w1 = fma(z.y, T[i][j][1], w1);
             }
             wp[2 * j] = w0;
             wp[2 * j + 1] = w1;
           }
-          double* myW = sW + (par * PS_JOBS + jb) * Qp;
-#pragma unroll
-          for (int c0 = 0; c0 < 2 * QT; c0 += 8) {
+          {
             double v8[8];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) v8[c] = (c0 + c < 2 * QT) ? wp[(c0 + c < 2 * QT) ? c0 + c : 0] : 0.0;
+            for (int c = 0; c < 8; ++c) v8[c] = (c < 2 * QH) ? wp[(c < 2 * QH) ? c : 0] : 0.0;
             const double tot = reduce8_over_g(v8, lane);
-            const int cc = c0 + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-            if (cc < 2 * QT) myW[8 * (cc >> 1) + 2 * t + (cc & 1)] = tot;
+            const int cc = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+            if (cc < 2 * QH) myW[8 * (QH * h + (cc >> 1)) + 2 * t + (cc & 1)] = tot;
           }
           // lambda of the strip's rows over this job's k range = the last column of T (the ones column of Z')
-          if (t == 3) {
-            const double l0 = T[0][QT - 1][1], l1 = T[1][QT - 1][1];
+          if (h == NH - 1 && t == 3) {
+            const double l0 = T[0][QH - 1][1], l1 = T[1][QH - 1][1];
             double* pl = sLam + (par * 4 + sc.jslot[jb]) * PS_LAM + 16 * sp + g;
             pl[0] = l0;
             pl[8] = l1;
+          }
           }
         }
       }

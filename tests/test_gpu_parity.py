@@ -607,9 +607,10 @@ def test_fused_pass_equals_forward_then_backward(impl, N, M, Q, chunk):
 @pytest.mark.parametrize("ks", [0, 1, 2, 4])
 @pytest.mark.parametrize("N,M,Q,chunk", [
     (5, 16, 8, 0), (37, 17, 9, 0), (300, 33, 3, 0), (611, 48, 23, 0), (1500, 50, 20, 0), (2000, 64, 16, 0),
-    (1203, 81, 7, 500), (4099, 100, 20, 0), (3001, 100, 10, 1024), (2500, 112, 22, 0), (900, 97, 17, 0)])
+    (1203, 81, 7, 500), (4099, 100, 20, 0), (3001, 100, 10, 1024), (2500, 112, 22, 0), (900, 97, 17, 0),
+    (2100, 100, 40, 0), (700, 50, 30, 300), (1000, 112, 47, 0), (333, 20, 33, 0)])
 def test_small_inducing_set_kernels(N, M, Q, chunk, ks):
-    """psi2_small.cuh (one CTA holds the whole pair matrix of a row; M <= 112, Q <= 23) against the 64 x 64 block
+    """psi2_small.cuh (one CTA holds the whole pair matrix of a row; M <= 112, Q <= 47) against the 64 x 64 block
     kernels and the oracle: every super-row count, stage-2 width and k split, fewer rows than CTAs, ragged row
     ranges, row chunks, forward / backward / fused."""
     import torch

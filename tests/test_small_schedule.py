@@ -25,8 +25,14 @@ def schedule(M, Q, ks=0, backward=1):
                 kslots=a[97], jsp=a[98:130], jkb=a[130:162], jke=a[162:194], jslot=a[194:226])
 
 
+def qtiles(Q):
+    """8-wide stage-2 column tiles: Q and the ones column; 5 is served by the 6-tile (two halves of 3) kernel."""
+    qt = Q // 8 + 1
+    return 6 if qt == 5 else qt
+
+
 SHAPES = [(1, 1), (7, 3), (16, 8), (17, 9), (33, 3), (48, 23), (50, 20), (64, 16), (81, 7), (97, 17), (100, 10),
-          (100, 20), (104, 23), (112, 22)]
+          (100, 20), (104, 23), (112, 22), (100, 40), (50, 30), (112, 46), (20, 33)]
 
 
 @pytest.mark.parametrize("ks", [0, 1, 2, 4])
@@ -40,6 +46,8 @@ def test_schedule_covers_every_supertile_and_k_step_once(M, Q, ks):
         tiles = sorted(int(sc["su"][w, s]) for w in range(16) for s in range(sc["ns"][w]))
         assert tiles == list(range(NS))                       # every supertile exactly once
         assert sc["ns"].max() <= 2
+        if Q > 23:
+            assert sc["nj"].max() <= 1 and sc["njobs"] <= 16      # wide Q: one job per warp
         if not backward:
             assert sc["njobs"] == 0 and sc["nj"].sum() == 0
             continue
@@ -69,20 +77,20 @@ def test_schedule_covers_every_supertile_and_k_step_once(M, Q, ks):
                 load4[w % 4] += ((4 if vi == 2 else 1) if i == j else vi * vj) * ((Q + 3) // 4)
             for jj in range(sc["nj"][w]):
                 j = sc["jw"][w, jj]
-                load4[w % 4] += (sc["jke"][j] - sc["jkb"][j]) * (2 if 16 * sc["jsp"][j] + 8 < M8 else 1) * (Q // 8 + 1)
+                load4[w % 4] += (sc["jke"][j] - sc["jkb"][j]) * (2 if 16 * sc["jsp"][j] + 8 < M8 else 1) * qtiles(Q)
         if Ms >= 4:
             assert load4.max() <= 1.25 * load4.mean(), load4
 
 
 def test_large_shapes_are_left_to_the_block_kernels():
-    assert schedule(113, 20) is None and schedule(100, 24) is None and schedule(512, 64) is None
+    assert schedule(113, 20) is None and schedule(100, 48) is None and schedule(512, 64) is None
     assert b"block kernels" in load().rgp_psi_last_error()
 
 
 def emulate(M, Q, ks, N, seed=0):
     rng = np.random.default_rng(seed)
     sc = schedule(M, Q, ks, 1)
-    Ms = (M + 15) // 16; Mp16 = 16 * Ms; Qp = (Q // 8 + 1) * 8; qk = (Q + 3) // 4 * 4; M8 = (M + 7) // 8 * 8
+    Ms = (M + 15) // 16; Mp16 = 16 * Ms; Qp = 8 * qtiles(Q); qk = (Q + 3) // 4 * 4; M8 = (M + 7) // 8 * 8
     Z = np.zeros((Mp16, Qp)); Z[:M, :Q] = rng.normal(size=(M, Q))
     Z1 = Z.copy(); Z1[:M, Qp - 1] = 1.0                   # the kernel's shared-memory tile: ones in its last column
     Cm = np.zeros((Mp16, Mp16)); c = rng.normal(size=(M, M)); Cm[:M, :M] = (c + c.T) / 2
@@ -149,7 +157,8 @@ def emulate(M, Q, ks, N, seed=0):
 
 
 @pytest.mark.parametrize("M,Q,ks", [(1, 1, 0), (17, 9, 2), (33, 3, 1), (50, 20, 4), (97, 17, 0), (100, 20, 0),
-                                    (100, 20, 4), (104, 23, 1), (112, 16, 2), (64, 8, 0)])
+                                    (100, 20, 4), (104, 23, 1), (112, 16, 2), (64, 8, 0), (100, 40, 0), (50, 30, 4),
+                                    (36, 33, 0)])
 def test_emulated_data_flow_matches_the_definitions(M, Q, ks):
     e = emulate(M, Q, ks, N=2, seed=M + Q)
     assert max(e[:4]) < 1e-13, e
