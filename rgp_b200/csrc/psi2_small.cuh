@@ -321,22 +321,27 @@ k_psi2_small(int64_t rc, int M, int Q, int Mp, int Ms, int nt, int qk, int QC, i
           auto column = [&](auto kst_c, auto ioff_c, auto two_c, const double* pa, const double* pb, int klo, int khi) {
             constexpr int KST = decltype(kst_c)::value, IOFF = decltype(ioff_c)::value;
             constexpr bool TWO = decltype(two_c)::value;
+            auto kstep = [&](int kk) {
+              const double a0 = pa[kk * KST];
+              double a1 = 0.0;
+              if constexpr (TWO) a1 = pa[kk * KST + IOFF];
+              double bq[QH];
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              if (kk >= klo && kk < khi) {
-                const double a0 = pa[kk * KST];
-                double a1 = 0.0;
-                if constexpr (TWO) a1 = pa[kk * KST + IOFF];
-                double bq[QH];
+              for (int j = 0; j < QH; ++j) bq[j] = pb[kk * 4 * RS + 8 * j];
 #pragma unroll
-                for (int j = 0; j < QH; ++j) bq[j] = pb[kk * 4 * RS + 8 * j];
+              for (int j = 0; j < QH; ++j) dmma(T[0][j][0], T[0][j][1], a0, bq[j]);
+              if constexpr (TWO) {
 #pragma unroll
-                for (int j = 0; j < QH; ++j) dmma(T[0][j][0], T[0][j][1], a0, bq[j]);
-                if constexpr (TWO) {
-#pragma unroll
-                  for (int j = 0; j < QH; ++j) dmma(T[1][j][0], T[1][j][1], a1, bq[j]);
-                }
+                for (int j = 0; j < QH; ++j) dmma(T[1][j][0], T[1][j][1], a1, bq[j]);
               }
+            };
+            if (klo <= 0 && khi >= 4) {            // a whole column: straight-line code, loads of the next k-step overlap the MMAs
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) kstep(kk);
+            } else {
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                if (kk >= klo && kk < khi) kstep(kk);
             }
           };
           using I4 = std::integral_constant<int, 4>;
