@@ -344,7 +344,7 @@ static void small_schedule(int M, int Ms, int QT, int qk, int KS, int JMAX, bool
   sc->kslots = (signed char)kslots;
 }
 
-// small_m: 0 = never, 1 = whenever the shape fits, 2 (default) = when it also saves >= 35 % of the DMMAs
+// small_m: 0 = never, 1 = whenever the shape fits, 2 (default) = where they measured faster (rule below)
 static SmallPlan small_plan(const rgp_psi_ctx* h, const Shape& s) {
   SmallPlan p;
   if (h->small_m == 0) return p;
@@ -352,10 +352,11 @@ static SmallPlan small_plan(const rgp_psi_ctx* h, const Shape& s) {
   int QT = s.Q / 8 + 1;                                 // stage-2 columns: Q and the ones column, in tiles of 8
   if (QT == 5) QT = 6;                                  // Q > 23: two column passes of QT / 2 tiles (4 or 6 tiles)
   if (Ms > PS_MS_MAX || QT > 6) return p;
-  // measured (profiles/small_ab_r02.jsonl): the small kernels win where they compute <= ~0.65 of the block kernels' DMMAs
-  // (M = 100 / 112, M = 33); at M = 50 (0.69) and M = 64 (1.3) the block kernels are as fast or faster
-  if (h->small_m == 2 && small_dmma_per_row(s.M, Ms, QT, s.qk) > 0.65 * block_dmma_per_row(s, s.QC == 64 && s.Q <= 48))
-    return p;
+  // measured (profiles/small_ab_r02.jsonl): with 6 - 7 super rows (M = 81 ... 112) the small kernels win up to ~0.8 of the
+  // block kernels' DMMAs (M = 100 / 112 at Q = 7 ... 46); with fewer rows per CTA pass only when they save more
+  // (M = 33 wins at 0.37; M = 50 ties at 0.69, loses at 0.81; M = 64, Q = 16 loses at 1.3)
+  const double ratio = small_dmma_per_row(s.M, Ms, QT, s.qk) / block_dmma_per_row(s, s.QC == 64 && s.Q <= 48);
+  if (h->small_m == 2 && ratio > (Ms >= 6 ? 0.82 : 0.65)) return p;
   p.ok = true;
   p.Ms = Ms;
   p.Mp16 = 16 * Ms;
@@ -508,7 +509,7 @@ static int backward(rgp_psi_ctx* h, cudaStream_t st, int64_t N, int M, int Q, co
   const size_t p2_count = sp.ok ? (size_t)Rs * sp.Mp16 * sp.Mp16 : (size_t)s.nblocks * R * 4096;
   const int tn_tiles = s.nt * (2 * QC / 64 > 0 ? (2 * QC + 63) / 64 : 1);
   const int splits = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)64, (int64_t)(2 * h->sm_count / std::max(1, tn_tiles)),
-                                                                 (s.rc + 255) / 256}));
+                                                                 (s.rc + 63) / 64}));
   const int nfin = (int)std::min<int64_t>(ceil_div(s.rc, 4), (int64_t)8 * h->sm_count);
   size_t need = bump_size(Q, 8) + bump_size((size_t)Mp * s.RS, 8) + bump_size((size_t)Mp * 2 * QC, 8) +
                 bump_size((size_t)s.nblocks * 4096, 8) + bump_size(s.rc * QC, 8) +
@@ -605,15 +606,15 @@ static int backward(rgp_psi_ctx* h, cudaStream_t st, int64_t N, int M, int Q, co
                dL1 ? L1 : (const double*)nullptr, dL1 ? R1 : (const double*)nullptr,
                dL0 ? dL0 + r0 : (const double*)nullptr, dL0c, dmu + r0 * Q, dS + r0 * Q, part);
     // Gl = lam^T [Mp x rows] . A2 [rows x 2QC]  (split over rows);  GL = L1^T . A1
-    const int sp = (int)std::max<int64_t>(1, std::min<int64_t>(splits, (rows + 255) / 256));
-    dim3 gtn(s.nt, ceil_div(2 * QC, 64), sp);
+    const int nsplit = (int)std::max<int64_t>(1, std::min<int64_t>(splits, (rows + 63) / 64));   // short K per split at small N
+    dim3 gtn(s.nt, ceil_div(2 * QC, 64), nsplit);
     RGP_LAUNCH(h, st, "dz_gemm", (k_gemm<false, false>), gtn, 256, 0, op(lam, 1, Mp, Mp),
                op(A2, 1, 2 * QC, 2 * QC), rows, epi_plain(Gl, 2 * QC, (int64_t)Mp * 2 * QC));
     if (dL1)
       RGP_LAUNCH(h, st, "dz_gemm", (k_gemm<false, false>), gtn, 256, 0, op(L1, 1, Mp, Mp),
                  op(A1, 1, 2 * QC, 2 * QC), rows, epi_plain(GL, 2 * QC, (int64_t)Mp * 2 * QC));
     RGP_LAUNCH(h, st, "final_small", k_final_small, ceil_div((int64_t)M * Q + Q + 1, 128), 128, 0, M, Mp, Q,
-               QC, ZB, Gl, sp, dL1 ? GL : (const double*)nullptr, sp, ACCp, nc, part, nf, dZ, dell, dvar);
+               QC, ZB, Gl, nsplit, dL1 ? GL : (const double*)nullptr, nsplit, ACCp, nc, part, nf, dZ, dell, dvar);
   }
   return 0;
 }

@@ -346,7 +346,19 @@ __global__ void k_final_small(int M, int Mp, int Q, int QC, const double* __rest
         Ga += GL[((int64_t)s * Mp + m) * 2 * QC + q];
         Gb += GL[((int64_t)s * Mp + m) * 2 * QC + QC + q];
       }
-    for (int c = 0; c < ncta; ++c) acc += ACCp[((int64_t)c * Mp + m) * QC + q];
+    {                                            // CTA partials in fixed order, eight loads in flight
+      const double* p = ACCp + (int64_t)m * QC + q;
+      const int64_t stride = (int64_t)Mp * QC;
+      int c = 0;
+      for (; c + 8 <= ncta; c += 8) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = p[(c + u) * stride];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc += v[u];
+      }
+      for (; c < ncta; ++c) acc += p[c * stride];
+    }
     dZ[idx] += 2.0 * ga + 4.0 * z * gb + 2.0 * acc + Ga + 2.0 * z * Gb;
   }
   if (idx < Q + 1) {

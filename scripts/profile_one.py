@@ -1,4 +1,4 @@
-"""Forward + backward three times at one shape, for ncu:  ncu --set full -k regex:k_psi2 -s 2 -c 2 python scripts/profile_one.py [rows M Q]"""
+"""Forward + backward three times at one shape, for ncu:  ncu --set full -k regex:k_psi2 -s 2 -c 2 python scripts/profile_one.py [rows M Q [small_m]]"""
 import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
@@ -13,6 +13,8 @@ Z = torch.randn((M, Q), generator=g, **f64); ell = (torch.rand(Q, generator=g, *
 dL1 = torch.randn((rows, M), generator=g, **f64) / M
 dL2 = torch.randn((M, M), generator=g, **f64) / (M * M)
 dp = DevicePsi(0)
+if len(sys.argv) > 4:
+    dp.handle.set_option("small_m", int(sys.argv[4]))
 for _ in range(3):
     dp.forward(mu, S, Z, ell, 1.3)
     dp.backward(mu, S, Z, ell, 1.3, -0.5, dL1, dL2)
