@@ -1,7 +1,7 @@
 """Shape sweep (configs[4] of BASELINE.json): psi statistics + all gradients at N = 64K ... 16M rows, M = 128 ... 1024,
 Q = 16 ... 128, on 1 / 2 / 4 / 8 GPUs.
 
-    python scripts/sweep.py                                      1 GPU
+    python scripts/sweep.py [--quick | --small]                  1 GPU
     python -m torch.distributed.run --nproc-per-node G ... scripts/sweep.py
 
 N is the TOTAL row count of a point; with G ranks every rank takes its row block (rgp_b200.sharded.row_partition)
@@ -91,6 +91,9 @@ def main():
               (64 * K, 1024, 128), (Mi, 1024, 128),
               (256 * K, 1024, 64), (Mi, 512, 32), (2 * Mi, 64, 64), (Mi, 128, 64),
               (Mi, 100, 20), (Mi, 200, 40), (Mi, 50, 20), (256 * K, 500, 60)]
+    if "--small" in sys.argv:    # the shapes of the reference's own models (small inducing sets) and their neighbours
+        points = [(Mi, 100, 20), (Mi, 100, 10), (Mi, 100, 40), (Mi, 112, 23), (Mi, 50, 20), (Mi, 33, 20), (Mi, 128, 16),
+                  (Mi, 200, 40)]
     if "--quick" in sys.argv:
         points = [p for p in points if p[0] * f_row(p[1], p[2]) < 3e13]
     for N, M, Q in points:
