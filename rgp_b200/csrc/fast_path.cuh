@@ -247,7 +247,7 @@ static int launch_bwd(rgp_psi_ctx* h, cudaStream_t st, const Shape& s, int64_t r
 // ---- small inducing sets (psi2_small.cuh): one CTA holds the whole pair matrix of a row -------------------
 struct SmallPlan {
   bool ok = false;
-  int Ms = 0, Mp16 = 0, QT = 0, KS = 0, JMAX = 1;
+  int Ms = 0, Mp16 = 0, QT = 0, KS = 0, JMAX = 1, warps = PS_WARPS;
   SmallSched fwd, bwd;     // which warp computes which supertiles (forward only) / supertiles and jobs (backward)
 };
 
@@ -282,7 +282,7 @@ static inline double small_dmma_per_row(int M, int Ms, int QT, int qk) {
 // Warp w issues on SM sub-partition w % 4, so the items are dealt greedily (largest first) to the least loaded
 // sub-partition, then to its least loaded warp with a free slot.  Costs are FP64-pipe cycles: 16 per DMMA plus
 // the scalar epilogue / fold work.
-static void small_schedule(int M, int Ms, int QT, int qk, int KS, int JMAX, bool bwd, SmallSched* sc) {
+static void small_schedule(int M, int Ms, int QT, int qk, int KS, int JMAX, int warps, bool bwd, SmallSched* sc) {
   memset(sc, 0, sizeof(*sc));
   const int M8 = (M + 7) & ~7;
   struct Item { double cost; int kind, a, b, c, d; };   // kind 0: supertile index a; kind 1: job (strip a, columns [b, c), slot d)
@@ -320,7 +320,7 @@ static void small_schedule(int M, int Ms, int QT, int qk, int KS, int JMAX, bool
   int njobs = 0;
   for (const Item& it : items) {
     int best = -1;
-    for (int w = 0; w < PS_WARPS; ++w) {
+    for (int w = 0; w < warps; ++w) {
       if (it.kind == 0 ? sc->ns[w] >= PS_S1 : sc->nj[w] >= JMAX) continue;
       if (best < 0 || pload[w & 3] < pload[best & 3] - 1e-9 ||
           (pload[w & 3] < pload[best & 3] + 1e-9 && wload[w] < wload[best] - 1e-9))
@@ -361,11 +361,16 @@ static SmallPlan small_plan(const rgp_psi_ctx* h, const Shape& s) {
   p.Ms = Ms;
   p.Mp16 = 16 * Ms;
   p.QT = QT;
+  // 8-warp CTAs, two per SM (independent barriers), when two of them fit in shared memory and the supertiles fit 16 slots
+  const bool fit8 = Ms <= 5 && small_smem_doubles(Ms, QT, true) * 8 <= 110 * 1024;
+  p.warps = h->small_warps > 0 ? (h->small_warps == 8 && fit8 ? 8 : PS_WARPS) : PS_WARPS;
   p.KS = h->small_ks > 0 ? h->small_ks : (Ms >= 5 ? 2 : 4);   // ~13 ... 16 jobs (measured: profiles/small_ab_r02.jsonl)
-  if (QT > 3) p.KS = std::min(p.KS, PS_WARPS / Ms >= 4 ? 4 : (PS_WARPS / Ms >= 2 ? 2 : 1));   // wide Q: one job per warp
-  p.JMAX = (Ms * p.KS + PS_WARPS - 1) / PS_WARPS;
-  small_schedule(s.M, Ms, QT, s.qk, p.KS, p.JMAX, false, &p.fwd);
-  small_schedule(s.M, Ms, QT, s.qk, p.KS, p.JMAX, true, &p.bwd);
+  const int jmax_allowed = QT > 3 ? 1 : 2;                    // wide Q: one job per warp
+  while (p.KS > 1 && Ms * p.KS > jmax_allowed * p.warps) p.KS /= 2;
+  if (Ms * p.KS > jmax_allowed * p.warps) return SmallPlan();
+  p.JMAX = (Ms * p.KS + p.warps - 1) / p.warps;
+  small_schedule(s.M, Ms, QT, s.qk, p.KS, p.JMAX, p.warps, false, &p.fwd);
+  small_schedule(s.M, Ms, QT, s.qk, p.KS, p.JMAX, p.warps, true, &p.bwd);
   return p;
 }
 
@@ -376,13 +381,13 @@ static int launch_small_qt(rgp_psi_ctx* h, cudaStream_t st, const Shape& s, cons
   const char* name = MODE == 0 ? "psi2_fwd" : (MODE == 1 ? "psi2_bwd" : "psi2_bwd_fused");
   const int smem = small_smem_doubles(p.Ms, QT, MODE != 0) * 8;
   if constexpr (MODE == 0) {
-    RGP_LAUNCH(h, st, name, (k_psi2_small<QT, 0, 1>), Rs, PS_THREADS, smem, rows, s.M, s.Q, s.Mp, p.Ms, s.nt, s.qk,
+    RGP_LAUNCH(h, st, name, (k_psi2_small<QT, 0, 1>), Rs, 32 * p.warps, smem, rows, s.M, s.Q, s.Mp, p.Ms, s.nt, s.qk,
                s.QC, s.RS, p.fwd, Zt, Ct, w, HP, lam, Wq, ACCp, P2s);
   } else if (p.JMAX == 1 || QT > 3) {
-    RGP_LAUNCH(h, st, name, (k_psi2_small<QT, MODE, 1>), Rs, PS_THREADS, smem, rows, s.M, s.Q, s.Mp, p.Ms, s.nt,
+    RGP_LAUNCH(h, st, name, (k_psi2_small<QT, MODE, 1>), Rs, 32 * p.warps, smem, rows, s.M, s.Q, s.Mp, p.Ms, s.nt,
                s.qk, s.QC, s.RS, p.bwd, Zt, Ct, w, HP, lam, Wq, ACCp, P2s);
   } else if constexpr (QT <= 3) {
-    RGP_LAUNCH(h, st, name, (k_psi2_small<QT, MODE, 2>), Rs, PS_THREADS, smem, rows, s.M, s.Q, s.Mp, p.Ms, s.nt,
+    RGP_LAUNCH(h, st, name, (k_psi2_small<QT, MODE, 2>), Rs, 32 * p.warps, smem, rows, s.M, s.Q, s.Mp, p.Ms, s.nt,
                s.qk, s.QC, s.RS, p.bwd, Zt, Ct, w, HP, lam, Wq, ACCp, P2s);
   }
   return 0;
@@ -399,8 +404,8 @@ static int launch_small(rgp_psi_ctx* h, cudaStream_t st, const Shape& s, const S
   return launch_small_qt<6, MODE>(h, st, s, p, rows, Rs, Zt, Ct, w, HP, lam, Wq, ACCp, P2s);
 }
 
-static inline int small_grid(const rgp_psi_ctx* h, int64_t rows) {
-  return (int)std::max<int64_t>(1, std::min<int64_t>(h->sm_count, rows));
+static inline int small_grid(const rgp_psi_ctx* h, const SmallPlan& p, int64_t rows) {
+  return (int)std::max<int64_t>(1, std::min<int64_t>((p.warps == 8 ? 2 : 1) * h->sm_count, rows));
 }
 
 // lam[0] += sum_{g>=1} lam[g]  (and the same for Wq); only launched when G > 1
@@ -437,7 +442,7 @@ static int forward(rgp_psi_ctx* h, cudaStream_t st, int64_t N, int M, int Q, con
   pick_grid(s.rc, s.nblocks, 2 * h->sm_count, &R, &G);
   const int QC = s.QC;
   const SmallPlan sp = small_plan(h, s);
-  const int Rs = small_grid(h, s.rc);
+  const int Rs = small_grid(h, sp, s.rc);
   const size_t p2_count = sp.ok ? (size_t)Rs * sp.Mp16 * sp.Mp16 : (size_t)s.nblocks * R * 4096;
   size_t need = bump_size(Q, 8) + bump_size((size_t)s.Mp * s.RS, 8) + bump_size((size_t)s.Mp * 2 * QC, 8) +
                 bump_size(p2_count, 8) + bump_size(s.rc * QC, 8) +
@@ -471,7 +476,7 @@ static int forward(rgp_psi_ctx* h, cudaStream_t st, int64_t N, int M, int Q, con
       RGP_TRY(gemm_nt(h, st, "psi1_fwd", s, rows, A1, ZB, e));
     }
     if (sp.ok) {
-      const int Rr = std::min(Rs, small_grid(h, rows));
+      const int Rr = std::min(Rs, small_grid(h, sp, rows));
       RGP_TRY(launch_small<0>(h, st, s, sp, rows, Rr, Zt, nullptr, w, HP, nullptr, nullptr, nullptr, P2p));
       RGP_LAUNCH(h, st, "psi2_reduce", k_psi2_reduce_small, ceil_div((int64_t)M * M, 256), 256, 0, M, sp.Mp16, Rr,
                  variance * variance, P2p, (chunk > 0 || h->accumulate) ? 1 : 0, psi2);
@@ -500,7 +505,7 @@ static int backward(rgp_psi_ctx* h, cudaStream_t st, int64_t N, int M, int Q, co
   Shape s = make_shape(h, N, M, Q);
   if (use_pipelined(h, s.QC, Q, psi2_out != nullptr)) s.RS = s.QC + 4;   // the Z' tile layout follows the kernel
   const SmallPlan sp = small_plan(h, s);
-  const int Rs = small_grid(h, s.rc);
+  const int Rs = small_grid(h, sp, s.rc);
   int R, G;
   pick_grid(s.rc, s.nblocks, h->sm_count, &R, &G);
   if (sp.ok) G = 1;
@@ -556,7 +561,7 @@ static int backward(rgp_psi_ctx* h, cudaStream_t st, int64_t N, int M, int Q, co
     pick_grid(rows, s.nblocks, h->sm_count, &Rc, &Gc);
     Rc = std::min(Rc, R);
     Gc = std::min(Gc, G);
-    const int Rr = std::min(Rs, small_grid(h, rows));
+    const int Rr = std::min(Rs, small_grid(h, sp, rows));
     const int nc = sp.ok ? Rr * sp.bwd.kslots : Rc * Gc;
     RGP_CUDA(cudaMemsetAsync(lam, 0, sizeof(double) * (size_t)Gc * rows * Mp, st));
     RGP_CUDA(cudaMemsetAsync(Wq, 0, sizeof(double) * (size_t)Gc * rows * QC, st));

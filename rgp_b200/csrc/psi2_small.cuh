@@ -20,7 +20,9 @@
 //             lambda_n, W_n are written once with plain stores, in a fixed order (deterministic, no atomics).
 //
 // Which warp computes which supertiles and jobs is a small table made on the host (SmallSched, fast_path.cuh): it
-// balances the FP64-pipe load per SM sub-partition (warp w runs on sub-partition w % 4).
+// balances the FP64-pipe load per SM sub-partition (warp w runs on sub-partition w % 4).  With at most 5 super rows
+// (M <= 80) the CTA has 8 warps instead of 16 and two CTAs share an SM: their barriers are independent, so one CTA's
+// stage 2 overlaps the other's stage 1.
 // The per-row vectors (ws[Qp], H[Mp16]) arrive by TMA bulk copies into a two-slot ring (SmallRowStage), as in the
 // block kernels.  The forward-only kernel needs a barrier only when a ring slot is recycled (every PS_VR rows).
 #pragma once
@@ -154,12 +156,12 @@ k_psi2_small(int64_t rc, int M, int Q, int Mp, int Ms, int nt, int qk, int QC, i
   rv.htile = rc * 64;
   rv.QC = QC; rv.Qp = Qp; rv.Mp16 = Mp16; rv.VB = VB;
   rv.init_barriers(tid);
-  for (int idx = tid; idx < Mp16 * Qp; idx += PS_THREADS) {
+  for (int idx = tid; idx < Mp16 * Qp; idx += blockDim.x) {
     const int m = idx / Qp, c = idx - m * Qp;
     sZ[m * RS + c] = c < Q ? Zt[(size_t)m * RSz + c] : ((c == Qp - 1 && m < M) ? 1.0 : 0.0);   // last column: ones (lambda)
   }
   if constexpr (BWD)
-    for (int idx = tid; idx < 2 * 4 * PS_LAM; idx += PS_THREADS) sLam[idx] = 0.0;   // (slot, strip) pairs without a job stay 0
+    for (int idx = tid; idx < 2 * 4 * PS_LAM; idx += blockDim.x) sLam[idx] = 0.0;   // (slot, strip) pairs without a job stay 0
 
   // this warp's supertiles
   const int ns = sc.ns[wid];

@@ -255,6 +255,9 @@ int rgp_psi_set_option(rgp_psi_handle_t h, const char* key, int64_t value) {
     if (value != 0 && value != 1 && value != 2 && value != 4)
       return set_error(RGP_PSI_ERR_INVALID, "small_ks must be 0, 1, 2 or 4");
     h->small_ks = (int)value;
+  } else if (!strcmp(key, "small_warps")) {
+    if (value != 0 && value != 8 && value != 16) return set_error(RGP_PSI_ERR_INVALID, "small_warps must be 0, 8 or 16");
+    h->small_warps = (int)value;
 #ifdef RGP_DEBUG
   // experiment knobs: they make kernels skip work (wrong results) or change occupancy, so the
   // production library does not know them

@@ -513,7 +513,7 @@ def test_options_are_validated():
     h = Handle(0)
     h._ensure()
     # the experiment knobs of round 1 (debug_skip, trace_ptr, fwd_smem_pad) are not options of the production library
-    for key, val in (("impl", 7), ("bwd_pipe", 3), ("small_m", 3), ("small_ks", 3), ("row_chunk", -1), ("no_such_option", 1), ("debug_skip", 1),
+    for key, val in (("impl", 7), ("bwd_pipe", 3), ("small_m", 3), ("small_ks", 3), ("small_warps", 4), ("row_chunk", -1), ("no_such_option", 1), ("debug_skip", 1),
                      ("trace_ptr", 4096), ("fwd_smem_pad", 1024), ("bwd_warps", 16)):
         with pytest.raises(PsiError):
             h.set_option(key, val)
@@ -618,6 +618,7 @@ def test_small_inducing_set_kernels(N, M, Q, chunk, ks):
     small, block = DevicePsi(0, impl=0), DevicePsi(0, impl=0)
     small.handle.set_option("small_m", 1)
     small.handle.set_option("small_ks", ks)
+    small.handle.set_option("small_warps", 8 if (N + ks) % 2 else 16)     # both CTA sizes over the parameter grid
     block.handle.set_option("small_m", 0)
     if chunk:
         small.handle.set_option("row_chunk", chunk)
