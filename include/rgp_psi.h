@@ -117,12 +117,15 @@ int rgp_psi_backward_dev(rgp_psi_handle_t h, void* stream, int64_t N, int M, int
 int rgp_host_digest(const void* data, int64_t nbytes, int threads, uint64_t out[2]);
 
 /* Work table of the small-inducing-set kernels (pure host code; introspection for tests and DESIGN.md).
- * For shape (M, Q), stage-2 k split `ks` (0 = default) and pass (`backward` 0 / 1) writes, as signed bytes,
- *   [0..15]  supertiles per warp        [16..47]  their indices, 2 per warp (row-major upper triangle of the
- *   16 x 16 supertile grid)             [48..63]  jobs per warp          [64..95]  their job indices, 2 per warp
- *   [96] number of jobs  [97] k slots   [98..129] strip of job j         [130..161] first k-step   [162..193] end
- *   k-step   [194..225] accumulator slot
- * and returns the number of bytes (226), or -1 (message set) when the small kernels do not serve the shape
+ * For shape (M, Q), stage-2 k split `ks` (0 = default) and pass (`backward`: 0 forward only, 1 backward only,
+ * 2 backward + Psi2) writes, as signed bytes,
+ *   [0..15]  supertiles per warp        [16..79]  their indices, 4 per warp (row-major upper triangle of the
+ *   16 x 16 supertile grid)             [80..95]  jobs per warp          [96..127] their job indices, 2 per warp
+ *   [128] number of jobs  [129] k slots [130..161] strip of job j        [162..193] first k-step   [194..225] end
+ *   k-step   [226..257] accumulator slot
+ *   [258] warps per CTA (16: one CTA per SM, 8: two)   [259] supertile slots per warp   [260] buffers of L (2: one
+ *   barrier per row, 1: two)   [261] job slots per warp
+ * and returns the number of bytes (262), or -1 (message set) when the small kernels do not serve the shape
  * or `out_bytes` is too small. */
 int rgp_psi_small_schedule(int M, int Q, int ks, int backward, signed char* out, int out_bytes);
 

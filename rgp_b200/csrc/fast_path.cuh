@@ -42,28 +42,17 @@ static int init_qc() {
 }
 
 template <int QT>
-static int init_small_wide() {      // Q > 23: one job per warp
-  RGP_CUDA(cudaFuncSetAttribute((k_psi2_small<QT, 0, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                small_smem_doubles(PS_MS_MAX, QT, false) * 8));
-  RGP_CUDA(cudaFuncSetAttribute((k_psi2_small<QT, 1, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                small_smem_doubles(PS_MS_MAX, QT, true) * 8));
-  RGP_CUDA(cudaFuncSetAttribute((k_psi2_small<QT, 2, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                small_smem_doubles(PS_MS_MAX, QT, true) * 8));
-  return 0;
-}
-
-template <int QT>
 static int init_small() {
-  RGP_CUDA(cudaFuncSetAttribute((k_psi2_small<QT, 0, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                small_smem_doubles(PS_MS_MAX, QT, false) * 8));
-  RGP_CUDA(cudaFuncSetAttribute((k_psi2_small<QT, 1, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                small_smem_doubles(PS_MS_MAX, QT, true) * 8));
-  RGP_CUDA(cudaFuncSetAttribute((k_psi2_small<QT, 1, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                small_smem_doubles(PS_MS_MAX, QT, true) * 8));
-  RGP_CUDA(cudaFuncSetAttribute((k_psi2_small<QT, 2, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                small_smem_doubles(PS_MS_MAX, QT, true) * 8));
-  RGP_CUDA(cudaFuncSetAttribute((k_psi2_small<QT, 2, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                small_smem_doubles(PS_MS_MAX, QT, true) * 8));
+  constexpr int fwd = small_smem_doubles(PS_MS_MAX, QT, false) * 8, bwd = small_smem_doubles(PS_MS_MAX, QT, true) * 8;
+  RGP_CUDA(cudaFuncSetAttribute((k_psi2_small<QT, 0, 1, 4, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, fwd));
+  RGP_CUDA(cudaFuncSetAttribute((k_psi2_small<QT, 1, 1, 2, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, bwd));
+  RGP_CUDA(cudaFuncSetAttribute((k_psi2_small<QT, 2, 1, 2, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, bwd));
+  if constexpr (QT <= 3) {     // two jobs per warp and the single-buffer variant exist for Q <= 23 only
+    RGP_CUDA(cudaFuncSetAttribute((k_psi2_small<QT, 1, 2, 2, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, bwd));
+    RGP_CUDA(cudaFuncSetAttribute((k_psi2_small<QT, 2, 2, 2, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, bwd));
+    RGP_CUDA(cudaFuncSetAttribute((k_psi2_small<QT, 1, 1, 4, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  small_smem_doubles(PS_MS_MAX, QT, true, 1) * 8));
+  }
   return 0;
 }
 
@@ -71,8 +60,8 @@ static int init(rgp_psi_ctx*) {
   RGP_TRY(init_small<1>());
   RGP_TRY(init_small<2>());
   RGP_TRY(init_small<3>());
-  RGP_TRY(init_small_wide<4>());
-  RGP_TRY(init_small_wide<6>());
+  RGP_TRY(init_small<4>());
+  RGP_TRY(init_small<6>());
   RGP_TRY(init_qc<16>());
   RGP_TRY(init_qc<32>());
   RGP_TRY(init_qc<64>());
@@ -245,10 +234,16 @@ static int launch_bwd(rgp_psi_ctx* h, cudaStream_t st, const Shape& s, int64_t r
 }
 
 // ---- small inducing sets (psi2_small.cuh): one CTA holds the whole pair matrix of a row -------------------
+// One kernel configuration of the small family: CTA size, supertile slots per warp, buffers of L, k split, and the
+// work table (which warp computes which supertiles / jobs).
+struct SmallVariant {
+  int warps = PS_WARPS, s1 = 2, nbuf = 2, KS = 1, JMAX = 1;
+  SmallSched sched;
+};
 struct SmallPlan {
   bool ok = false;
-  int Ms = 0, Mp16 = 0, QT = 0, KS = 0, JMAX = 1, warps = PS_WARPS;
-  SmallSched fwd, bwd;     // which warp computes which supertiles (forward only) / supertiles and jobs (backward)
+  int Ms = 0, Mp16 = 0, QT = 0;
+  SmallVariant fwd, bwd, fused;     // forward only / backward only / backward + Psi2
 };
 
 // DMMAs per row of the 64 x 64 block kernels / of the small kernel (both passes), used to choose between them
@@ -282,7 +277,7 @@ static inline double small_dmma_per_row(int M, int Ms, int QT, int qk) {
 // Warp w issues on SM sub-partition w % 4, so the items are dealt greedily (largest first) to the least loaded
 // sub-partition, then to its least loaded warp with a free slot.  Costs are FP64-pipe cycles: 16 per DMMA plus
 // the scalar epilogue / fold work.
-static void small_schedule(int M, int Ms, int QT, int qk, int KS, int JMAX, int warps, bool bwd, SmallSched* sc) {
+static void small_schedule(int M, int Ms, int QT, int qk, int KS, int JMAX, int warps, int s1cap, bool bwd, SmallSched* sc) {
   memset(sc, 0, sizeof(*sc));
   const int M8 = (M + 7) & ~7;
   struct Item { double cost; int kind, a, b, c, d; };   // kind 0: supertile index a; kind 1: job (strip a, columns [b, c), slot d)
@@ -321,7 +316,7 @@ static void small_schedule(int M, int Ms, int QT, int qk, int KS, int JMAX, int 
   for (const Item& it : items) {
     int best = -1;
     for (int w = 0; w < warps; ++w) {
-      if (it.kind == 0 ? sc->ns[w] >= PS_S1 : sc->nj[w] >= JMAX) continue;
+      if (it.kind == 0 ? sc->ns[w] >= s1cap : sc->nj[w] >= JMAX) continue;
       if (best < 0 || pload[w & 3] < pload[best & 3] - 1e-9 ||
           (pload[w & 3] < pload[best & 3] + 1e-9 && wload[w] < wload[best] - 1e-9))
         best = w;
@@ -353,24 +348,42 @@ static SmallPlan small_plan(const rgp_psi_ctx* h, const Shape& s) {
   if (QT == 5) QT = 6;                                  // Q > 23: two column passes of QT / 2 tiles (4 or 6 tiles)
   if (Ms > PS_MS_MAX || QT > 6) return p;
   // measured (profiles/small_ab_r02.jsonl): with 6 - 7 super rows (M = 81 ... 112) the small kernels win up to ~0.8 of the
-  // block kernels' DMMAs (M = 100 / 112 at Q = 7 ... 46); with fewer rows per CTA pass only when they save more
-  // (M = 33 wins at 0.37; M = 50 ties at 0.69, loses at 0.81; M = 64, Q = 16 loses at 1.3)
+  // block kernels' DMMAs (M = 100 / 112 at Q = 7 ... 46); with fewer super rows only when they save more
+  // (M = 33, Q = 20 wins at 0.37 and M = 50, Q = 20 at 0.69; M = 50, Q = 40 loses at 0.81, M = 64, Q = 16 at 1.3)
   const double ratio = small_dmma_per_row(s.M, Ms, QT, s.qk) / block_dmma_per_row(s, s.QC == 64 && s.Q <= 48);
-  if (h->small_m == 2 && ratio > (Ms >= 6 ? 0.82 : 0.65)) return p;
+  if (h->small_m == 2 && ratio > (Ms >= 6 ? 0.82 : 0.72)) return p;
   p.ok = true;
   p.Ms = Ms;
   p.Mp16 = 16 * Ms;
   p.QT = QT;
-  // 8-warp CTAs, two per SM (independent barriers), when two of them fit in shared memory and the supertiles fit 16 slots
-  const bool fit8 = Ms <= 5 && small_smem_doubles(Ms, QT, true) * 8 <= 110 * 1024;
-  p.warps = h->small_warps > 0 ? (h->small_warps == 8 && fit8 ? 8 : PS_WARPS) : PS_WARPS;
-  p.KS = h->small_ks > 0 ? h->small_ks : (Ms >= 5 ? 2 : 4);   // ~13 ... 16 jobs (measured: profiles/small_ab_r02.jsonl)
-  const int jmax_allowed = QT > 3 ? 1 : 2;                    // wide Q: one job per warp
-  while (p.KS > 1 && Ms * p.KS > jmax_allowed * p.warps) p.KS /= 2;
-  if (Ms * p.KS > jmax_allowed * p.warps) return SmallPlan();
-  p.JMAX = (Ms * p.KS + p.warps - 1) / p.warps;
-  small_schedule(s.M, Ms, QT, s.qk, p.KS, p.JMAX, p.warps, false, &p.fwd);
-  small_schedule(s.M, Ms, QT, s.qk, p.KS, p.JMAX, p.warps, true, &p.bwd);
+  // Variants (measured in profiles/small_ab_r02.jsonl; option small_warps = 16 / 8 forces one family for A/B runs):
+  //  * 16 warps, one CTA per SM, L double-buffered (one barrier per row): serves everything;
+  //  * 8 warps, two CTAs per SM with independent barriers, L double-buffered: when two CTAs fit (M <= 64 ... 80);
+  //  * 8 warps, two CTAs per SM, L single-buffered (two barriers per row, the other CTA fills the gaps): backward-only
+  //    pass at Q <= 23 when even the single buffer is what lets two CTAs fit (M = 81 ... 112);
+  //  * forward only (no L): always 8 warps, two CTAs per SM.
+  const int want = h->small_warps;
+  const int half_sm = 113 * 1024;
+  auto make = [&](SmallVariant* v, int mode) -> bool {
+    const bool bwd = mode != 0;
+    v->warps = PS_WARPS; v->s1 = 2; v->nbuf = 2;
+    if (want != 16) {
+      if (mode == 0) { v->warps = 8; v->s1 = 4; }
+      else if (Ms <= 5 && small_smem_doubles(Ms, QT, true, 2) * 8 <= half_sm) { v->warps = 8; v->s1 = 2; }
+      else if (mode == 1 && QT <= 3 && small_smem_doubles(Ms, QT, true, 1) * 8 <= half_sm && (want == 8 || Ms >= 6)) {
+        v->warps = 8; v->s1 = 4; v->nbuf = 1;
+      }
+    }
+    if (Ms * (Ms + 1) / 2 > v->s1 * v->warps) { v->warps = PS_WARPS; v->s1 = 2; v->nbuf = 2; }
+    const int jmax_allowed = (QT > 3 || v->warps == 8) ? 1 : 2;     // one job per warp for wide Q and in the 8-warp CTAs
+    v->KS = h->small_ks > 0 ? h->small_ks : (Ms >= 5 ? 2 : 4);      // ~13 ... 16 jobs per row with 16 warps
+    while (v->KS > 1 && Ms * v->KS > jmax_allowed * v->warps) v->KS /= 2;
+    if (bwd && Ms * v->KS > jmax_allowed * v->warps) return false;
+    v->JMAX = std::max(1, (Ms * v->KS + v->warps - 1) / v->warps);
+    small_schedule(s.M, Ms, QT, s.qk, v->KS, v->JMAX, v->warps, v->s1, bwd, &v->sched);
+    return true;
+  };
+  if (!make(&p.fwd, 0) || !make(&p.bwd, 1) || !make(&p.fused, 2)) return SmallPlan();
   return p;
 }
 
@@ -379,17 +392,19 @@ static int launch_small_qt(rgp_psi_ctx* h, cudaStream_t st, const Shape& s, cons
                            const double* Zt, const double* Ct, const double* w, const double* HP, double* lam,
                            double* Wq, double* ACCp, double* P2s) {
   const char* name = MODE == 0 ? "psi2_fwd" : (MODE == 1 ? "psi2_bwd" : "psi2_bwd_fused");
-  const int smem = small_smem_doubles(p.Ms, QT, MODE != 0) * 8;
+  const SmallVariant& v = MODE == 0 ? p.fwd : (MODE == 1 ? p.bwd : p.fused);
+  const int smem = small_smem_doubles(p.Ms, QT, MODE != 0, v.nbuf) * 8;
+#define RGP_SMALL_ARGS rows, s.M, s.Q, s.Mp, p.Ms, s.nt, s.qk, s.QC, s.RS, v.sched, Zt, Ct, w, HP, lam, Wq, ACCp, P2s
   if constexpr (MODE == 0) {
-    RGP_LAUNCH(h, st, name, (k_psi2_small<QT, 0, 1>), Rs, 32 * p.warps, smem, rows, s.M, s.Q, s.Mp, p.Ms, s.nt, s.qk,
-               s.QC, s.RS, p.fwd, Zt, Ct, w, HP, lam, Wq, ACCp, P2s);
-  } else if (p.JMAX == 1 || QT > 3) {
-    RGP_LAUNCH(h, st, name, (k_psi2_small<QT, MODE, 1>), Rs, 32 * p.warps, smem, rows, s.M, s.Q, s.Mp, p.Ms, s.nt,
-               s.qk, s.QC, s.RS, p.bwd, Zt, Ct, w, HP, lam, Wq, ACCp, P2s);
+    RGP_LAUNCH(h, st, name, (k_psi2_small<QT, 0, 1, 4, 2>), Rs, 32 * v.warps, smem, RGP_SMALL_ARGS);
+  } else if (v.nbuf == 1) {
+    if constexpr (MODE == 1 && QT <= 3) RGP_LAUNCH(h, st, name, (k_psi2_small<QT, 1, 1, 4, 1>), Rs, 32 * v.warps, smem, RGP_SMALL_ARGS);
+  } else if (v.JMAX == 1 || QT > 3) {
+    RGP_LAUNCH(h, st, name, (k_psi2_small<QT, MODE, 1, 2, 2>), Rs, 32 * v.warps, smem, RGP_SMALL_ARGS);
   } else if constexpr (QT <= 3) {
-    RGP_LAUNCH(h, st, name, (k_psi2_small<QT, MODE, 2>), Rs, 32 * p.warps, smem, rows, s.M, s.Q, s.Mp, p.Ms, s.nt,
-               s.qk, s.QC, s.RS, p.bwd, Zt, Ct, w, HP, lam, Wq, ACCp, P2s);
+    RGP_LAUNCH(h, st, name, (k_psi2_small<QT, MODE, 2, 2, 2>), Rs, 32 * v.warps, smem, RGP_SMALL_ARGS);
   }
+#undef RGP_SMALL_ARGS
   return 0;
 }
 
@@ -404,8 +419,8 @@ static int launch_small(rgp_psi_ctx* h, cudaStream_t st, const Shape& s, const S
   return launch_small_qt<6, MODE>(h, st, s, p, rows, Rs, Zt, Ct, w, HP, lam, Wq, ACCp, P2s);
 }
 
-static inline int small_grid(const rgp_psi_ctx* h, const SmallPlan& p, int64_t rows) {
-  return (int)std::max<int64_t>(1, std::min<int64_t>((p.warps == 8 ? 2 : 1) * h->sm_count, rows));
+static inline int small_grid(const rgp_psi_ctx* h, const SmallVariant& v, int64_t rows) {
+  return (int)std::max<int64_t>(1, std::min<int64_t>((v.warps == 8 ? 2 : 1) * h->sm_count, rows));
 }
 
 // lam[0] += sum_{g>=1} lam[g]  (and the same for Wq); only launched when G > 1
@@ -442,7 +457,7 @@ static int forward(rgp_psi_ctx* h, cudaStream_t st, int64_t N, int M, int Q, con
   pick_grid(s.rc, s.nblocks, 2 * h->sm_count, &R, &G);
   const int QC = s.QC;
   const SmallPlan sp = small_plan(h, s);
-  const int Rs = small_grid(h, sp, s.rc);
+  const int Rs = small_grid(h, sp.fwd, s.rc);
   const size_t p2_count = sp.ok ? (size_t)Rs * sp.Mp16 * sp.Mp16 : (size_t)s.nblocks * R * 4096;
   size_t need = bump_size(Q, 8) + bump_size((size_t)s.Mp * s.RS, 8) + bump_size((size_t)s.Mp * 2 * QC, 8) +
                 bump_size(p2_count, 8) + bump_size(s.rc * QC, 8) +
@@ -476,7 +491,7 @@ static int forward(rgp_psi_ctx* h, cudaStream_t st, int64_t N, int M, int Q, con
       RGP_TRY(gemm_nt(h, st, "psi1_fwd", s, rows, A1, ZB, e));
     }
     if (sp.ok) {
-      const int Rr = std::min(Rs, small_grid(h, sp, rows));
+      const int Rr = std::min(Rs, small_grid(h, sp.fwd, rows));
       RGP_TRY(launch_small<0>(h, st, s, sp, rows, Rr, Zt, nullptr, w, HP, nullptr, nullptr, nullptr, P2p));
       RGP_LAUNCH(h, st, "psi2_reduce", k_psi2_reduce_small, ceil_div((int64_t)M * M, 256), 256, 0, M, sp.Mp16, Rr,
                  variance * variance, P2p, (chunk > 0 || h->accumulate) ? 1 : 0, psi2);
@@ -505,12 +520,13 @@ static int backward(rgp_psi_ctx* h, cudaStream_t st, int64_t N, int M, int Q, co
   Shape s = make_shape(h, N, M, Q);
   if (use_pipelined(h, s.QC, Q, psi2_out != nullptr)) s.RS = s.QC + 4;   // the Z' tile layout follows the kernel
   const SmallPlan sp = small_plan(h, s);
-  const int Rs = small_grid(h, sp, s.rc);
+  const SmallVariant& sv = psi2_out ? sp.fused : sp.bwd;
+  const int Rs = small_grid(h, sv, s.rc);
   int R, G;
   pick_grid(s.rc, s.nblocks, h->sm_count, &R, &G);
   if (sp.ok) G = 1;
   const int QC = s.QC, Mp = s.Mp;
-  const int ncta = sp.ok ? Rs * sp.bwd.kslots : R * G;
+  const int ncta = sp.ok ? Rs * sv.sched.kslots : R * G;
   const size_t p2_count = sp.ok ? (size_t)Rs * sp.Mp16 * sp.Mp16 : (size_t)s.nblocks * R * 4096;
   const int tn_tiles = s.nt * (2 * QC / 64 > 0 ? (2 * QC + 63) / 64 : 1);
   const int splits = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)64, (int64_t)(2 * h->sm_count / std::max(1, tn_tiles)),
@@ -561,8 +577,8 @@ static int backward(rgp_psi_ctx* h, cudaStream_t st, int64_t N, int M, int Q, co
     pick_grid(rows, s.nblocks, h->sm_count, &Rc, &Gc);
     Rc = std::min(Rc, R);
     Gc = std::min(Gc, G);
-    const int Rr = std::min(Rs, small_grid(h, sp, rows));
-    const int nc = sp.ok ? Rr * sp.bwd.kslots : Rc * Gc;
+    const int Rr = std::min(Rs, small_grid(h, sv, rows));
+    const int nc = sp.ok ? Rr * sv.sched.kslots : Rc * Gc;
     RGP_CUDA(cudaMemsetAsync(lam, 0, sizeof(double) * (size_t)Gc * rows * Mp, st));
     RGP_CUDA(cudaMemsetAsync(Wq, 0, sizeof(double) * (size_t)Gc * rows * QC, st));
     RGP_CUDA(cudaMemsetAsync(ACCp, 0, sizeof(double) * (size_t)nc * Mp * QC, st));

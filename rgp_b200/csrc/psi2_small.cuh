@@ -24,7 +24,7 @@
 // (M <= 80) the CTA has 8 warps instead of 16 and two CTAs share an SM: their barriers are independent, so one CTA's
 // stage 2 overlaps the other's stage 1.
 // The per-row vectors (ws[Qp], H[Mp16]) arrive by TMA bulk copies into a two-slot ring (SmallRowStage), as in the
-// block kernels.  The forward-only kernel needs a barrier only when a ring slot is recycled (every PS_VR rows).
+// block kernels.  The forward-only kernel needs a barrier only when a ring slot is recycled (every 4 rows).
 #pragma once
 #include <type_traits>
 
@@ -36,10 +36,12 @@ namespace fast {
 constexpr int PS_THREADS = 512;
 constexpr int PS_WARPS = PS_THREADS / 32;
 constexpr int PS_MS_MAX = 7;      // 16-row super rows: M <= 112
-constexpr int PS_S1 = 2;          // supertile slots per warp (28 supertiles <= 2 * 16)
-constexpr int PS_VR = 4;          // rows per TMA batch
+constexpr int PS_S1 = 4;          // supertile slots per warp in the work table (kernels use 2 with 16 warps, 4 with 8 warps)
 constexpr int PS_JOBS = 32;       // job list length
-__host__ __device__ constexpr int PS_JOBS_OF(int QT) { return QT > 3 ? 16 : 32; }   // jobs per row (wide Q: one per warp)
+// jobs per row that get a partial slot (wide Q and the single-buffer variant: one per warp)
+__host__ __device__ constexpr int PS_JOBS_OF(int QT, int nbuf = 2) { return (QT > 3 || nbuf == 1) ? 16 : 32; }
+// rows per TMA batch (the single-buffer variant has two CTAs per SM and half the ring)
+__host__ __device__ constexpr int PS_VR_OF(int nbuf) { return nbuf == 1 ? 2 : 4; }
 constexpr int PS_ST = 320;        // doubles per packed supertile: 16 rows x stride 20
 constexpr int PS_QT_MAX = 6;
 constexpr int PS_LAM = 16 * PS_MS_MAX;   // lambda partials: [parity][k slot <= 4][PS_LAM]
@@ -54,10 +56,10 @@ struct SmallSched {
 };
 
 // shared-memory size in doubles (host and device agree through this one function)
-__host__ __device__ constexpr int small_smem_doubles(int Ms, int QT, bool bwd) {
+__host__ __device__ constexpr int small_smem_doubles(int Ms, int QT, bool bwd, int nbuf = 2) {
   const int Mp16 = 16 * Ms, Qp = 8 * QT;
-  int d = Mp16 * (Qp + 4) + 2 * PS_VR * (Qp + Mp16) + 258;
-  if (bwd) d += 2 * PS_JOBS_OF(QT) * Qp + 2 * 4 * PS_LAM + 2 * (Ms * (Ms + 1) / 2) * PS_ST;
+  int d = Mp16 * (Qp + 4) + 2 * PS_VR_OF(nbuf) * (Qp + Mp16) + 258;
+  if (bwd) d += nbuf * PS_JOBS_OF(QT, nbuf) * Qp + nbuf * 4 * PS_LAM + nbuf * (Ms * (Ms + 1) / 2) * PS_ST;
   return d;
 }
 
@@ -70,6 +72,7 @@ struct SmallRowStage {
   const double* wrow = nullptr;
   const double* hp = nullptr;
   int64_t htile = 0;          // doubles between two 64-wide tiles of HP
+  int vr = 4;                 // rows per batch
   int QC = 0, Qp = 0, Mp16 = 0, VB = 0;   // the ring slot of a row is [ws (Qp) | H (Mp16)]; min(Qp, QC) of ws are copied
 
   RGP_DEVINL void init_barriers(int tid) {
@@ -81,15 +84,15 @@ struct SmallRowStage {
   }
   RGP_DEVINL void begin(int64_t r0_, int64_t r1_, int tid) {
     r0 = r0_; r1 = r1_;
-    nb = r1 > r0 ? (r1 - r0 + PS_VR - 1) / PS_VR : 0;
+    nb = r1 > r0 ? (r1 - r0 + vr - 1) / vr : 0;
     next = 0;
     if (tid == 0 && nb > 0) issue();
   }
   RGP_DEVINL void issue() {
-    const int64_t n0 = r0 + next * PS_VR;
-    const int rows = (int)((r1 - n0 < PS_VR) ? r1 - n0 : PS_VR);
+    const int64_t n0 = r0 + next * vr;
+    const int rows = (int)((r1 - n0 < vr) ? r1 - n0 : vr);
     const int slot = (int)(next & 1);
-    double* dst = ring + slot * PS_VR * VB;
+    double* dst = ring + slot * vr * VB;
     const int h0 = Mp16 < 64 ? Mp16 : 64, qc = Qp < QC ? Qp : QC;
     mbar_expect_tx(&mbar[slot], (uint32_t)(rows * (qc + Mp16) * 8));
     for (int w = 0; w < rows; ++w) {
@@ -101,15 +104,15 @@ struct SmallRowStage {
   }
   // issuing thread, when every thread has finished all rows < r0 + idx
   RGP_DEVINL void refill(int64_t idx) {
-    while (next < nb && next <= idx / PS_VR + 1 && (next - 1) * PS_VR <= idx) issue();
+    while (next < nb && next <= idx / vr + 1 && (next - 1) * vr <= idx) issue();
   }
   RGP_DEVINL const double* row(int64_t idx) {
-    const int slot = (int)((idx / PS_VR) & 1);
-    if (idx % PS_VR == 0) {
+    const int slot = (int)((idx / vr) & 1);
+    if (idx % vr == 0) {
       mbar_wait(&mbar[slot], (phase_bits >> slot) & 1u);
       phase_bits ^= 1u << slot;
     }
-    return ring + slot * PS_VR * VB + (idx % PS_VR) * VB;
+    return ring + slot * vr * VB + (idx % vr) * VB;
   }
 };
 
@@ -122,7 +125,10 @@ RGP_DEVINL int st_index(int lo, int hi, int Ms) { return lo * Ms - lo * (lo - 1)
 //   ACCp[cta * kslots + slot][Mp][QC]          sum_n ws (L_n Z') over this CTA's rows and one k range (plain stores
 //                                              where a job exists; the buffer is zeroed before the launch)
 //   P2s [cta][Mp16][Mp16]                      sum_n p over this CTA's rows (MODE 0 / 2), full symmetric
-template <int QT, int MODE, int JMAX>
+// S1: supertile slots per warp (2 with 16 warps, 4 with 8 warps).  NBUF: buffers of L.  2 = double-buffered by row parity,
+// one barrier per row.  1 = single buffer and a second barrier per row (L consumed), half the shared memory: two 8-warp
+// CTAs share an SM at M <= 112 and fill each other's barrier and phase gaps (backward-only pass, Q <= 23).
+template <int QT, int MODE, int JMAX, int S1 = 2, int NBUF = 2>
 __global__ void __launch_bounds__(PS_THREADS, 1)
 k_psi2_small(int64_t rc, int M, int Q, int Mp, int Ms, int nt, int qk, int QC, int RSz,
              const __grid_constant__ SmallSched sc,
@@ -136,11 +142,12 @@ k_psi2_small(int64_t rc, int M, int Q, int Mp, int Ms, int nt, int qk, int QC, i
   const int Mp16 = 16 * Ms, VB = Qp + Mp16, M8 = (M + 7) & ~7, NS = Ms * (Ms + 1) / 2;
   extern __shared__ __align__(16) double smem[];
   double* sZ = smem;                         // [Mp16][RS]
-  double* sV = sZ + Mp16 * RS;               // row-vector ring: 2 slots x PS_VR rows x VB
-  double* sT = sV + 2 * PS_VR * VB;          // exp table (256) + 2 mbarriers
+  constexpr int VR = PS_VR_OF(NBUF), JOBS = PS_JOBS_OF(QT, NBUF);
+  double* sV = sZ + Mp16 * RS;               // row-vector ring: 2 slots x VR rows x VB
+  double* sT = sV + 2 * VR * VB;             // exp table (256) + 2 mbarriers
   double* sW = sT + 258;                     // [2][jobs][Qp]      W partials per job, by row parity
-  double* sLam = sW + 2 * PS_JOBS_OF(QT) * Qp;   // [2][4][PS_LAM]  lambda partials per k slot
-  double* sL = sLam + 2 * 4 * PS_LAM;        // [2][NS][PS_ST]     packed supertiles of L_n, by row parity
+  double* sLam = sW + NBUF * JOBS * Qp;      // [NBUF][4][PS_LAM]  lambda partials per k slot
+  double* sL = sLam + NBUF * 4 * PS_LAM;     // [NBUF][NS][PS_ST]  packed supertiles of L_n, by row parity
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, t = lane & 3;
   const int R = gridDim.x;
@@ -154,29 +161,29 @@ k_psi2_small(int64_t rc, int M, int Q, int Mp, int Ms, int nt, int qk, int QC, i
   rv.wrow = wrow;
   rv.hp = HP;
   rv.htile = rc * 64;
-  rv.QC = QC; rv.Qp = Qp; rv.Mp16 = Mp16; rv.VB = VB;
+  rv.QC = QC; rv.Qp = Qp; rv.Mp16 = Mp16; rv.VB = VB; rv.vr = VR;
   rv.init_barriers(tid);
   for (int idx = tid; idx < Mp16 * Qp; idx += blockDim.x) {
     const int m = idx / Qp, c = idx - m * Qp;
     sZ[m * RS + c] = c < Q ? Zt[(size_t)m * RSz + c] : ((c == Qp - 1 && m < M) ? 1.0 : 0.0);   // last column: ones (lambda)
   }
   if constexpr (BWD)
-    for (int idx = tid; idx < 2 * 4 * PS_LAM; idx += blockDim.x) sLam[idx] = 0.0;   // (slot, strip) pairs without a job stay 0
+    for (int idx = tid; idx < NBUF * 4 * PS_LAM; idx += blockDim.x) sLam[idx] = 0.0;   // (slot, strip) pairs without a job stay 0
 
   // this warp's supertiles
   const int ns = sc.ns[wid];
-  int su[PS_S1], si[PS_S1], sj[PS_S1];
+  int su[S1], si[S1], sj[S1];
 #pragma unroll
-  for (int s = 0; s < PS_S1; ++s) {
+  for (int s = 0; s < S1; ++s) {
     su[s] = s < ns ? sc.su[wid][s] : 0;
     int i = 0, rem = su[s];
     while (rem >= Ms - i) { rem -= Ms - i; ++i; }
     si[s] = i;
     sj[s] = i + rem;
   }
-  double creg[PS_S1][2][2][2], pacc[PS_S1][2][2][2];
+  double creg[S1][2][2][2], pacc[S1][2][2][2];
 #pragma unroll
-  for (int s = 0; s < PS_S1; ++s)
+  for (int s = 0; s < S1; ++s)
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -205,10 +212,10 @@ k_psi2_small(int64_t rc, int M, int Q, int Mp, int Ms, int nt, int qk, int QC, i
   // lambda_n, W_n of a finished row: fixed-order sums of the partials
   const int njobs = sc.njobs, kslots = sc.kslots;
   auto flush_row = [&](int64_t n) {
-    const int par = (int)(n & 1);
+    const int par = NBUF == 2 ? (int)(n & 1) : 0;
     if (tid < Qp) {
       if (tid < QC) {
-        const double* p = sW + par * PS_JOBS_OF(QT) * Qp + tid;
+        const double* p = sW + par * JOBS * Qp + tid;
         double s = 0.0;
         for (int jb = 0; jb < njobs; ++jb) s += p[jb * Qp];
         Wq[n * QC + tid] = s;
@@ -230,10 +237,10 @@ k_psi2_small(int64_t rc, int M, int Q, int Mp, int Ms, int nt, int qk, int QC, i
   for (int64_t n = r0; n < r1; ++n) {
     const double* v = rv.row(n - r0);
     const double* H = v + Qp;
-    double* Lb = sL + (n & 1) * NS * PS_ST;
+    double* Lb = sL + (NBUF == 2 ? (int)(n & 1) : 0) * NS * PS_ST;
     // ------------------------------------------------------------------ stage 1 + exp (+ L)
 #pragma unroll
-    for (int s = 0; s < PS_S1; ++s) {
+    for (int s = 0; s < S1; ++s) {
       if (s < ns) {
         double acc[2][2][2];
         const int mi = 16 * si[s] + g, mj = 16 * sj[s] + 2 * t;
@@ -291,23 +298,24 @@ k_psi2_small(int64_t rc, int M, int Q, int Mp, int Ms, int nt, int qk, int QC, i
     if constexpr (!BWD) {
       // the ring slot of this batch is recycled once every thread has consumed its last row
       const int64_t idx = n - r0;
-      if (idx % PS_VR == PS_VR - 1 && n + 1 < r1) {
+      if (idx % VR == VR - 1 && n + 1 < r1) {
         __syncthreads();
         if (tid == 0) rv.refill(idx + 1);
       }
     } else {
       __syncthreads();                                // L_n complete; every thread has finished row n - 1
       if (tid == 0) rv.refill(n - r0);
-      if (n > r0) flush_row(n - 1);
+      if constexpr (NBUF == 2)
+        if (n > r0) flush_row(n - 1);
       // ---------------------------------------------------------------- stage 2: T = L Z' by jobs
-      const int par = (int)(n & 1);
+      const int par = NBUF == 2 ? (int)(n & 1) : 0;
 #pragma unroll
       for (int jj = 0; jj < JMAX; ++jj) {
         if (jj < nj) {
           const int jb = sc.jw[wid][jj];
           const int sp = sc.jsp[jb], kb = sc.jkb[jb], ke = sc.jke[jb];   // k-steps [kb, ke): k-step 4 sk + kk = columns 16 sk + 4 kk ...
           const bool two = 16 * sp + 8 < M8;          // the strip's second 8 rows are not all padding
-          double* myW = sW + (par * PS_JOBS_OF(QT) + jb) * Qp;
+          double* myW = sW + (par * JOBS + jb) * Qp;
           // Q > 23: the stage-2 columns go in two halves of QH tiles (registers hold one half of T at a time)
 #pragma unroll
           for (int h = 0; h < NH; ++h) {
@@ -400,12 +408,18 @@ k_psi2_small(int64_t rc, int M, int Q, int Mp, int Ms, int nt, int qk, int QC, i
           }
         }
       }
+      if constexpr (NBUF == 1) {
+        __syncthreads();                              // L_n consumed (stage 1 of row n + 1 may overwrite it), partials complete
+        flush_row(n);
+      }
     }
   }
 
   if constexpr (BWD) {
-    __syncthreads();                                  // partials of the last row complete
-    if (r1 > r0) flush_row(r1 - 1);
+    if constexpr (NBUF == 2) {
+      __syncthreads();                                // partials of the last row complete
+      if (r1 > r0) flush_row(r1 - 1);
+    }
 #pragma unroll
     for (int jj = 0; jj < JMAX; ++jj) {
       if (jj < nj) {
@@ -425,7 +439,7 @@ k_psi2_small(int64_t rc, int M, int Q, int Mp, int Ms, int nt, int qk, int QC, i
   if constexpr (FWD) {
     double* out = P2s + (size_t)blockIdx.x * Mp16 * Mp16;
 #pragma unroll
-    for (int s = 0; s < PS_S1; ++s)
+    for (int s = 0; s < S1; ++s)
       if (s < ns) {
         const bool offd = si[s] != sj[s];
 #pragma unroll

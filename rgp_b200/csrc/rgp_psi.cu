@@ -853,19 +853,24 @@ int rgp_psi_kernel_times(rgp_psi_handle_t h, int cap, const char** names, double
 }
 
 int rgp_psi_small_schedule(int M, int Q, int ks, int backward, signed char* out, int out_bytes) {
-  static_assert(sizeof(fast::SmallSched) == 226, "layout documented in rgp_psi.h");
-  if (!out || out_bytes < (int)sizeof(fast::SmallSched))
-    return set_error(RGP_PSI_ERR_INVALID, "small_schedule: out must hold %d bytes", (int)sizeof(fast::SmallSched));
-  if (M < 1 || Q < 1 || Q > RGP_PSI_MAX_Q || !(ks == 0 || ks == 1 || ks == 2 || ks == 4))
-    return set_error(RGP_PSI_ERR_INVALID, "small_schedule: bad shape or k split");
+  static_assert(sizeof(fast::SmallSched) == 258, "layout documented in rgp_psi.h");
+  if (!out || out_bytes < (int)sizeof(fast::SmallSched) + 4)
+    return set_error(RGP_PSI_ERR_INVALID, "small_schedule: out must hold %d bytes", (int)sizeof(fast::SmallSched) + 4);
+  if (M < 1 || Q < 1 || Q > RGP_PSI_MAX_Q || !(ks == 0 || ks == 1 || ks == 2 || ks == 4) || backward < 0 || backward > 2)
+    return set_error(RGP_PSI_ERR_INVALID, "small_schedule: bad shape, k split or pass");
   rgp_psi_ctx tmp;
   tmp.small_m = 1;
   tmp.small_ks = ks;
   const fast::Shape s = fast::make_shape(&tmp, 1, M, Q);
   const fast::SmallPlan p = fast::small_plan(&tmp, s);
   if (!p.ok) return set_error(RGP_PSI_ERR_INVALID, "small_schedule: M=%d Q=%d is served by the block kernels", M, Q);
-  memcpy(out, backward ? &p.bwd : &p.fwd, sizeof(fast::SmallSched));
-  return (int)sizeof(fast::SmallSched);
+  const fast::SmallVariant& v = backward == 0 ? p.fwd : (backward == 1 ? p.bwd : p.fused);
+  memcpy(out, &v.sched, sizeof(fast::SmallSched));
+  out[258] = (signed char)v.warps;
+  out[259] = (signed char)v.s1;
+  out[260] = (signed char)v.nbuf;
+  out[261] = (signed char)v.JMAX;
+  return (int)sizeof(fast::SmallSched) + 4;
 }
 
 int rgp_psi_fp64_peak(rgp_psi_handle_t h, void* stream, int reps, double* tflops_out) {

@@ -16,13 +16,15 @@ from rgp_b200._lib import load
 
 
 def schedule(M, Q, ks=0, backward=1):
-    buf = C.create_string_buffer(226)
-    n = load().rgp_psi_small_schedule(M, Q, ks, backward, buf, 226)
+    """backward: 0 forward only, 1 backward only, 2 backward + Psi2 (fused)."""
+    buf = C.create_string_buffer(262)
+    n = load().rgp_psi_small_schedule(M, Q, ks, backward, buf, 262)
     if n < 0:
         return None
     a = np.frombuffer(buf.raw, dtype=np.int8).astype(int)
-    return dict(ns=a[0:16], su=a[16:48].reshape(16, 2), nj=a[48:64], jw=a[64:96].reshape(16, 2), njobs=a[96],
-                kslots=a[97], jsp=a[98:130], jkb=a[130:162], jke=a[162:194], jslot=a[194:226])
+    return dict(ns=a[0:16], su=a[16:80].reshape(16, 4), nj=a[80:96], jw=a[96:128].reshape(16, 2), njobs=a[128],
+                kslots=a[129], jsp=a[130:162], jkb=a[162:194], jke=a[194:226], jslot=a[226:258],
+                warps=a[258], s1=a[259], nbuf=a[260], jmax=a[261])
 
 
 def qtiles(Q):
@@ -40,14 +42,21 @@ SHAPES = [(1, 1), (7, 3), (16, 8), (17, 9), (33, 3), (48, 23), (50, 20), (64, 16
 def test_schedule_covers_every_supertile_and_k_step_once(M, Q, ks):
     Ms = (M + 15) // 16
     NS = Ms * (Ms + 1) // 2
-    for backward in (0, 1):
+    for backward in (0, 1, 2):
         sc = schedule(M, Q, ks, backward)
         assert sc is not None
+        W = sc["warps"]
+        assert W in (8, 16) and sc["s1"] in (2, 4) and sc["nbuf"] in (1, 2)
+        assert (sc["ns"][W:] == 0).all() and (sc["nj"][W:] == 0).all()     # only the CTA's warps get work
         tiles = sorted(int(sc["su"][w, s]) for w in range(16) for s in range(sc["ns"][w]))
         assert tiles == list(range(NS))                       # every supertile exactly once
-        assert sc["ns"].max() <= 2
-        if Q > 23:
-            assert sc["nj"].max() <= 1 and sc["njobs"] <= 16      # wide Q: one job per warp
+        assert sc["ns"].max() <= sc["s1"] and sc["nj"].max() <= sc["jmax"]
+        if backward == 0:
+            assert W == 8 and sc["s1"] == 4                    # forward only: 8-warp CTAs, two per SM
+        if Q > 23 or W == 8:
+            assert sc["nj"].max() <= 1 and sc["njobs"] <= 16      # wide Q / 8-warp CTAs: one job per warp
+        if sc["nbuf"] == 1:
+            assert backward == 1 and W == 8 and Q <= 23 and M > 80   # single-buffered L: backward-only pass, M = 81 ... 112
         if not backward:
             assert sc["njobs"] == 0 and sc["nj"].sum() == 0
             continue
@@ -78,7 +87,7 @@ def test_schedule_covers_every_supertile_and_k_step_once(M, Q, ks):
             for jj in range(sc["nj"][w]):
                 j = sc["jw"][w, jj]
                 load4[w % 4] += (sc["jke"][j] - sc["jkb"][j]) * (2 if 16 * sc["jsp"][j] + 8 < M8 else 1) * qtiles(Q)
-        if Ms >= 4:
+        if Ms >= 4 and W == 16:
             assert load4.max() <= 1.25 * load4.mean(), load4
 
 
