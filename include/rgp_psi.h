@@ -81,7 +81,7 @@ int rgp_psi_destroy(rgp_psi_handle_t h);
  * where one CTA holds the whole pair matrix of a row: 0 = never, 1 = whenever the shape fits, 2 (default) =
  * when they also save work against the 64 x 64 block kernels), "small_ks" (their stage-2 k split: 0 =
  * default, or 1 / 2 / 4), "small_warps" (their CTA size: 0 = default, 16 = 16 warps and one CTA per SM, 8 = 8 warps
- * and two CTAs per SM where that fits, M <= 80), "profile" (1 = record a CUDA-event pair around every kernel
+ * and two CTAs per SM where that fits, M <= 64), "profile" (1 = record a CUDA-event pair around every kernel
  * launch).  Experiment knobs that change results or occupancy ("debug_skip", "fwd_smem_pad") exist only
  * in libraries compiled with -DRGP_DEBUG. */
 int rgp_psi_set_option(rgp_psi_handle_t h, const char* key, int64_t value);

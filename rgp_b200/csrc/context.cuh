@@ -42,7 +42,7 @@ struct rgp_psi_ctx {
   int bwd_pipe = 2;       // Psi2 backward kernel: 0 row-at-a-time, 1 software-pipelined (psi2_bwdp.cuh), 2 (default) = the faster of the two per pass type
   int small_m = 2;        // small-inducing-set kernels (psi2_small.cuh): 0 never, 1 whenever the shape fits, 2 (default) when they also save work
   int small_ks = 0;       // their stage-2 k split: 0 = default, or 1 / 2 / 4
-  int small_warps = 0;    // their CTA size: 0 / 16 = 16 warps, one CTA per SM; 8 = 8 warps, two CTAs per SM, where that fits (M <= 80)
+  int small_warps = 0;    // their CTA size: 0 / 16 = 16 warps, one CTA per SM; 8 = 8 warps, two CTAs per SM, where that fits (M <= 64; the default there)
   int debug_skip = 0;     // timing experiments only, settable in RGP_DEBUG builds; always 0 in production
   int fwd_smem_pad = 0;   // tuning knob (RGP_DEBUG builds): extra dynamic smem for k_psi2_fwd (forces 1 CTA/SM)
   // device workspace arena (grow-only) and a bump pointer valid for one call

@@ -44,15 +44,19 @@ static int init_qc() {
 template <int QT>
 static int init_small() {
   constexpr int fwd = small_smem_doubles(PS_MS_MAX, QT, false) * 8, bwd = small_smem_doubles(PS_MS_MAX, QT, true) * 8;
-  RGP_CUDA(cudaFuncSetAttribute((k_psi2_small<QT, 0, 1, 4, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, fwd));
+  RGP_CUDA(cudaFuncSetAttribute((k_psi2_small<QT, 0, 1, 2, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, fwd));
   RGP_CUDA(cudaFuncSetAttribute((k_psi2_small<QT, 1, 1, 2, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, bwd));
   RGP_CUDA(cudaFuncSetAttribute((k_psi2_small<QT, 2, 1, 2, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, bwd));
-  if constexpr (QT <= 3) {     // two jobs per warp and the single-buffer variant exist for Q <= 23 only
+  if constexpr (QT <= 3) {     // two jobs per warp exist for Q <= 23 only
     RGP_CUDA(cudaFuncSetAttribute((k_psi2_small<QT, 1, 2, 2, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, bwd));
     RGP_CUDA(cudaFuncSetAttribute((k_psi2_small<QT, 2, 2, 2, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, bwd));
+  }
+#ifdef RGP_DEBUG
+  RGP_CUDA(cudaFuncSetAttribute((k_psi2_small<QT, 0, 1, 4, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, fwd));
+  if constexpr (QT <= 3)
     RGP_CUDA(cudaFuncSetAttribute((k_psi2_small<QT, 1, 1, 4, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   small_smem_doubles(PS_MS_MAX, QT, true, 1) * 8));
-  }
+#endif
   return 0;
 }
 
@@ -358,23 +362,24 @@ static SmallPlan small_plan(const rgp_psi_ctx* h, const Shape& s) {
   p.QT = QT;
   // Variants (measured in profiles/small_ab_r02.jsonl; option small_warps = 16 / 8 forces one family for A/B runs):
   //  * 16 warps, one CTA per SM, L double-buffered (one barrier per row): serves everything;
-  //  * 8 warps, two CTAs per SM with independent barriers, L double-buffered: when two CTAs fit (M <= 64 ... 80);
-  //  * 8 warps, two CTAs per SM, L single-buffered (two barriers per row, the other CTA fills the gaps): backward-only
-  //    pass at Q <= 23 when even the single buffer is what lets two CTAs fit (M = 81 ... 112);
-  //  * forward only (no L): always 8 warps, two CTAs per SM.
+  //  * 8 warps, two CTAs per SM with independent barriers (one CTA's stage 2 overlaps the other's stage 1), when two CTAs
+  //    fit in shared memory (used for M <= 64, where it was measured): backward 5.02 -> 4.00 ms at (50, 20),
+  //    3.21 -> 2.33 ms at (33, 20), forward 1.89 -> 1.61 / 1.68 -> 1.10 ms;
+  //  * measured and NOT used (experiment builds only, small_warps = 8): 8-warp CTAs with 4 supertile slots per warp for
+  //    M = 81 ... 112 - forward 4.33 -> 4.63 ms, and a single-buffered L with a second barrier per row so that two such
+  //    CTAs fit - backward 10.30 -> 12.10 ms at (100, 20).
   const int want = h->small_warps;
   const int half_sm = 113 * 1024;
   auto make = [&](SmallVariant* v, int mode) -> bool {
     const bool bwd = mode != 0;
     v->warps = PS_WARPS; v->s1 = 2; v->nbuf = 2;
-    if (want != 16) {
+    if (want != 16 && Ms <= 4 && small_smem_doubles(Ms, QT, bwd, 2) * 8 <= half_sm) v->warps = 8;   // measured at M = 33 ... 64
+#ifdef RGP_DEBUG
+    if (want == 8 && v->warps == PS_WARPS) {
       if (mode == 0) { v->warps = 8; v->s1 = 4; }
-      else if (Ms <= 5 && small_smem_doubles(Ms, QT, true, 2) * 8 <= half_sm) { v->warps = 8; v->s1 = 2; }
-      else if (mode == 1 && QT <= 3 && small_smem_doubles(Ms, QT, true, 1) * 8 <= half_sm && (want == 8 || Ms >= 6)) {
-        v->warps = 8; v->s1 = 4; v->nbuf = 1;
-      }
+      else if (mode == 1 && QT <= 3 && small_smem_doubles(Ms, QT, true, 1) * 8 <= half_sm) { v->warps = 8; v->s1 = 4; v->nbuf = 1; }
     }
-    if (Ms * (Ms + 1) / 2 > v->s1 * v->warps) { v->warps = PS_WARPS; v->s1 = 2; v->nbuf = 2; }
+#endif
     const int jmax_allowed = (QT > 3 || v->warps == 8) ? 1 : 2;     // one job per warp for wide Q and in the 8-warp CTAs
     v->KS = h->small_ks > 0 ? h->small_ks : (Ms >= 5 ? 2 : 4);      // ~13 ... 16 jobs per row with 16 warps
     while (v->KS > 1 && Ms * v->KS > jmax_allowed * v->warps) v->KS /= 2;
@@ -395,10 +400,13 @@ static int launch_small_qt(rgp_psi_ctx* h, cudaStream_t st, const Shape& s, cons
   const SmallVariant& v = MODE == 0 ? p.fwd : (MODE == 1 ? p.bwd : p.fused);
   const int smem = small_smem_doubles(p.Ms, QT, MODE != 0, v.nbuf) * 8;
 #define RGP_SMALL_ARGS rows, s.M, s.Q, s.Mp, p.Ms, s.nt, s.qk, s.QC, s.RS, v.sched, Zt, Ct, w, HP, lam, Wq, ACCp, P2s
-  if constexpr (MODE == 0) {
-    RGP_LAUNCH(h, st, name, (k_psi2_small<QT, 0, 1, 4, 2>), Rs, 32 * v.warps, smem, RGP_SMALL_ARGS);
-  } else if (v.nbuf == 1) {
-    if constexpr (MODE == 1 && QT <= 3) RGP_LAUNCH(h, st, name, (k_psi2_small<QT, 1, 1, 4, 1>), Rs, 32 * v.warps, smem, RGP_SMALL_ARGS);
+  if (v.s1 == 4) {
+#ifdef RGP_DEBUG
+    if constexpr (MODE == 0) RGP_LAUNCH(h, st, name, (k_psi2_small<QT, 0, 1, 4, 2>), Rs, 32 * v.warps, smem, RGP_SMALL_ARGS);
+    else if constexpr (MODE == 1 && QT <= 3) RGP_LAUNCH(h, st, name, (k_psi2_small<QT, 1, 1, 4, 1>), Rs, 32 * v.warps, smem, RGP_SMALL_ARGS);
+#endif
+  } else if constexpr (MODE == 0) {
+    RGP_LAUNCH(h, st, name, (k_psi2_small<QT, 0, 1, 2, 2>), Rs, 32 * v.warps, smem, RGP_SMALL_ARGS);
   } else if (v.JMAX == 1 || QT > 3) {
     RGP_LAUNCH(h, st, name, (k_psi2_small<QT, MODE, 1, 2, 2>), Rs, 32 * v.warps, smem, RGP_SMALL_ARGS);
   } else if constexpr (QT <= 3) {

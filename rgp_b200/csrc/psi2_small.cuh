@@ -20,9 +20,9 @@
 //             lambda_n, W_n are written once with plain stores, in a fixed order (deterministic, no atomics).
 //
 // Which warp computes which supertiles and jobs is a small table made on the host (SmallSched, fast_path.cuh): it
-// balances the FP64-pipe load per SM sub-partition (warp w runs on sub-partition w % 4).  With at most 5 super rows
-// (M <= 80) the CTA has 8 warps instead of 16 and two CTAs share an SM: their barriers are independent, so one CTA's
-// stage 2 overlaps the other's stage 1.
+// balances the FP64-pipe load per SM sub-partition (warp w runs on sub-partition w % 4).  Where two CTAs fit in shared
+// memory (M <= 64) the CTA has 8 warps instead of 16 and two CTAs share
+// an SM: their barriers are independent, so one CTA's stage 2 overlaps the other's stage 1.
 // The per-row vectors (ws[Qp], H[Mp16]) arrive by TMA bulk copies into a two-slot ring (SmallRowStage), as in the
 // block kernels.  The forward-only kernel needs a barrier only when a ring slot is recycled (every 4 rows).
 #pragma once
@@ -125,9 +125,10 @@ RGP_DEVINL int st_index(int lo, int hi, int Ms) { return lo * Ms - lo * (lo - 1)
 //   ACCp[cta * kslots + slot][Mp][QC]          sum_n ws (L_n Z') over this CTA's rows and one k range (plain stores
 //                                              where a job exists; the buffer is zeroed before the launch)
 //   P2s [cta][Mp16][Mp16]                      sum_n p over this CTA's rows (MODE 0 / 2), full symmetric
-// S1: supertile slots per warp (2 with 16 warps, 4 with 8 warps).  NBUF: buffers of L.  2 = double-buffered by row parity,
-// one barrier per row.  1 = single buffer and a second barrier per row (L consumed), half the shared memory: two 8-warp
-// CTAs share an SM at M <= 112 and fill each other's barrier and phase gaps (backward-only pass, Q <= 23).
+// S1: supertile slots per warp.  NBUF: buffers of L - 2 = double-buffered by row parity, one barrier per row.
+// The product uses S1 = 2, NBUF = 2.  (S1 = 4 with 8-warp CTAs, and NBUF = 1 = a single buffer with a second barrier per
+// row so that two 8-warp CTAs fit at M = 81 ... 112, are measured negative results: forward 4.33 -> 4.63 ms, backward
+// 10.30 -> 12.10 ms at M = 100, Q = 20; they are instantiated in -DRGP_DEBUG experiment builds only.)
 template <int QT, int MODE, int JMAX, int S1 = 2, int NBUF = 2>
 __global__ void __launch_bounds__(PS_THREADS, 1)
 k_psi2_small(int64_t rc, int M, int Q, int Mp, int Ms, int nt, int qk, int QC, int RSz,

@@ -51,12 +51,11 @@ def test_schedule_covers_every_supertile_and_k_step_once(M, Q, ks):
         tiles = sorted(int(sc["su"][w, s]) for w in range(16) for s in range(sc["ns"][w]))
         assert tiles == list(range(NS))                       # every supertile exactly once
         assert sc["ns"].max() <= sc["s1"] and sc["nj"].max() <= sc["jmax"]
-        if backward == 0:
-            assert W == 8 and sc["s1"] == 4                    # forward only: 8-warp CTAs, two per SM
+        assert sc["s1"] == 2 and sc["nbuf"] == 2               # the product variants (others: experiment builds only)
+        if W == 8:
+            assert NS <= 16                                    # 8-warp CTAs (two per SM): supertiles fit 2 slots x 8 warps
         if Q > 23 or W == 8:
             assert sc["nj"].max() <= 1 and sc["njobs"] <= 16      # wide Q / 8-warp CTAs: one job per warp
-        if sc["nbuf"] == 1:
-            assert backward == 1 and W == 8 and Q <= 23 and M > 80   # single-buffered L: backward-only pass, M = 81 ... 112
         if not backward:
             assert sc["njobs"] == 0 and sc["nj"].sum() == 0
             continue
