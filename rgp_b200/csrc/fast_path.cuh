@@ -427,8 +427,10 @@ static int launch_small(rgp_psi_ctx* h, cudaStream_t st, const Shape& s, const S
   return launch_small_qt<6, MODE>(h, st, s, p, rows, Rs, Zt, Ct, w, HP, lam, Wq, ACCp, P2s);
 }
 
+// CTAs of a small-kernel launch: one (16 warps) or two (8 warps) per SM, and at least 4 rows per CTA so that the
+// prologue (Z' tile, C fragments, exp table) is amortised at the N ~ 500 of the system-identification models
 static inline int small_grid(const rgp_psi_ctx* h, const SmallVariant& v, int64_t rows) {
-  return (int)std::max<int64_t>(1, std::min<int64_t>((v.warps == 8 ? 2 : 1) * h->sm_count, rows));
+  return (int)std::max<int64_t>(1, std::min<int64_t>((v.warps == 8 ? 2 : 1) * h->sm_count, (rows + 3) / 4));
 }
 
 // lam[0] += sum_{g>=1} lam[g]  (and the same for Wq); only launched when G > 1
