@@ -1,7 +1,7 @@
 """Tiny runs of every kernel family for compute-sanitizer (memcheck / racecheck / synccheck):
     compute-sanitizer --tool memcheck python tests/tools/sanitize_small.py
 Covers the default fast path (software-pipelined backward kernel with TMA row-vector staging), the
-row-at-a-time backward kernel, the fused pass, the lag-window kernels and the latent-terms kernel; results are checked against the oracle."""
+row-at-a-time backward kernel, the fused pass, the small-inducing-set kernels, the lag-window kernels and the latent-terms kernel; results are checked against the oracle."""
 import os, sys
 import numpy as np
 import torch
@@ -14,12 +14,16 @@ from rgp_b200.lagwindow import LagWindow
 
 t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
 worst = 0.0
-variants = [{}, {"bwd_pipe": 0}, {"bwd_pipe": 1}]
-for opts in variants:
+variants = [{"small_m": 0}, {"small_m": 0, "bwd_pipe": 0}, {"small_m": 0, "bwd_pipe": 1}]
+shapes = [(37, 70, 20), (21, 130, 64), (9, 64, 33)]
+small_shapes = [(37, 100, 20), (21, 50, 20), (19, 100, 40), (5, 33, 7), (300, 112, 23)]   # 16-warp, 8-warp, wide-Q, tiny, > 1 row per CTA
+if os.environ.get("SANITIZE_ONLY_SMALL"):     # only the small-inducing-set kernels (psi2_small.cuh)
+    variants = []
+for opts in variants + [{"small_m": 1}, {"small_m": 1, "small_ks": 4}]:
     dp = DevicePsi(0, impl=1)
     for k, v in opts.items():
         dp.handle.set_option(k, v)
-    for (N, M, Q) in [(37, 70, 20), (21, 130, 64), (9, 64, 33)]:
+    for (N, M, Q) in (small_shapes if opts.get("small_m") == 1 else shapes):
         var, ell, Z, mu, S = make_inputs(N, M, Q, seed=4)
         dL0, dL1, dL2 = make_upstream(N, M)
         of = psi_forward(var, ell, Z, mu, S); ob = psi_backward(dL0, dL1, dL2, var, ell, Z, mu, S)
@@ -30,6 +34,10 @@ for opts in variants:
         errs += [relerr(a.cpu().numpy(), b) for a, b in zip(out, ob)] + [relerr(a.cpu().numpy(), b) for a, b in zip(fo, ob)]
         worst = max(worst, max(errs))
         print(opts, (N, M, Q), "max rel err %.2e" % max(errs), flush=True)
+if os.environ.get("SANITIZE_ONLY_SMALL"):
+    assert worst < 1e-10, worst
+    print("sanitize_small (small kernels only): all results match the oracle, worst rel err %.2e" % worst)
+    sys.exit(0)
 lw = LagWindow(dp.handle, (9, 6), 3, 2, (9, 7), 2, 3)
 lat, ctl = torch.randn((15, 2), dtype=torch.float64, device="cuda"), torch.randn((16, 3), dtype=torch.float64, device="cuda")
 X = lw.gather(lat, ctl)
