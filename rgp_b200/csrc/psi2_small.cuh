@@ -5,7 +5,7 @@
 // The 64 x 64 block kernels of psi2_kernels.cuh pay for padding there: M = 100 is computed as 128 (136 8x8 tiles
 // of the pair matrix instead of 91), Q = 20 as 32 stage-2 columns, lambda / W go through 3 block passes of
 // red.global.add, and 8 warps (2 per scheduler) cannot hide the DMMA issue latency of the short k loops.  Here ONE
-// CTA of 16 warps holds the whole problem of a row:
+// CTA (16 warps; 8 warps and two CTAs per SM at M <= 64) holds the whole problem of a row:
 //
 //   Z' [Mp16][Qp + 4] in shared memory (Mp16 = M rounded up to 16, Qp = 8 (Q / 8 + 1): at least one spare column,
 //   the last one holds ONES so that T[:, Qp - 1] = L 1 = lambda comes out of the stage-2 MMAs for free) and the UPPER
@@ -21,8 +21,8 @@
 //
 // Which warp computes which supertiles and jobs is a small table made on the host (SmallSched, fast_path.cuh): it
 // balances the FP64-pipe load per SM sub-partition (warp w runs on sub-partition w % 4).  Where two CTAs fit in shared
-// memory (M <= 64) the CTA has 8 warps instead of 16 and two CTAs share
-// an SM: their barriers are independent, so one CTA's stage 2 overlaps the other's stage 1.
+// memory (M <= 64) the CTA has 8 warps instead of 16 and two CTAs share an SM: their barriers are independent, so one
+// CTA's stage 2 overlaps the other's stage 1.
 // The per-row vectors (ws[Qp], H[Mp16]) arrive by TMA bulk copies into a two-slot ring (SmallRowStage), as in the
 // block kernels.  The forward-only kernel needs a barrier only when a ring slot is recycled (every 4 rows).
 #pragma once
@@ -36,14 +36,13 @@ namespace fast {
 constexpr int PS_THREADS = 512;
 constexpr int PS_WARPS = PS_THREADS / 32;
 constexpr int PS_MS_MAX = 7;      // 16-row super rows: M <= 112
-constexpr int PS_S1 = 4;          // supertile slots per warp in the work table (kernels use 2 with 16 warps, 4 with 8 warps)
+constexpr int PS_S1 = 4;          // supertile slots per warp in the work table (the product kernels use 2; 4 in experiment builds)
 constexpr int PS_JOBS = 32;       // job list length
 // jobs per row that get a partial slot (wide Q and the single-buffer variant: one per warp)
 __host__ __device__ constexpr int PS_JOBS_OF(int QT, int nbuf = 2) { return (QT > 3 || nbuf == 1) ? 16 : 32; }
 // rows per TMA batch (the single-buffer variant has two CTAs per SM and half the ring)
 __host__ __device__ constexpr int PS_VR_OF(int nbuf) { return nbuf == 1 ? 2 : 4; }
 constexpr int PS_ST = 320;        // doubles per packed supertile: 16 rows x stride 20
-constexpr int PS_QT_MAX = 6;
 constexpr int PS_LAM = 16 * PS_MS_MAX;   // lambda partials: [parity][k slot <= 4][PS_LAM]
 
 struct SmallSched {
