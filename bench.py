@@ -242,6 +242,49 @@ def parity_check(dp, world, rank, dev):
 
 
 # ------------------------------------------------------------------------ our arm
+def model_shapes(local, peak_tf, rows=1 << 20):
+    """rows/s of forward + backward at the shapes of the reference's models (one GPU, inputs resident, CUDA events,
+    1 warm + 2 timed steps).  Never fails the bench: an error is reported in place of the numbers."""
+    import torch
+    from rgp_b200.device import DevicePsi
+    out = []
+    try:
+        dev = torch.device("cuda", local)
+        dp = DevicePsi(local)
+        f64 = dict(dtype=torch.float64, device=dev)
+        for M, Q in ((100, 20), (100, 40), (50, 20)):
+            g = torch.Generator(device=dev).manual_seed(7)
+            mu = torch.randn((rows, Q), generator=g, **f64)
+            S = torch.rand((rows, Q), generator=g, **f64) * 0.49 + 0.01
+            Z = torch.randn((M, Q), generator=g, **f64)
+            ell = (torch.rand(Q, generator=g, **f64) * 0.7 + 0.7) * Q ** 0.5
+            dL1 = torch.randn((rows, M), generator=g, **f64) / M
+            dL2 = torch.randn((M, M), generator=g, **f64) / (M * M)
+            psi1 = torch.empty((rows, M), **f64)
+            dmu, dS = torch.empty((rows, Q), **f64), torch.empty((rows, Q), **f64)
+
+            def step():
+                dp.forward(mu, S, Z, ell, 1.3, psi1_out=psi1)
+                dp.backward(mu, S, Z, ell, 1.3, -0.5, dL1, dL2, dmu_out=dmu, dS_out=dS)
+            step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step()
+            step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 2
+            rps = rows / (ms * 1e-3)
+            out.append({"M": M, "Q": Q, "rows": rows, "ms_per_step": ms, "rows_per_s": rps,
+                        "frac_of_fp64_peak": rps * flops_row_total(M, Q) / 1e12 / peak_tf if peak_tf else None})
+            del mu, S, dL1, psi1, dmu, dS
+        torch.cuda.empty_cache()
+    except Exception as e:      # informational only
+        out.append({"error": repr(e)})
+    return out
+
+
 def ours(args):
     import numpy as np
     import torch
@@ -377,6 +420,10 @@ def ours(args):
                  "max_rel_diff_dZ_vs_two_phase": float((fo[2] - out[2]).abs().max() / out[2].abs().max()),
                  "note": "rgp_psi_fused_dev: one pass for statistics + gradients (SVI bound); not the headline metric"}
 
+    # Informational: the shapes of the reference's own models (configs 1 - 4: M = 50 ... 100, Q = 10 ... 40), which are
+    # served by the small-inducing-set kernels, at 2^20 rows on this GPU.
+    shapes = model_shapes(local, peak_tf) if (rank == 0 and not args.no_model_shapes) else None
+
     # dominant kernel -> roofline (fp64 CUDA-core pipe; see DESIGN.md "Measurement")
     roof = None
     if ktimes:
@@ -442,7 +489,7 @@ def ours(args):
             "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": cfg, "parity": parity,
             "roofline": roof, "whole_step": whole, "kernel_ms": kshare,
-            "cpu_baseline": cpu, "e2e": e2e, "strong_scaling": other, "fused_svi_pass": fused,
+            "cpu_baseline": cpu, "e2e": e2e, "strong_scaling": other, "fused_svi_pass": fused, "model_shapes": shapes,
             "gpu_launches": launches, "clocks": clocks, "checksum": checksum,
         }
         print(json.dumps(line), flush=True)
@@ -533,6 +580,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--ref-rows", type=int, default=128, help="rows per step of the reference (CPU) arm")
     ap.add_argument("--no-fused", action="store_true", help="skip the informational fused-pass measurement")
+    ap.add_argument("--no-model-shapes", action="store_true", help="skip the informational M = 100 / 50 measurements")
     ap.add_argument("--no-strong", action="store_true", help="skip the informational strong-scaling measurement")
     ap.add_argument("--svi-steps-total", type=int, default=10_000_000, help="svi10m: time steps of the synthetic sequence")
     ap.add_argument("--svi-minibatches", type=int, default=4, help="svi10m: minibatches evaluated (timed)")
