@@ -124,8 +124,9 @@ int rgp_host_digest(const void* data, int64_t nbytes, int threads, uint64_t out[
  *   [128] number of jobs  [129] k slots [130..161] strip of job j        [162..193] first k-step   [194..225] end
  *   k-step   [226..257] accumulator slot
  *   [258] warps per CTA (16: one CTA per SM, 8: two)   [259] supertile slots per warp   [260] buffers of L (2: one
- *   barrier per row, 1: two)   [261] job slots per warp
- * and returns the number of bytes (262), or -1 (message set) when the small kernels do not serve the shape
+ *   barrier per row, 1: two)   [261] job slots per warp   [262] 1 if the default rule ("small_m" = 2) serves this
+ *   shape with the small kernels, 0 if it leaves it to the block kernels
+ * and returns the number of bytes (263), or -1 (message set) when the small kernels do not serve the shape
  * or `out_bytes` is too small. */
 int rgp_psi_small_schedule(int M, int Q, int ks, int backward, signed char* out, int out_bytes);
 

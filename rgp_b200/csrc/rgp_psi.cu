@@ -854,8 +854,8 @@ int rgp_psi_kernel_times(rgp_psi_handle_t h, int cap, const char** names, double
 
 int rgp_psi_small_schedule(int M, int Q, int ks, int backward, signed char* out, int out_bytes) {
   static_assert(sizeof(fast::SmallSched) == 258, "layout documented in rgp_psi.h");
-  if (!out || out_bytes < (int)sizeof(fast::SmallSched) + 4)
-    return set_error(RGP_PSI_ERR_INVALID, "small_schedule: out must hold %d bytes", (int)sizeof(fast::SmallSched) + 4);
+  if (!out || out_bytes < (int)sizeof(fast::SmallSched) + 5)
+    return set_error(RGP_PSI_ERR_INVALID, "small_schedule: out must hold %d bytes", (int)sizeof(fast::SmallSched) + 5);
   if (M < 1 || Q < 1 || Q > RGP_PSI_MAX_Q || !(ks == 0 || ks == 1 || ks == 2 || ks == 4) || backward < 0 || backward > 2)
     return set_error(RGP_PSI_ERR_INVALID, "small_schedule: bad shape, k split or pass");
   rgp_psi_ctx tmp;
@@ -870,7 +870,9 @@ int rgp_psi_small_schedule(int M, int Q, int ks, int backward, signed char* out,
   out[259] = (signed char)v.s1;
   out[260] = (signed char)v.nbuf;
   out[261] = (signed char)v.JMAX;
-  return (int)sizeof(fast::SmallSched) + 4;
+  tmp.small_m = 2;                                  // would the default rule pick the small kernels for this shape?
+  out[262] = (signed char)(fast::small_plan(&tmp, s).ok ? 1 : 0);
+  return (int)sizeof(fast::SmallSched) + 5;
 }
 
 int rgp_psi_fp64_peak(rgp_psi_handle_t h, void* stream, int reps, double* tflops_out) {

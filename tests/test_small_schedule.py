@@ -17,14 +17,14 @@ from rgp_b200._lib import load
 
 def schedule(M, Q, ks=0, backward=1):
     """backward: 0 forward only, 1 backward only, 2 backward + Psi2 (fused)."""
-    buf = C.create_string_buffer(262)
-    n = load().rgp_psi_small_schedule(M, Q, ks, backward, buf, 262)
+    buf = C.create_string_buffer(263)
+    n = load().rgp_psi_small_schedule(M, Q, ks, backward, buf, 263)
     if n < 0:
         return None
     a = np.frombuffer(buf.raw, dtype=np.int8).astype(int)
     return dict(ns=a[0:16], su=a[16:80].reshape(16, 4), nj=a[80:96], jw=a[96:128].reshape(16, 2), njobs=a[128],
                 kslots=a[129], jsp=a[130:162], jkb=a[162:194], jke=a[194:226], jslot=a[226:258],
-                warps=a[258], s1=a[259], nbuf=a[260], jmax=a[261])
+                warps=a[258], s1=a[259], nbuf=a[260], jmax=a[261], auto=a[262])
 
 
 def qtiles(Q):
@@ -93,6 +93,21 @@ def test_schedule_covers_every_supertile_and_k_step_once(M, Q, ks):
 def test_large_shapes_are_left_to_the_block_kernels():
     assert schedule(113, 20) is None and schedule(100, 48) is None and schedule(512, 64) is None
     assert b"block kernels" in load().rgp_psi_last_error()
+
+
+# (M, Q) -> does the default rule use the small kernels?  Each line is a measurement of profiles/small_ab_r02.jsonl
+# (build "final" / v8): where the small kernels were faster in forward, backward AND fused, the rule must pick them.
+MEASURED = {(100, 20): 1, (100, 10): 1, (100, 40): 1, (112, 23): 1, (112, 46): 1, (80, 20): 1, (33, 20): 1, (50, 20): 1,
+            (100, 7): 1, (100, 30): 1,
+            (64, 16): 0, (50, 40): 0}          # slower in at least two of the three passes
+
+
+def test_default_rule_follows_the_measurements():
+    for (M, Q), want in MEASURED.items():
+        assert schedule(M, Q)["auto"] == want, (M, Q)
+    # CTA size: two 8-warp CTAs per SM where measured (M <= 64), else 16 warps
+    assert schedule(50, 20)["warps"] == 8 and schedule(33, 20, backward=0)["warps"] == 8
+    assert schedule(100, 20)["warps"] == 16 and schedule(80, 20)["warps"] == 16
 
 
 def emulate(M, Q, ks, N, seed=0):
